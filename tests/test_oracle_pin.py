@@ -1,0 +1,163 @@
+"""Pins the plain-C oracle (oracle/t360_oracle.c) before anything is allowed to trust it.
+
+The reference has no tests or golden vectors of its own, so the pins are
+(a) tests/golden/golden.json -- outputs of THE REFERENCE ITSELF run in the build container
+    (oracle/_ref = unmodified reference sources + oracle/shim, driving cv2 4.13.0; generator
+    tests/golden/make_golden.py) -- checked without needing /root/reference at run time;
+(b) live comparison with oracle/_ref and cv2 where those are present.
+"""
+import numpy as np
+import pytest
+
+from oracle import c_oracle as co
+from oracle import ref_harness as rh
+from tests.golden.cases import FULL, SMALL, plane_dims
+
+cv2 = pytest.importorskip("cv2")
+
+
+def _ctx(case):
+    return rh.default_context(**case["ov"])
+
+
+def test_context_abi_size():
+    import ctypes
+    assert ctypes.sizeof(rh.FrameTransformContext) == 112
+    assert rh.FrameTransformContext.interpolation_alg.offset == 28
+    assert rh.FrameTransformContext.kernel_adjust_factor.offset == 108
+
+
+def test_noise_generator_matches_numpy_and_survey():
+    a = co.noise_plane(1920, 960)
+    assert a[0, :8].tolist() == [0, 81, 48, 133, 36, 204, 92, 24]
+    assert rh.sha16(a) == "ff168fc9d025a214"
+    assert np.array_equal(a, rh.noise_plane(1920, 960))
+    assert np.array_equal(co.noise_plane(333, 77, plane=2, frame=5), rh.noise_plane(333, 77, plane=2, frame=5))
+
+
+@pytest.mark.parametrize("name", sorted(SMALL))
+def test_oracle_vs_golden(name, golden):
+    """C oracle end to end (map -> plan -> low-pass -> remap) == the reference's recorded outputs."""
+    case = SMALL[name]
+    ctx = _ctx(case)
+    barrel = ctx.output_layout in (rh.LAYOUT_BARREL, rh.LAYOUT_BARREL_SPLIT)
+    for plane in (0, 1):
+        g = golden["small"][name]["planes"][str(plane)]
+        iw, ih, ow, oh, idx = plane_dims(case, plane)
+        assert g["dims"] == [iw, ih, ow, oh, idx]
+        plan = co.OraclePlan(ctx, iw, ih, ow, oh)
+        assert co.fnv1a64(plan.map) == g["map_fnv"], "geometry differs from the reference"
+        assert plan.nsegs == g["nsegs"]
+        if plan.nsegs:
+            lst = co.plan_as_list(plan.segs, plan.nsegs, plan.taps)
+            rects = np.array([s[:4] for s in lst], np.int32)
+            taps = np.concatenate([np.concatenate([s[4], s[5]]) for s in lst])
+            assert co.fnv1a64(rects) == g["rects_fnv"], "low-pass tile table differs from the reference"
+            assert co.fnv1a64(taps) == g["taps_fnv"], "low-pass kernels differ from the reference"
+        src = co.noise_plane(iw, ih, plane=plane, frame=0)
+        assert rh.sha16(src) == g["src_sha"]
+        out = co.transform_plane(ctx, plan, src, ow, oh, map_index=idx, prefill=7 if barrel else 0)
+        assert out[0, :8].tolist() == g["out_head"]
+        assert int(out.sum(dtype=np.int64)) == g["out_sum"]
+        assert rh.sha16(out) == g["out_sha"], "pixels differ from the reference"
+
+
+@pytest.mark.slow
+@pytest.mark.parametrize("name", ["cfg2", "cfg3"])
+def test_oracle_vs_golden_full_size(name, golden):
+    case = FULL[name]
+    ctx = _ctx(case)
+    g = golden["full"][name]["planes"]["0"]
+    iw, ih, ow, oh, idx = plane_dims(case, 0)
+    plan = co.OraclePlan(ctx, iw, ih, ow, oh)
+    assert co.fnv1a64(plan.map) == g["map_fnv"]
+    out = co.transform_plane(ctx, plan, co.noise_plane(iw, ih), ow, oh)
+    assert rh.sha16(out) == g["out_sha"]
+
+
+@pytest.mark.parametrize("interp", [rh.NEAREST, rh.LINEAR, rh.CUBIC, rh.LANCZOS4])
+def test_remap_arithmetic_vs_cv2(interp):
+    """bit-exact against cv2.remap, BORDER_WRAP, coordinates spilling over every edge."""
+    rng = np.random.default_rng(1234 + interp)
+    src = rng.integers(0, 256, (97, 131), dtype=np.uint8)
+    m = np.empty((300, 400, 2), np.float32)
+    m[..., 0] = rng.uniform(-9, 131 + 9, (300, 400))
+    m[..., 1] = rng.uniform(-9, 97 + 9, (300, 400))
+    m[:50, :, 0] = np.round(m[:50, :, 0] * 2) / 2  # exact .5 ties exercise round-half-even
+    m[:50, :, 1] = np.round(m[:50, :, 1] * 64) / 64
+    want = cv2.remap(src, m, None, interp, borderMode=cv2.BORDER_WRAP)
+    got = co.remap_u8(src, m, interp, 3)
+    assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("interp", [
+    rh.NEAREST,
+    pytest.param(rh.LINEAR, marks=pytest.mark.xfail(
+        reason="cv2 4.13 remapBilinear blends partially-inside pixels on the last row/column under "
+               "BORDER_TRANSPARENT with a renormalised-weights formula that is not restated yet "
+               "(barrel layouts are SURVEY.md 8f rank 4)", strict=False)),
+    rh.CUBIC, rh.LANCZOS4])
+def test_remap_transparent_vs_cv2(interp):
+    rng = np.random.default_rng(99 + interp)
+    src = rng.integers(0, 256, (64, 80), dtype=np.uint8)
+    m = np.empty((120, 150, 2), np.float32)
+    m[..., 0] = rng.uniform(-6, 86, (120, 150))
+    m[..., 1] = rng.uniform(-6, 70, (120, 150))
+    m[10:20, 10:30] = (-1.0, 0.0)  # the reference's "no mapping" marker (cpp:1305-1306)
+    want = np.full((120, 150), 128, np.uint8)
+    cv2.remap(src, m, None, interp, dst=want, borderMode=cv2.BORDER_TRANSPARENT)
+    got = co.remap_u8(src, m, interp, 5, dst=np.full((120, 150), 128, np.uint8))
+    assert np.array_equal(got, want)
+
+
+def test_itab_sums():
+    for interp in (rh.LINEAR, rh.CUBIC, rh.LANCZOS4):
+        t = co.build_itab(interp)
+        assert (t.reshape(1024, -1).astype(np.int32).sum(1) == 32768).all()
+
+
+@pytest.mark.parametrize("sx,sy", [(0.75, 0.75), (1.2, 0.75), (7.2, 0.75), (2.3, 1.6), (14.9, 3.1)])
+def test_sepfilter_arithmetic_vs_cv2(sx, sy):
+    """The FMA model of cv2 4.13's optimized sepFilter2D (see t360_oracle.c): bit-exact on whole planes."""
+    src = co.noise_plane(1024, 384, plane=1, frame=3)
+
+    def gauss(sigma):
+        half = int(np.float32(sigma) * 2)
+        u = np.arange(-half, half + 1)
+        v = np.exp(-(u * u).astype(np.float32) * np.float32(0.5 / (np.float32(sigma) * np.float32(sigma)))).astype(np.float32)
+        return (v / v.sum(dtype=np.float32)).astype(np.float32)
+
+    kx, ky = gauss(sx), gauss(sy)
+    want = cv2.sepFilter2D(src, -1, kx.reshape(1, -1), ky.reshape(1, -1), borderType=cv2.BORDER_REPLICATE)
+    got = co.sepfilter_roi(src, 0, 0, 1024, 384, kx, ky, np.zeros_like(src))
+    assert np.array_equal(got, want)
+    # a tile in the middle of the plane must equal the same window of the whole-plane result (non-isolated ROI)
+    tile = co.sepfilter_roi(src, 300, 100, 240, 128, kx, ky, np.zeros_like(src))
+    assert np.array_equal(tile[100:228, 300:540], want[100:228, 300:540])
+
+
+@pytest.mark.skipif(not rh.ref_available(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("name", ["lp_tiles", "eac_tb_lanczos", "offcenter_adjust", "cube_to_equirect", "barrel"])
+def test_oracle_vs_live_reference(name):
+    """Same comparison as the golden test but against the compiled reference run live (different frame seed)."""
+    case = SMALL[name]
+    ctx = _ctx(case)
+    ref = rh.RefTransform(ctx)
+    for plane in (0, 2):
+        iw, ih, ow, oh, idx = plane_dims(case, plane)
+        assert ref.generate_map(iw, ih, ow, oh, idx)
+        plan = co.OraclePlan(ctx, iw, ih, ow, oh)
+        assert np.array_equal(plan.map.view(np.uint32), ref.map(idx).view(np.uint32))
+        rs = ref.segments(idx)
+        mine = co.plan_as_list(plan.segs, plan.nsegs, plan.taps) if plan.nsegs else []
+        assert len(rs) == len(mine)
+        for a, b in zip(rs, mine):
+            assert a[:4] == b[:4]
+            assert np.array_equal(a[4].view(np.uint32), b[4].view(np.uint32))
+            assert np.array_equal(a[5].view(np.uint32), b[5].view(np.uint32))
+        src = co.noise_plane(iw, ih, plane=plane, frame=17)
+        barrel = ctx.output_layout in (rh.LAYOUT_BARREL, rh.LAYOUT_BARREL_SPLIT)
+        want = ref.transform_plane(src, ow, oh, idx, image_plane=plane, prefill=9 if barrel else 0)
+        got = co.transform_plane(ctx, plan, src, ow, oh, map_index=idx, prefill=9 if barrel else 0)
+        assert np.array_equal(got, want)
+    ref.close()
