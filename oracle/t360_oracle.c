@@ -538,7 +538,13 @@ void t360o_build_itab(int interp, int16_t* itab) {
           isum += it[k1 * k + k2] = sat_i16_round(v * 32768.0f);
         }
       }
-      if (isum != 32768 && k > 2) { /* for k == 2 the products are exact and the sum never drifts */
+      if (isum != 32768 && k == 2) {
+        /* only phase (0,0): 1.0*32768 saturates to 32767.  OpenCV's fix-up scans [1,3)x[1,3), i.e. entry
+         * (1,1) of this phase and three not-yet-written entries of the next one (static zeros), so the
+         * missing 1 lands on entry (1,1).  The interpolated value is unaffected (|b-a| < 16384). */
+        it[3] = (int16_t)(it[3] - (isum - 32768));
+      }
+      if (isum != 32768 && k > 2) {
         int diff = isum - 32768, h = k / 2, Mk1 = h, Mk2 = h, mk1 = h, mk2 = h;
         for (int k1 = h; k1 < h + 2; k1++)
           for (int k2 = h; k2 < h + 2; k2++) {
