@@ -1,0 +1,67 @@
+/* transform360-b200: extensions beyond the reference's four-function C-ABI.
+ *
+ * Nothing here is needed by a drop-in caller (see Transform360/VideoFrameTransformHandler.h).
+ * These entry points exist for (1) zero-copy / asynchronous callers that already hold frames in
+ * device memory (e.g. an AV_PIX_FMT_CUDA filter, bench.py's device-resident leg), and (2) tests that
+ * inspect the host-side plan without a GPU.  Plain C, plain pointers and sizes, no torch types.
+ */
+#ifndef TRANSFORM360_B200_EXT_H
+#define TRANSFORM360_B200_EXT_H
+
+#include "Transform360/VideoFrameTransformHandler.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- host-only plan inspection (never touches CUDA) ------------------------------------------ */
+typedef struct T360HostPlan T360HostPlan;
+
+/* Runs the host planner (the re-implementation of the reference's generateMapForPlane, cpp:504-576)
+ * for one plane and keeps the result in host memory. */
+T360HostPlan* T360B200_hostPlanCreate(const FrameTransformContext* ctx, int inputWidth, int inputHeight,
+                                      int outputWidth, int outputHeight);
+void T360B200_hostPlanDestroy(T360HostPlan* plan);
+/* info[0..5] = mapWidth, mapHeight, numSegments, numTaps, kernelSizeOfInterpolation, numTileJobs */
+int T360B200_hostPlanInfo(const T360HostPlan* plan, int info[6]);
+/* float32 [mapHeight][mapWidth][2]: the reference's warp map values (cpp:544-545) */
+const float* T360B200_hostPlanMap(const T360HostPlan* plan);
+/* int32 [mapHeight][mapWidth][2]: what the kernels consume.  word0 = first tap column (before wrapping),
+ * word1 = (first tap row << 10) | phase, phase = (fracY32 << 5) | fracX32 (0 for nearest). */
+const int32_t* T360B200_hostPlanSamples(const T360HostPlan* plan);
+/* low-pass segment i in the reference's order: rect = left, top, width, height; taps = kx then ky */
+int T360B200_hostPlanSegment(const T360HostPlan* plan, int i, int rect[4], int numTaps[2], const float** kx,
+                             const float** ky);
+/* OpenCV-compatible fixed-point interpolation table: int16 [1024][k][k]; returns k (0 if unsupported) */
+int T360B200_remapTable(int interpolationAlg, const int16_t** table);
+
+/* ---- device-resident / asynchronous entry points ----------------------------------------------- */
+/* Same contract as VideoFrameTransform_transformFramePlane, but both planes are CUDA device pointers,
+ * the work is enqueued on `cudaStream` (a cudaStream_t; NULL = the transform's own stream) and the call
+ * returns without synchronising.  Returns 1 if everything was enqueued. */
+int T360B200_transformFramePlaneAsync(VideoFrameTransform* transform, const uint8_t* deviceInput,
+                                      uint8_t* deviceOutput, int inputWidth, int inputHeight, int inputPitch,
+                                      int outputWidth, int outputHeight, int outputPitch,
+                                      int transformMatPlaneIndex, void* cudaStream);
+/* Runs only the segmented low-pass stage (reference filterPlane, cpp:621-704) device to device. */
+int T360B200_lowPassPlaneAsync(VideoFrameTransform* transform, const uint8_t* deviceInput, uint8_t* deviceOutput,
+                               int width, int height, int inputPitch, int outputPitch,
+                               int transformMatPlaneIndex, void* cudaStream);
+/* Blocks until everything enqueued on the transform's own stream has finished; 1 = ok. */
+int T360B200_synchronize(VideoFrameTransform* transform);
+/* The transform's own stream (cudaStream_t) */
+void* T360B200_stream(VideoFrameTransform* transform);
+
+/* ---- bookkeeping ---------------------------------------------------------------------------------- */
+/* Number of this library's kernels launched by the calling process so far. */
+unsigned long long T360B200_kernelLaunchCount(void);
+/* Bytes of device memory held by the plan of one index (sampling plan + low-pass tables). */
+unsigned long long T360B200_planDeviceBytes(VideoFrameTransform* transform, int transformMatPlaneIndex);
+/* CUDA devices visible (0 when there is none or the driver is absent). */
+int T360B200_deviceCount(void);
+const char* T360B200_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TRANSFORM360_B200_EXT_H */

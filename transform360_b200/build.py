@@ -1,0 +1,60 @@
+"""Builds transform360_b200/lib/libTransform360.so (the drop-in C-ABI library) in-tree with nvcc for sm_100a.
+
+    python -m transform360_b200.build [--force] [--verbose]
+
+The artifact name follows the reference's CMake target (Transform360/CMakeLists.txt:9: libTransform360).
+The .so is git-ignored but travels to the GPU box with gpurun.
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+from pathlib import Path
+
+PKG = Path(__file__).resolve().parent
+ROOT = PKG.parent
+CSRC = PKG / "csrc"
+LIB_DIR = PKG / "lib"
+LIB = LIB_DIR / "libTransform360.so"
+SOURCES = ["geometry.cpp", "lowpass_plan.cpp", "sampling.cpp", "kernels.cu", "video_frame_transform.cpp"]
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+
+
+def nvcc_path() -> str:
+    p = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not Path(p).exists():
+        raise FileNotFoundError("nvcc not found (needed to build libTransform360.so)")
+    return p
+
+
+def needs_build() -> bool:
+    if not LIB.exists():
+        return True
+    t = LIB.stat().st_mtime
+    deps = list(CSRC.glob("*")) + list((ROOT / "include").rglob("*.h")) + [Path(__file__)]
+    return any(d.stat().st_mtime > t for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> Path:
+    if not force and not needs_build():
+        return LIB
+    LIB_DIR.mkdir(exist_ok=True)
+    # host code: -ffp-contract=off keeps the planner's float sequence identical to the reference's build
+    host_flags = "-fPIC,-fvisibility=hidden,-ffp-contract=off,-fno-fast-math,-Wall"
+    cmd = [nvcc_path(), *ARCH, "-O3", "-lineinfo", "-std=c++17", "--shared", "-Xcompiler", host_flags,
+           "-Xptxas", "-v" if verbose else "-warn-spills", "-I", str(ROOT / "include"), "-I", str(CSRC),
+           "-o", str(LIB)] + [str(CSRC / s) for s in SOURCES]
+    env = dict(os.environ)
+    r = subprocess.run(cmd, capture_output=True, text=True, env=env)
+    if verbose or r.returncode != 0:
+        sys.stderr.write(" ".join(cmd) + "\n" + r.stdout + r.stderr)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc failed building libTransform360.so")
+    return LIB
+
+
+if __name__ == "__main__":
+    p = build(force="--force" in sys.argv, verbose="--verbose" in sys.argv)
+    print(p)

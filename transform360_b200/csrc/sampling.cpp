@@ -1,0 +1,161 @@
+// Fixed-point sampling plan: turns the float warp map into what the gather kernels consume, and builds
+// the interpolation weight tables.  The arithmetic to be reproduced is OpenCV's cv::remap for an 8-bit
+// source with a CV_32FC2 map (the call at reference VideoFrameTransform.cpp:748-754); OpenCV is an
+// external, un-pinned dependency of the reference (CMakeLists.txt:11), its published algorithm is
+// restated in SURVEY.md Appendix A and pinned against cv2 4.13.0 in tests/test_oracle_pin.py:
+//   * coordinates are quantised to 1/32 pixel with round-half-even, integer parts saturate to int16;
+//   * a k x k window (k = 2, 4, 8) is weighted with 15-bit fixed-point products of two 1-D kernels,
+//     each 2-D entry rounded separately and the window patched so that it sums to exactly 32768;
+//   * the result is (sum + 16384) >> 15, saturated to 8 bits.
+#include <cfloat>
+#include <cmath>
+#include <cstdio>
+#include <memory>
+#include <mutex>
+
+#include "host_plan.h"
+
+namespace t360 {
+namespace {
+
+constexpr int kFracBits = 5, kPhases1D = 1 << kFracBits, kPhases2D = kPhases1D * kPhases1D;
+constexpr int kWeightOne = 1 << 15;
+
+inline int roundHalfEven(float v) { return static_cast<int>(std::lrintf(v)); }  // default FP environment
+inline int clampToShort(int v) { return v < -32768 ? -32768 : (v > 32767 ? 32767 : v); }
+
+// 1-D interpolation kernels at offset t in [0,1): taps for positions -(k/2-1) .. k/2
+void taps1D(int k, float t, float* w) {
+  if (k == 2) {
+    w[0] = 1.f - t;
+    w[1] = t;
+  } else if (k == 4) {  // Keys cubic, a = -0.75
+    const float a = -0.75f;
+    w[0] = ((a * (t + 1) - 5 * a) * (t + 1) + 8 * a) * (t + 1) - 4 * a;
+    w[1] = ((a + 2) * t - (a + 3)) * t * t + 1;
+    w[2] = ((a + 2) * (1 - t) - (a + 3)) * (1 - t) * (1 - t) + 1;
+    w[3] = 1.f - w[0] - w[1] - w[2];
+  } else {  // Lanczos a = 4, evaluated through the angle-addition form OpenCV uses
+    if (t < FLT_EPSILON) {
+      for (int i = 0; i < 8; ++i) w[i] = 0;
+      w[3] = 1;
+      return;
+    }
+    const double r = 0.70710678118654752440084436210485;
+    const double rot[8][2] = {{1, 0}, {-r, -r}, {0, 1}, {r, -r}, {-1, 0}, {r, r}, {0, -1}, {-r, r}};
+    const double phi0 = -(t + 3) * M_PI * 0.25, s0 = std::sin(phi0), c0 = std::cos(phi0);
+    float total = 0;
+    for (int i = 0; i < 8; ++i) {
+      const double phi = -(t + 3 - i) * M_PI * 0.25;
+      w[i] = static_cast<float>((rot[i][0] * s0 + rot[i][1] * c0) / (phi * phi));
+      total += w[i];
+    }
+    total = 1.f / total;
+    for (int i = 0; i < 8; ++i) w[i] *= total;
+  }
+}
+
+std::unique_ptr<int16_t[]> buildTable(int k) {
+  std::unique_ptr<int16_t[]> tab(new int16_t[static_cast<size_t>(kPhases2D) * k * k]());
+  float oneD[kPhases1D * 8];
+  const float step = 1.f / kPhases1D;
+  for (int p = 0; p < kPhases1D; ++p) taps1D(k, p * step, oneD + p * k);
+  for (int py = 0; py < kPhases1D; ++py)
+    for (int px = 0; px < kPhases1D; ++px) {
+      int16_t* cell = tab.get() + static_cast<size_t>(py * kPhases1D + px) * k * k;
+      int total = 0;
+      for (int r = 0; r < k; ++r) {
+        const float wy = oneD[py * k + r];
+        for (int c = 0; c < k; ++c) {
+          const float w = wy * oneD[px * k + c];
+          total += cell[r * k + c] = static_cast<int16_t>(clampToShort(roundHalfEven(w * kWeightOne)));
+        }
+      }
+      if (total == kWeightOne) continue;
+      const int excess = total - kWeightOne;
+      if (k == 2) {
+        // only the (0,0) phase: weight 1.0 saturates to 32767 and OpenCV's patch lands on entry (1,1)
+        cell[3] = static_cast<int16_t>(cell[3] - excess);
+        continue;
+      }
+      // patch the largest (deficit) or smallest (excess) entry of the 2x2 block at [k/2, k/2+2)^2
+      const int h = k / 2;
+      int hiR = h, hiC = h, loR = h, loC = h;
+      for (int r = h; r < h + 2; ++r)
+        for (int c = h; c < h + 2; ++c) {
+          if (cell[r * k + c] < cell[loR * k + loC]) { loR = r; loC = c; }
+          else if (cell[r * k + c] > cell[hiR * k + hiC]) { hiR = r; hiC = c; }
+        }
+      if (excess < 0) cell[hiR * k + hiC] = static_cast<int16_t>(cell[hiR * k + hiC] - excess);
+      else cell[loR * k + loC] = static_cast<int16_t>(cell[loR * k + loC] - excess);
+    }
+  return tab;
+}
+
+}  // namespace
+
+int remapTable(int interpolationAlg, const int16_t** table) {
+  static std::mutex mu;
+  static std::unique_ptr<int16_t[]> cache[9];
+  const int k = kernelSizeOf(interpolationAlg);
+  if (k < 2) {
+    if (table) *table = nullptr;
+    return k;
+  }
+  std::lock_guard<std::mutex> lock(mu);
+  if (!cache[k]) cache[k] = buildTable(k);
+  if (table) *table = cache[k].get();
+  return k;
+}
+
+void quantizeWarpMap(HostPlan& plan) {
+  const int k = plan.kernelSize;
+  const size_t n = static_cast<size_t>(plan.mapW) * plan.mapH;
+  plan.samples.resize(n);
+  const float* m = plan.map.data();
+  for (size_t i = 0; i < n; ++i) {
+    const float fx = m[2 * i], fy = m[2 * i + 1];
+    SamplePoint s;
+    if (k == 1) {
+      s.col0 = clampToShort(roundHalfEven(fx));
+      s.rowPhase = clampToShort(roundHalfEven(fy)) * 1024;
+    } else {
+      const int X = roundHalfEven(fx * kPhases1D), Y = roundHalfEven(fy * kPhases1D);
+      const int phase = (Y & (kPhases1D - 1)) * kPhases1D + (X & (kPhases1D - 1));
+      s.col0 = clampToShort(X >> kFracBits) - (k / 2 - 1);
+      s.rowPhase = (clampToShort(Y >> kFracBits) - (k / 2 - 1)) * 1024 + phase;
+    }
+    plan.samples[i] = s;
+  }
+}
+
+bool buildHostPlan(const FrameTransformContext& ctx, int inW, int inH, int outW, int outH, HostPlan& plan) {
+  plan = HostPlan{};
+  plan.ctx = ctx;
+  if (inW <= 0 || inH <= 0 || outW <= 0 || outH <= 0) {
+    std::printf("Could not generate map: non-positive plane size %dx%d -> %dx%d.\n", inW, inH, outW, outH);
+    return false;
+  }
+  plan.inW = inW; plan.inH = inH; plan.outW = outW; plan.outH = outH;
+  // render size before the optional area down-scale (reference cpp:524-526)
+  plan.mapW = static_cast<int>(ctx.width_scale_factor * outW + 0.5);
+  plan.mapH = static_cast<int>(ctx.height_scale_factor * outH + 0.5);
+  if (plan.mapW <= 0 || plan.mapH <= 0) {
+    std::printf("Could not generate map: scale factors give an empty plane.\n");
+    return false;
+  }
+  plan.kernelSize = kernelSizeOf(ctx.interpolation_alg);
+  plan.transparentBorder = ctx.output_layout == LAYOUT_BARREL || ctx.output_layout == LAYOUT_BARREL_SPLIT;
+  if (!buildWarpMap(plan)) return false;
+  if (plan.kernelSize > 0) quantizeWarpMap(plan);
+  if (ctx.enable_low_pass_filter) {
+    if (ctx.num_vertical_segments < 1 || ctx.num_horizontal_segments < 1) {
+      std::printf("Could not generate map: segment counts must be positive.\n");
+      return false;
+    }
+    if (!buildLowPassPlan(plan)) return false;
+  }
+  return true;
+}
+
+}  // namespace t360

@@ -1,0 +1,486 @@
+// class VideoFrameTransform + the extern "C" boundary.
+//
+// Mirrors the reference's public surface (VideoFrameTransform.h:40-75, VideoFrameTransformHandler.cpp:18-64):
+// same class name behind the opaque handle, same four C entry points, same bool/int results, messages on
+// stdout.  Everything behind it is new: the host planner (geometry.cpp, lowpass_plan.cpp, sampling.cpp)
+// produces the plan, it is uploaded once, and each frame plane is two kernel launches at most
+// (segmented low-pass, gather).  There is no CPU pixel path: if CUDA is unavailable the calls fail.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <new>
+#include <stdexcept>
+#include <vector>
+
+#include "host_plan.h"
+#include "kernels.cuh"
+#include "transform360_b200.h"
+
+#define T360_API extern "C" __attribute__((visibility("default")))
+
+namespace {
+
+using t360::BlurJob;
+using t360::HostPlan;
+
+struct CudaFail {
+  cudaError_t err;
+  const char* what;
+};
+
+#define CU(call)                                       \
+  do {                                                 \
+    cudaError_t e__ = (call);                          \
+    if (e__ != cudaSuccess) throw CudaFail{e__, #call}; \
+  } while (0)
+
+template <typename T>
+struct DeviceBuffer {
+  T* ptr = nullptr;
+  size_t count = 0;
+  DeviceBuffer() = default;
+  DeviceBuffer(const DeviceBuffer&) = delete;
+  DeviceBuffer& operator=(const DeviceBuffer&) = delete;
+  DeviceBuffer(DeviceBuffer&& o) noexcept : ptr(o.ptr), count(o.count) { o.ptr = nullptr; o.count = 0; }
+  DeviceBuffer& operator=(DeviceBuffer&& o) noexcept {
+    if (this != &o) { release(); ptr = o.ptr; count = o.count; o.ptr = nullptr; o.count = 0; }
+    return *this;
+  }
+  ~DeviceBuffer() { release(); }
+  void release() {
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr;
+    count = 0;
+  }
+  void reserve(size_t n) {  // grow-only
+    if (n <= count) return;
+    release();
+    CU(cudaMalloc(reinterpret_cast<void**>(&ptr), n * sizeof(T)));
+    count = n;
+  }
+  size_t bytes() const { return count * sizeof(T); }
+};
+
+// Device-resident plan of one plan index (what the reference keeps in warpMats_, filterKernelsX_/Y_,
+// segmentFilteringConfigs_; VideoFrameTransform.h:150-159).
+struct DevicePlan {
+  int inW = 0, inH = 0, outW = 0, outH = 0, mapW = 0, mapH = 0;
+  int kernelSize = 0;
+  bool transparent = false, lowPass = false, blurNeedsClear = false;
+  DeviceBuffer<int2> samples;
+  int samplesPitch = 0;
+  DeviceBuffer<BlurJob> tileJobs, directJobs;
+  int numTileJobs = 0, numDirectJobs = 0, tileSmem = 0;
+  DeviceBuffer<float> taps;
+  size_t deviceBytes() const { return samples.bytes() + tileJobs.bytes() + directJobs.bytes() + taps.bytes(); }
+};
+
+constexpr int kPitchAlign = 256;
+inline int alignedPitch(int w) { return (w + kPitchAlign - 1) / kPitchAlign * kPitchAlign; }
+
+}  // namespace
+
+class VideoFrameTransform {
+ public:
+  explicit VideoFrameTransform(FrameTransformContext* ctx) { std::memcpy(&ctx_, ctx, sizeof(ctx_)); }
+
+  ~VideoFrameTransform() {
+    if (deviceReady_) {
+      cudaSetDevice(device_);
+      plans_.clear();
+      for (auto& w : weights_) w.release();
+      stagingIn_.release(); stagingOut_.release(); blurred_.release();
+      if (stream_) cudaStreamDestroy(stream_);
+    }
+  }
+
+  // reference generateMapForPlane (cpp:504-576): plan on the host, upload once.
+  bool generateMapForPlane(int inW, int inH, int outW, int outH, int planIndex) {
+    try {
+      HostPlan host;
+      if (!t360::buildHostPlan(ctx_, inW, inH, outW, outH, host)) return false;
+      ensureDevice();
+      std::lock_guard<std::mutex> lock(mu_);
+      plans_[planIndex] = upload(host);
+      return true;
+    } catch (const CudaFail& f) {
+      std::printf("Could not generate map for plane %d. Error: CUDA %s (%s) in %s\n", planIndex,
+                  cudaGetErrorName(f.err), cudaGetErrorString(f.err), f.what);
+    } catch (const std::exception& ex) {
+      std::printf("Could not generate map for plane %d. Error: %s\n", planIndex, ex.what());
+    }
+    return false;
+  }
+
+  // reference transformFramePlane (cpp:1319-1351): host or device planes, synchronous.
+  bool transformFramePlane(uint8_t* in, uint8_t* out, int inW, int inH, int inPitch, int outW, int outH, int outPitch,
+                           int planIndex, int imagePlaneIndex) {
+    try {
+      if (!in || !out || inW <= 0 || inH <= 0 || outW <= 0 || outH <= 0 || inPitch < inW || outPitch < outW) {
+        std::printf("Could not transform the plane %d. Error: invalid plane description\n", imagePlaneIndex);
+        return false;
+      }
+      ensureDevice();
+      const bool inOnDevice = isDevicePointer(in), outOnDevice = isDevicePointer(out);
+      const DevicePlan* plan = findPlan(planIndex, imagePlaneIndex);
+      if (!plan) return false;
+      const uint8_t* dIn = in;
+      uint8_t* dOut = out;
+      int dInPitch = inPitch, dOutPitch = outPitch;
+      if (!inOnDevice) {
+        dInPitch = alignedPitch(inW);
+        stagingIn_.reserve(static_cast<size_t>(dInPitch) * inH + 64);
+        CU(cudaMemcpy2DAsync(stagingIn_.ptr, dInPitch, in, inPitch, inW, inH, cudaMemcpyHostToDevice, stream_));
+        dIn = stagingIn_.ptr;
+      }
+      if (!outOnDevice) {
+        dOutPitch = alignedPitch(outW);
+        stagingOut_.reserve(static_cast<size_t>(dOutPitch) * outH + 64);
+        dOut = stagingOut_.ptr;
+        if (plan->transparent) {
+          // barrel layouts leave unmapped pixels untouched: chroma planes start at 128 (reference cpp:743-747),
+          // the luma plane keeps whatever the caller's buffer holds
+          if (planIndex) CU(cudaMemset2DAsync(dOut, dOutPitch, 128, outW, outH, stream_));
+          else CU(cudaMemcpy2DAsync(dOut, dOutPitch, out, outPitch, outW, outH, cudaMemcpyHostToDevice, stream_));
+        }
+      } else if (plan->transparent && planIndex) {
+        CU(cudaMemset2DAsync(dOut, dOutPitch, 128, outW, outH, stream_));
+      }
+      if (!enqueue(*plan, dIn, dOut, inW, inH, dInPitch, outW, outH, dOutPitch, stream_, imagePlaneIndex)) return false;
+      if (!outOnDevice)
+        CU(cudaMemcpy2DAsync(out, outPitch, dOut, dOutPitch, outW, outH, cudaMemcpyDeviceToHost, stream_));
+      CU(cudaStreamSynchronize(stream_));
+      return true;
+    } catch (const CudaFail& f) {
+      std::printf("Could not transform the plane %d. Error: CUDA %s (%s) in %s\n", imagePlaneIndex,
+                  cudaGetErrorName(f.err), cudaGetErrorString(f.err), f.what);
+      cudaGetLastError();
+    } catch (const std::exception& ex) {
+      std::printf("Could not transform the plane %d. Error: %s\n", imagePlaneIndex, ex.what());
+    }
+    return false;
+  }
+
+  // device to device, asynchronous
+  bool transformDevice(const uint8_t* dIn, uint8_t* dOut, int inW, int inH, int inPitch, int outW, int outH,
+                       int outPitch, int planIndex, cudaStream_t stream) {
+    try {
+      ensureDevice();
+      const DevicePlan* plan = findPlan(planIndex, planIndex);
+      if (!plan) return false;
+      cudaStream_t s = stream ? stream : stream_;
+      if (plan->transparent && planIndex) CU(cudaMemset2DAsync(dOut, outPitch, 128, outW, outH, s));
+      return enqueue(*plan, dIn, dOut, inW, inH, inPitch, outW, outH, outPitch, s, planIndex);
+    } catch (const CudaFail& f) {
+      std::printf("Could not transform the plane %d. Error: CUDA %s (%s) in %s\n", planIndex, cudaGetErrorName(f.err),
+                  cudaGetErrorString(f.err), f.what);
+      cudaGetLastError();
+    } catch (const std::exception& ex) {
+      std::printf("Could not transform the plane %d. Error: %s\n", planIndex, ex.what());
+    }
+    return false;
+  }
+
+  bool lowPassDevice(const uint8_t* dIn, uint8_t* dOut, int w, int h, int inPitch, int outPitch, int planIndex,
+                     cudaStream_t stream) {
+    try {
+      ensureDevice();
+      const DevicePlan* plan = findPlan(planIndex, planIndex);
+      if (!plan) return false;
+      if (!plan->lowPass) {
+        std::printf("Could not filter plane %d. Error: plan has no low-pass stage\n", planIndex);
+        return false;
+      }
+      runLowPass(*plan, dIn, dOut, w, h, inPitch, outPitch, stream ? stream : stream_);
+      return true;
+    } catch (const CudaFail& f) {
+      std::printf("Could not filter plane %d. Error: CUDA %s (%s) in %s\n", planIndex, cudaGetErrorName(f.err),
+                  cudaGetErrorString(f.err), f.what);
+      cudaGetLastError();
+    }
+    return false;
+  }
+
+  bool synchronize() {
+    if (!deviceReady_) return true;
+    return cudaStreamSynchronize(stream_) == cudaSuccess;
+  }
+  cudaStream_t stream() {
+    try { ensureDevice(); } catch (...) { return nullptr; }
+    return stream_;
+  }
+  size_t planBytes(int planIndex) {
+    std::lock_guard<std::mutex> lock(mu_);
+    auto it = plans_.find(planIndex);
+    return it == plans_.end() ? 0 : it->second.deviceBytes();
+  }
+
+ private:
+  void ensureDevice() {
+    if (deviceReady_) {
+      CU(cudaSetDevice(device_));
+      return;
+    }
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) throw CudaFail{e != cudaSuccess ? e : cudaErrorNoDevice, "cudaGetDeviceCount (no CUDA device: this library has no CPU fallback)"};
+    CU(cudaGetDevice(&device_));  // honour the caller's current device (one process per GPU sets it before)
+    cudaDeviceProp prop{};
+    CU(cudaGetDeviceProperties(&prop, device_));
+    numSMs_ = prop.multiProcessorCount;
+    CU(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+    deviceReady_ = true;
+  }
+
+  static bool isDevicePointer(const void* p) {
+    cudaPointerAttributes a{};
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+      cudaGetLastError();
+      return false;
+    }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+  }
+
+  const DevicePlan* findPlan(int planIndex, int imagePlaneIndex) {
+    std::lock_guard<std::mutex> lock(mu_);
+    auto it = plans_.find(planIndex);
+    if (it == plans_.end()) {
+      std::printf("Could not transform the plane %d. Error: no map was generated for index %d\n", imagePlaneIndex, planIndex);
+      return nullptr;
+    }
+    return &it->second;
+  }
+
+  const int16_t* deviceWeights(int interpolationAlg) {
+    const int16_t* host = nullptr;
+    const int k = t360::remapTable(interpolationAlg, &host);
+    if (k < 2) return nullptr;
+    auto& buf = weights_[k];
+    if (!buf.ptr) {
+      buf.reserve(static_cast<size_t>(1024) * k * k);
+      CU(cudaMemcpy(buf.ptr, host, buf.bytes(), cudaMemcpyHostToDevice));
+    }
+    return buf.ptr;
+  }
+
+  DevicePlan upload(const HostPlan& h) {
+    DevicePlan d;
+    d.inW = h.inW; d.inH = h.inH; d.outW = h.outW; d.outH = h.outH; d.mapW = h.mapW; d.mapH = h.mapH;
+    d.kernelSize = h.kernelSize;
+    d.transparent = h.transparentBorder;
+    if (d.kernelSize > 0) {
+      deviceWeights(ctx_.interpolation_alg);
+      d.samplesPitch = (h.mapW + 3) & ~3;
+      std::vector<int2> padded(static_cast<size_t>(d.samplesPitch) * h.mapH, int2{0, 0});
+      for (int y = 0; y < h.mapH; ++y)
+        std::memcpy(&padded[static_cast<size_t>(y) * d.samplesPitch], &h.samples[static_cast<size_t>(y) * h.mapW],
+                    static_cast<size_t>(h.mapW) * sizeof(int2));
+      d.samples.reserve(padded.size());
+      CU(cudaMemcpy(d.samples.ptr, padded.data(), padded.size() * sizeof(int2), cudaMemcpyHostToDevice));
+    }
+    d.lowPass = ctx_.enable_low_pass_filter != 0;
+    if (d.lowPass) buildBlurJobs(h, d);
+    return d;
+  }
+
+  // Tiles of the plan, applied once (mono) or to both halves of a stereo frame (reference cpp:630-691), cut
+  // into CTA-sized jobs.  Segments that do not fit the plane are dropped, like the reference's caught cv::Exception.
+  void buildBlurJobs(const HostPlan& h, DevicePlan& d) {
+    std::vector<BlurJob> tiles, direct;
+    int offX[2] = {0, 0}, offY[2] = {0, 0}, passes = 1;
+    if (ctx_.input_stereo_format == STEREO_FORMAT_LR) { passes = 2; offX[1] = static_cast<int>(0.5 * h.inW); }
+    else if (ctx_.input_stereo_format == STEREO_FORMAT_TB) { passes = 2; offY[1] = static_cast<int>(0.5 * h.inH); }
+    std::vector<uint8_t> covered(static_cast<size_t>(h.inW) * h.inH, 0);
+    int tileSmem = 0;
+    for (int pass = 0; pass < passes; ++pass)
+      for (const t360::LowPassSegment& s : h.segments) {
+        const int left = s.left + offX[pass], top = s.top + offY[pass];
+        if (left < 0 || top < 0 || s.width <= 0 || s.height <= 0 || left + s.width > h.inW || top + s.height > h.inH) continue;
+        for (int y = 0; y < s.height; ++y) std::memset(&covered[static_cast<size_t>(top + y) * h.inW + left], 1, s.width);
+        for (int ty = 0; ty < s.height; ty += t360::kBlurTileH)
+          for (int tx = 0; tx < s.width; tx += t360::kBlurTileW) {
+            BlurJob j{left + tx, top + ty, std::min(t360::kBlurTileW, s.width - tx), std::min(t360::kBlurTileH, s.height - ty),
+                      s.kxOffset, s.kxCount, s.kyOffset, s.kyCount};
+            const long long need = static_cast<long long>(t360::blurTileSmem(j.w, j.h, j.kxCount, j.kyCount));
+            if (need <= t360::kBlurMaxSmem) {
+              tiles.push_back(j);
+              tileSmem = std::max(tileSmem, static_cast<int>(need));
+            } else {
+              direct.push_back(j);
+            }
+          }
+      }
+    d.blurNeedsClear = std::find(covered.begin(), covered.end(), 0) != covered.end();
+    d.numTileJobs = static_cast<int>(tiles.size());
+    d.numDirectJobs = static_cast<int>(direct.size());
+    d.tileSmem = tileSmem;
+    if (!tiles.empty()) {
+      d.tileJobs.reserve(tiles.size());
+      CU(cudaMemcpy(d.tileJobs.ptr, tiles.data(), tiles.size() * sizeof(BlurJob), cudaMemcpyHostToDevice));
+    }
+    if (!direct.empty()) {
+      d.directJobs.reserve(direct.size());
+      CU(cudaMemcpy(d.directJobs.ptr, direct.data(), direct.size() * sizeof(BlurJob), cudaMemcpyHostToDevice));
+    }
+    if (!h.taps.empty()) {
+      d.taps.reserve(h.taps.size());
+      CU(cudaMemcpy(d.taps.ptr, h.taps.data(), h.taps.size() * sizeof(float), cudaMemcpyHostToDevice));
+    }
+  }
+
+  void runLowPass(const DevicePlan& plan, const uint8_t* dIn, uint8_t* dOut, int w, int h, int inPitch, int outPitch,
+                  cudaStream_t s) {
+    if (plan.blurNeedsClear || w != plan.inW || h != plan.inH) CU(cudaMemset2DAsync(dOut, outPitch, 0, w, h, s));
+    if (w != plan.inW || h != plan.inH) {
+      // the tiles were laid out for other dimensions; the reference would filter whatever fits and leave the rest 0.
+      // Not reproduced tile by tile: refuse rather than silently differ.
+      throw std::runtime_error("plane size differs from the size the low-pass plan was generated for");
+    }
+    t360::BlurParams bp{dIn, dOut, w, h, inPitch, outPitch, plan.tileJobs.ptr, plan.numTileJobs, plan.taps.ptr, plan.tileSmem};
+    CU(t360::launchBlur(bp, s));
+    if (plan.numDirectJobs) {
+      bp.jobs = plan.directJobs.ptr;
+      bp.numJobs = plan.numDirectJobs;
+      CU(t360::launchBlurDirect(bp, s));
+    }
+  }
+
+  // reference transformPlane (cpp:707-794): [low-pass] -> gather.  Device pointers, asynchronous.
+  bool enqueue(const DevicePlan& plan, const uint8_t* dIn, uint8_t* dOut, int inW, int inH, int inPitch, int outW,
+               int outH, int outPitch, cudaStream_t s, int imagePlaneIndex) {
+    if (plan.kernelSize == 0) {
+      std::printf("Could not find interpolation algorithm for plane %d", imagePlaneIndex);  // reference cpp:780-784
+      return true;
+    }
+    if (outW != plan.mapW || outH != plan.mapH) {
+      // reference cpp:735-737, 755-777: render at map size, then cv::resize(INTER_AREA).  SURVEY.md 8(f) rank 4.
+      std::printf("Could not transform the plane %d. Error: output %dx%d differs from the planned %dx%d "
+                  "(area-resize path is not implemented yet)\n", imagePlaneIndex, outW, outH, plan.mapW, plan.mapH);
+      return false;
+    }
+    const uint8_t* src = dIn;
+    int srcPitch = inPitch;
+    if (plan.lowPass) {
+      const int bp = alignedPitch(inW);
+      blurred_.reserve(static_cast<size_t>(bp) * inH + 64);
+      runLowPass(plan, dIn, blurred_.ptr, inW, inH, inPitch, bp, s);
+      src = blurred_.ptr;
+      srcPitch = bp;
+    }
+    t360::GatherParams gp{src, inW, inH, srcPitch, dOut, outW, outH, outPitch, plan.samples.ptr, plan.samplesPitch,
+                          weights_[plan.kernelSize].ptr, plan.kernelSize, plan.transparent ? 1 : 0};
+    CU(t360::launchGather(gp, numSMs_, s));
+    return true;
+  }
+
+  FrameTransformContext ctx_;
+  std::mutex mu_;
+  std::map<int, DevicePlan> plans_;
+  DeviceBuffer<int16_t> weights_[9];
+  DeviceBuffer<uint8_t> stagingIn_, stagingOut_, blurred_;
+  cudaStream_t stream_ = nullptr;
+  int device_ = 0, numSMs_ = 0;
+  bool deviceReady_ = false;
+};
+
+// ---- the reference C-ABI (VideoFrameTransformHandler.h:22-47) ------------------------------------------
+T360_API VideoFrameTransform* VideoFrameTransform_new(FrameTransformContext* ctx) {
+  if (!ctx) return nullptr;
+  return new (std::nothrow) VideoFrameTransform(ctx);
+}
+
+T360_API void VideoFrameTransform_delete(VideoFrameTransform* transform) { delete transform; }
+
+T360_API int VideoFrameTransform_generateMapForPlane(VideoFrameTransform* transform, int inputWidth, int inputHeight,
+                                                     int outputWidth, int outputHeight, int transformMatPlaneIndex) {
+  if (!transform) return 0;
+  return transform->generateMapForPlane(inputWidth, inputHeight, outputWidth, outputHeight, transformMatPlaneIndex);
+}
+
+T360_API int VideoFrameTransform_transformFramePlane(VideoFrameTransform* transform, uint8_t* inputData,
+                                                     uint8_t* outputData, int inputWidth, int inputHeight,
+                                                     int inputWidthWithPadding, int outputWidth, int outputHeight,
+                                                     int outputWidthWithPadding, int transformMatPlaneIndex,
+                                                     int imagePlaneIndex) {
+  if (!transform) return 0;
+  return transform->transformFramePlane(inputData, outputData, inputWidth, inputHeight, inputWidthWithPadding,
+                                        outputWidth, outputHeight, outputWidthWithPadding, transformMatPlaneIndex,
+                                        imagePlaneIndex);
+}
+
+// ---- extensions (transform360_b200.h) --------------------------------------------------------------------
+struct T360HostPlan {
+  HostPlan plan;
+};
+
+T360_API T360HostPlan* T360B200_hostPlanCreate(const FrameTransformContext* ctx, int inW, int inH, int outW, int outH) {
+  if (!ctx) return nullptr;
+  std::unique_ptr<T360HostPlan> p(new (std::nothrow) T360HostPlan);
+  if (!p) return nullptr;
+  try {
+    if (!t360::buildHostPlan(*ctx, inW, inH, outW, outH, p->plan)) return nullptr;
+  } catch (const std::exception& ex) {
+    std::printf("Could not build the host plan. Error: %s\n", ex.what());
+    return nullptr;
+  }
+  return p.release();
+}
+T360_API void T360B200_hostPlanDestroy(T360HostPlan* plan) { delete plan; }
+T360_API int T360B200_hostPlanInfo(const T360HostPlan* plan, int info[6]) {
+  if (!plan || !info) return 0;
+  info[0] = plan->plan.mapW; info[1] = plan->plan.mapH;
+  info[2] = static_cast<int>(plan->plan.segments.size());
+  info[3] = static_cast<int>(plan->plan.taps.size());
+  info[4] = plan->plan.kernelSize;
+  info[5] = 0;
+  return 1;
+}
+T360_API const float* T360B200_hostPlanMap(const T360HostPlan* plan) { return plan ? plan->plan.map.data() : nullptr; }
+T360_API const int32_t* T360B200_hostPlanSamples(const T360HostPlan* plan) {
+  return plan && !plan->plan.samples.empty() ? reinterpret_cast<const int32_t*>(plan->plan.samples.data()) : nullptr;
+}
+T360_API int T360B200_hostPlanSegment(const T360HostPlan* plan, int i, int rect[4], int numTaps[2], const float** kx,
+                                      const float** ky) {
+  if (!plan || i < 0 || i >= static_cast<int>(plan->plan.segments.size())) return 0;
+  const t360::LowPassSegment& s = plan->plan.segments[i];
+  rect[0] = s.left; rect[1] = s.top; rect[2] = s.width; rect[3] = s.height;
+  numTaps[0] = s.kxCount; numTaps[1] = s.kyCount;
+  if (kx) *kx = plan->plan.taps.data() + s.kxOffset;
+  if (ky) *ky = plan->plan.taps.data() + s.kyOffset;
+  return 1;
+}
+T360_API int T360B200_remapTable(int interpolationAlg, const int16_t** table) { return t360::remapTable(interpolationAlg, table); }
+
+T360_API int T360B200_transformFramePlaneAsync(VideoFrameTransform* t, const uint8_t* dIn, uint8_t* dOut, int inW, int inH,
+                                               int inPitch, int outW, int outH, int outPitch, int planIndex, void* stream) {
+  if (!t || !dIn || !dOut) return 0;
+  return t->transformDevice(dIn, dOut, inW, inH, inPitch, outW, outH, outPitch, planIndex, static_cast<cudaStream_t>(stream));
+}
+T360_API int T360B200_lowPassPlaneAsync(VideoFrameTransform* t, const uint8_t* dIn, uint8_t* dOut, int w, int h, int inPitch,
+                                        int outPitch, int planIndex, void* stream) {
+  if (!t || !dIn || !dOut) return 0;
+  try {
+    return t->lowPassDevice(dIn, dOut, w, h, inPitch, outPitch, planIndex, static_cast<cudaStream_t>(stream));
+  } catch (const std::exception& ex) {
+    std::printf("Could not filter plane %d. Error: %s\n", planIndex, ex.what());
+    return 0;
+  }
+}
+T360_API int T360B200_synchronize(VideoFrameTransform* t) { return t ? t->synchronize() : 0; }
+T360_API void* T360B200_stream(VideoFrameTransform* t) { return t ? t->stream() : nullptr; }
+T360_API unsigned long long T360B200_kernelLaunchCount(void) { return t360::kernelLaunchCount(); }
+T360_API unsigned long long T360B200_planDeviceBytes(VideoFrameTransform* t, int planIndex) { return t ? t->planBytes(planIndex) : 0; }
+T360_API int T360B200_deviceCount(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+T360_API const char* T360B200_version(void) { return "transform360-b200 0.1 (sm_100a)"; }

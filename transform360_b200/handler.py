@@ -1,0 +1,256 @@
+"""Python mirror of the reference's C handler (VideoFrameTransformHandler.h:22-47) over libTransform360.so.
+
+This is a thin ctypes binding of the drop-in C-ABI -- the same four entry points the reference's ffmpeg
+filter calls (vf_transform360.c:141, 157, 334, 383) -- plus the extension entry points of
+``include/transform360_b200.h``.  It exists so that tests, ``bench.py`` and the multi-GPU stream driver
+can call the product exactly the way a C caller would.  There is no Python or CPU pixel path here: if the
+shared library is missing, ``load()`` raises; if no CUDA device is usable the C calls return 0.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+import numpy as np
+
+PKG = Path(__file__).resolve().parent
+LIB_PATH = PKG / "lib" / "libTransform360.so"
+
+# enums of Transform360/VideoFrameTransformHelper.h
+LAYOUT_CUBEMAP_32, LAYOUT_CUBEMAP_23_OFFCENTER, LAYOUT_FLAT_FIXED, LAYOUT_EQUIRECT = 0, 1, 2, 3
+LAYOUT_BARREL, LAYOUT_BARREL_SPLIT, LAYOUT_EAC_32, LAYOUT_N = 4, 5, 6, 7
+STEREO_FORMAT_TB, STEREO_FORMAT_LR, STEREO_FORMAT_MONO, STEREO_FORMAT_GUESS, STEREO_FORMAT_N = 0, 1, 2, 3, 4
+NEAREST, LINEAR, CUBIC, LANCZOS4 = 0, 1, 2, 4
+
+
+class FrameTransformContext(C.Structure):
+    """28 x 4 bytes, field for field the reference's struct (VideoFrameTransformHelper.h:56-90)."""
+    _fields_ = [
+        ("input_layout", C.c_int), ("output_layout", C.c_int),
+        ("input_stereo_format", C.c_int), ("output_stereo_format", C.c_int),
+        ("vflip", C.c_int), ("input_expand_coef", C.c_float), ("expand_coef", C.c_float),
+        ("interpolation_alg", C.c_int), ("width_scale_factor", C.c_float),
+        ("height_scale_factor", C.c_float), ("fixed_yaw", C.c_float), ("fixed_pitch", C.c_float),
+        ("fixed_roll", C.c_float), ("fixed_hfov", C.c_float), ("fixed_vfov", C.c_float),
+        ("fixed_cube_offcenter_x", C.c_float), ("fixed_cube_offcenter_y", C.c_float),
+        ("fixed_cube_offcenter_z", C.c_float), ("is_horizontal_offset", C.c_int),
+        ("enable_low_pass_filter", C.c_int), ("kernel_height_scale_factor", C.c_float),
+        ("min_kernel_half_height", C.c_float), ("max_kernel_half_height", C.c_float),
+        ("enable_multi_threading", C.c_int), ("num_vertical_segments", C.c_int),
+        ("num_horizontal_segments", C.c_int), ("adjust_kernel", C.c_int),
+        ("kernel_adjust_factor", C.c_float),
+    ]
+
+
+FILTER_DEFAULTS = dict(  # the reference's AVOption defaults (vf_transform360.c:407-987)
+    input_layout=LAYOUT_EQUIRECT, output_layout=LAYOUT_CUBEMAP_32, input_stereo_format=STEREO_FORMAT_MONO,
+    output_stereo_format=STEREO_FORMAT_MONO, vflip=0, input_expand_coef=1.01, expand_coef=1.01,
+    interpolation_alg=CUBIC, width_scale_factor=1.0, height_scale_factor=1.0, fixed_yaw=0.0, fixed_pitch=0.0,
+    fixed_roll=0.0, fixed_hfov=120.0, fixed_vfov=110.0, fixed_cube_offcenter_x=0.0, fixed_cube_offcenter_y=0.0,
+    fixed_cube_offcenter_z=0.0, is_horizontal_offset=0, enable_low_pass_filter=1, kernel_height_scale_factor=1.0,
+    min_kernel_half_height=1.0, max_kernel_half_height=10000.0, enable_multi_threading=1, num_vertical_segments=5,
+    num_horizontal_segments=1, adjust_kernel=1, kernel_adjust_factor=1.0)
+
+
+def make_context(**overrides) -> FrameTransformContext:
+    vals = dict(FILTER_DEFAULTS)
+    for k in overrides:
+        if k not in vals:
+            raise AttributeError(f"FrameTransformContext has no field {k!r}")
+    vals.update(overrides)
+    return FrameTransformContext(**vals)
+
+
+_lib = None
+
+
+def load(path: os.PathLike | None = None):
+    """dlopen()s the product library.  Raises if it has not been built: there is no fallback."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = Path(path) if path else LIB_PATH
+    if not p.exists():
+        raise FileNotFoundError(f"{p} not found: build it with `python -m transform360_b200.build` (needs nvcc); "
+                                "transform360_b200 has no CPU fallback")
+    L = C.CDLL(str(p), mode=os.RTLD_LOCAL)
+    vp, ci = C.c_void_p, C.c_int
+    L.VideoFrameTransform_new.restype = vp
+    L.VideoFrameTransform_new.argtypes = [C.POINTER(FrameTransformContext)]
+    L.VideoFrameTransform_delete.restype = None
+    L.VideoFrameTransform_delete.argtypes = [vp]
+    L.VideoFrameTransform_generateMapForPlane.restype = ci
+    L.VideoFrameTransform_generateMapForPlane.argtypes = [vp] + [ci] * 5
+    L.VideoFrameTransform_transformFramePlane.restype = ci
+    L.VideoFrameTransform_transformFramePlane.argtypes = [vp, vp, vp] + [ci] * 8
+    L.T360B200_hostPlanCreate.restype = vp
+    L.T360B200_hostPlanCreate.argtypes = [C.POINTER(FrameTransformContext)] + [ci] * 4
+    L.T360B200_hostPlanDestroy.restype = None
+    L.T360B200_hostPlanDestroy.argtypes = [vp]
+    L.T360B200_hostPlanInfo.restype = ci
+    L.T360B200_hostPlanInfo.argtypes = [vp, C.POINTER(ci)]
+    L.T360B200_hostPlanMap.restype = vp
+    L.T360B200_hostPlanMap.argtypes = [vp]
+    L.T360B200_hostPlanSamples.restype = vp
+    L.T360B200_hostPlanSamples.argtypes = [vp]
+    L.T360B200_hostPlanSegment.restype = ci
+    L.T360B200_hostPlanSegment.argtypes = [vp, ci, C.POINTER(ci), C.POINTER(ci), C.POINTER(vp), C.POINTER(vp)]
+    L.T360B200_remapTable.restype = ci
+    L.T360B200_remapTable.argtypes = [ci, C.POINTER(vp)]
+    L.T360B200_transformFramePlaneAsync.restype = ci
+    L.T360B200_transformFramePlaneAsync.argtypes = [vp, vp, vp] + [ci] * 7 + [vp]
+    L.T360B200_lowPassPlaneAsync.restype = ci
+    L.T360B200_lowPassPlaneAsync.argtypes = [vp, vp, vp] + [ci] * 5 + [vp]
+    L.T360B200_synchronize.restype = ci
+    L.T360B200_synchronize.argtypes = [vp]
+    L.T360B200_stream.restype = vp
+    L.T360B200_stream.argtypes = [vp]
+    L.T360B200_kernelLaunchCount.restype = C.c_ulonglong
+    L.T360B200_planDeviceBytes.restype = C.c_ulonglong
+    L.T360B200_planDeviceBytes.argtypes = [vp, ci]
+    L.T360B200_deviceCount.restype = ci
+    L.T360B200_version.restype = C.c_char_p
+    if path is None:
+        _lib = L
+    return L
+
+
+EXPORTED_SYMBOLS = [
+    "VideoFrameTransform_new", "VideoFrameTransform_delete", "VideoFrameTransform_generateMapForPlane",
+    "VideoFrameTransform_transformFramePlane", "T360B200_hostPlanCreate", "T360B200_hostPlanDestroy",
+    "T360B200_hostPlanInfo", "T360B200_hostPlanMap", "T360B200_hostPlanSamples", "T360B200_hostPlanSegment",
+    "T360B200_remapTable", "T360B200_transformFramePlaneAsync", "T360B200_lowPassPlaneAsync",
+    "T360B200_synchronize", "T360B200_stream", "T360B200_kernelLaunchCount", "T360B200_planDeviceBytes",
+    "T360B200_deviceCount", "T360B200_version",
+]
+
+
+class VideoFrameTransform:
+    """The opaque handle of the C-ABI with the reference's method names (VideoFrameTransform.h:40-75)."""
+
+    def __init__(self, ctx: FrameTransformContext):
+        self._lib = load()
+        self.ctx = ctx
+        self._h = self._lib.VideoFrameTransform_new(C.byref(ctx))
+        if not self._h:
+            raise MemoryError("VideoFrameTransform_new returned NULL")
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.VideoFrameTransform_delete(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # -- the reference API ------------------------------------------------------------------------
+    def generateMapForPlane(self, inputWidth, inputHeight, outputWidth, outputHeight, transformMatPlaneIndex) -> bool:
+        return bool(self._lib.VideoFrameTransform_generateMapForPlane(
+            self._h, inputWidth, inputHeight, outputWidth, outputHeight, transformMatPlaneIndex))
+
+    def transformFramePlane(self, inputData, outputData, inputWidth, inputHeight, inputWidthWithPadding,
+                            outputWidth, outputHeight, outputWidthWithPadding, transformMatPlaneIndex,
+                            imagePlaneIndex) -> bool:
+        """inputData / outputData: raw addresses (int) of host or CUDA device memory, as in the C call."""
+        return bool(self._lib.VideoFrameTransform_transformFramePlane(
+            self._h, inputData, outputData, inputWidth, inputHeight, inputWidthWithPadding, outputWidth,
+            outputHeight, outputWidthWithPadding, transformMatPlaneIndex, imagePlaneIndex))
+
+    # -- conveniences over numpy planes (host path of the C-ABI) -----------------------------
+    def transform_plane(self, src: np.ndarray, out_w: int, out_h: int, plan_index: int, image_plane: int = 0,
+                        out: np.ndarray | None = None) -> np.ndarray:
+        assert src.dtype == np.uint8 and src.ndim == 2 and src.strides[1] == 1
+        if out is None:
+            out = np.zeros((out_h, out_w), np.uint8)
+        assert out.dtype == np.uint8 and out.shape == (out_h, out_w) and out.strides[1] == 1
+        ok = self.transformFramePlane(src.ctypes.data, out.ctypes.data, src.shape[1], src.shape[0], src.strides[0],
+                                      out_w, out_h, out.strides[0], plan_index, image_plane)
+        if not ok:
+            raise RuntimeError("VideoFrameTransform_transformFramePlane returned 0 (message on stdout)")
+        return out
+
+    # -- extensions -------------------------------------------------------------------------------
+    def transform_plane_async(self, d_in: int, d_out: int, in_w, in_h, in_pitch, out_w, out_h, out_pitch, plan_index,
+                              stream: int = 0) -> bool:
+        return bool(self._lib.T360B200_transformFramePlaneAsync(self._h, d_in, d_out, in_w, in_h, in_pitch, out_w,
+                                                                out_h, out_pitch, plan_index, stream))
+
+    def low_pass_async(self, d_in: int, d_out: int, w, h, in_pitch, out_pitch, plan_index, stream: int = 0) -> bool:
+        return bool(self._lib.T360B200_lowPassPlaneAsync(self._h, d_in, d_out, w, h, in_pitch, out_pitch, plan_index,
+                                                         stream))
+
+    def synchronize(self) -> bool:
+        return bool(self._lib.T360B200_synchronize(self._h))
+
+    @property
+    def stream(self) -> int:
+        return self._lib.T360B200_stream(self._h) or 0
+
+    def plan_device_bytes(self, plan_index) -> int:
+        return int(self._lib.T360B200_planDeviceBytes(self._h, plan_index))
+
+
+class HostPlan:
+    """Host-side plan of one plane, computed without touching CUDA (T360B200_hostPlan*)."""
+
+    def __init__(self, ctx: FrameTransformContext, in_w, in_h, out_w, out_h):
+        self._lib = load()
+        self._h = self._lib.T360B200_hostPlanCreate(C.byref(ctx), in_w, in_h, out_w, out_h)
+        if not self._h:
+            raise ValueError("T360B200_hostPlanCreate failed (message on stdout)")
+        info = (C.c_int * 6)()
+        self._lib.T360B200_hostPlanInfo(self._h, info)
+        self.map_w, self.map_h, self.num_segments, self.num_taps, self.kernel_size = info[0], info[1], info[2], info[3], info[4]
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.T360B200_hostPlanDestroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    @property
+    def map(self) -> np.ndarray:
+        p = self._lib.T360B200_hostPlanMap(self._h)
+        n = self.map_w * self.map_h * 2
+        return np.frombuffer((C.c_float * n).from_address(p), np.float32).reshape(self.map_h, self.map_w, 2).copy()
+
+    @property
+    def samples(self) -> np.ndarray:
+        p = self._lib.T360B200_hostPlanSamples(self._h)
+        n = self.map_w * self.map_h * 2
+        return np.frombuffer((C.c_int32 * n).from_address(p), np.int32).reshape(self.map_h, self.map_w, 2).copy()
+
+    def segments(self):
+        out = []
+        rect, nk = (C.c_int * 4)(), (C.c_int * 2)()
+        kx, ky = C.c_void_p(), C.c_void_p()
+        for i in range(self.num_segments):
+            assert self._lib.T360B200_hostPlanSegment(self._h, i, rect, nk, C.byref(kx), C.byref(ky))
+            a = np.frombuffer((C.c_float * nk[0]).from_address(kx.value), np.float32).copy()
+            b = np.frombuffer((C.c_float * nk[1]).from_address(ky.value), np.float32).copy()
+            out.append((rect[0], rect[1], rect[2], rect[3], a, b))
+        return out
+
+
+def remap_table(interpolation_alg: int) -> np.ndarray | None:
+    L = load()
+    p = C.c_void_p()
+    k = L.T360B200_remapTable(interpolation_alg, C.byref(p))
+    if k < 2:
+        return None
+    return np.frombuffer((C.c_int16 * (1024 * k * k)).from_address(p.value), np.int16).reshape(1024, k, k).copy()
+
+
+def kernel_launch_count() -> int:
+    return int(load().T360B200_kernelLaunchCount())
+
+
+def device_count() -> int:
+    return int(load().T360B200_deviceCount())
