@@ -1,0 +1,394 @@
+#!/usr/bin/env python
+"""bench.py -- Mpixels/s of the projection-remap hot path on synthetic 8K equirect frames (BASELINE.json).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config cfg2|cfg3|cfg4] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A step = one yuv420p frame (3 planes) through the hot path ([segmented low-pass] -> gather).  Default
+workload = BASELINE.json configs[1] ("cfg2": MONO 7680x3840 equirect -> CUBEMAP_32 edge 1280 = 3840x2560,
+bicubic, low-pass off).  Mpx/s counts INPUT-plane pixels consumed.
+
+Legs (one JSON line on rank 0):
+  value         frames resident in HBM, T360B200_transformFramePlaneAsync per plane, CUDA events on the launch
+                stream, barrier + synchronize on both sides, max over ranks.  Inputs rotate through a ring larger
+                than L2 so every step reads its frame from HBM.
+  e2e           same metric through the reference's own C-ABI (VideoFrameTransform_transformFramePlane) with
+                pinned HOST planes: H2D of the inputs and D2H of the outputs are inside the timed region.
+  roofline      luma gather kernel: algorithmic bytes (inW*inH + outW*outH) / its CUDA-event
+                duration inside the timed region / measured HBM peak (MEASURED_PEAKS.json).
+  cpu_baseline  the reference's own CPU path (oracle/_ref: unmodified reference sources driving cv2) on this
+                box's host cores, bounded sample (N=1, rank 0 only).
+  --impl reference   only that CPU path, as its own JSON line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+METRIC = "Mpixels/s 8K equirect->cubemap bicubic (input-plane pixels consumed per second)"
+
+CONFIGS = {  # BASELINE.json configs[1..3]
+    "cfg2": dict(desc="MONO 7680x3840 equirect -> CUBEMAP_32 edge 1280 (3840x2560), bicubic, low-pass off, yuv420p frame (3 planes)",
+                 ov=dict(interpolation_alg=2, enable_low_pass_filter=0), inp=(7680, 3840), out=(3840, 2560)),
+    "cfg3": dict(desc="cfg2 + low-pass: num_horizontal_segments=32 num_vertical_segments=15 adjust_kernel=1",
+                 ov=dict(interpolation_alg=2, enable_low_pass_filter=1, num_horizontal_segments=32, num_vertical_segments=15,
+                         adjust_kernel=1), inp=(7680, 3840), out=(3840, 2560)),
+    "cfg4": dict(desc="TOP_BOTTOM stereo 7680x7680 equirect -> EAC_32 (3840x5120), Lanczos4, low-pass on, yuv420p frame",
+                 ov=dict(input_stereo_format=0, output_stereo_format=0, output_layout=6, interpolation_alg=4,
+                         enable_low_pass_filter=1, num_horizontal_segments=32, num_vertical_segments=15, adjust_kernel=1),
+                 inp=(7680, 7680), out=(3840, 5120)),
+}
+
+
+def measured_hbm_peak():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons while the timed regions run."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,utilization.gpu,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "50"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.split(",") for r in Path(self.f.name).read_text().splitlines() if r.count(",") >= 7]
+        os.unlink(self.f.name)
+        sm, reasons, busy = [], set(), []
+        for r in rows:
+            try:
+                r = [c.strip() for c in r]
+                clk, mx, util = float(r[0]), float(r[1]), float(r[3])
+            except ValueError:
+                continue
+            sm.append(clk)
+            if util > 0:
+                busy.append(clk)
+            out["sm_max_mhz"] = mx
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        use = busy or sm
+        if use:
+            out["sm_mhz"] = statistics.median(use)
+        out["samples"] = len(sm)
+        out["samples_under_load"] = len(busy)
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+# ------------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the reference's own CPU implementation of the path on the host cores
+# ------------------------------------------------------------------------------------------------------
+def reference_cpu_run(cfg, steps, warmup, budget_s=None):
+    """Times `steps` frames (3 planes each) through oracle/_ref + cv2 (kind 'reference'), or through the plain-C
+    oracle port when the compiled reference is absent (kind 'port').  Plans are built outside the timed region,
+    like on the GPU side.  Returns (seconds_per_step list, kind, cores, sample description)."""
+    from oracle import ref_harness as rh
+    from transform360_b200 import synth
+    from transform360_b200.stream import StreamSpec
+    spec = StreamSpec(cfg["inp"][0], cfg["inp"][1], cfg["out"][0], cfg["out"][1])
+    frames = [[synth.noise_plane(*spec.plane_dims(p)[:2], plane=p, frame=f) for p in range(3)] for f in range(2)]
+    cores = os.cpu_count() or 1
+    if rh.ref_available():
+        import cv2
+        cv2.setNumThreads(cores)
+        ref = rh.RefTransform(rh.default_context(**cfg["ov"]))
+        for idx, plane in ((0, 0), (1, 1)):
+            iw, ih, ow, oh, _ = spec.plane_dims(plane)
+            assert ref.generate_map(iw, ih, ow, oh, idx)
+
+        def one(frame):
+            for p in range(3):
+                iw, ih, ow, oh, idx = spec.plane_dims(p)
+                ref.transform_plane(frame[p], ow, oh, idx, image_plane=p)
+        kind, used = "reference", cores
+    else:
+        from oracle import c_oracle as co
+        octx = rh.default_context(**cfg["ov"])
+        plans = [co.OraclePlan(octx, *spec.plane_dims(p)[:4]) for p in (0, 1)]
+
+        def one(frame):
+            for p in range(3):
+                iw, ih, ow, oh, idx = spec.plane_dims(p)
+                co.transform_plane(octx, plans[idx], frame[p], ow, oh, map_index=idx)
+        kind, used = "port", 1
+    for i in range(warmup):
+        one(frames[i % 2])
+    times = []
+    t_begin = time.perf_counter()
+    for i in range(steps):
+        t0 = time.perf_counter()
+        one(frames[i % 2])
+        times.append(time.perf_counter() - t0)
+        if budget_s and time.perf_counter() - t_begin > budget_s:
+            break
+    sample = (f"{len(times)} yuv420p frames of the workload ({'unmodified reference sources + cv2 ' + __import__('cv2').__version__ if kind == 'reference' else 'plain-C oracle port'}), "
+              f"{used} host thread(s), plans prebuilt, noise frames")
+    return times, kind, used, sample
+
+
+def run_reference_arm(args, cfg, rank):
+    if rank != 0:
+        return
+    times, kind, cores, sample = reference_cpu_run(cfg, args.steps, max(args.warmup, 1))
+    from transform360_b200.stream import StreamSpec
+    spec = StreamSpec(cfg["inp"][0], cfg["inp"][1], cfg["out"][0], cfg["out"][1])
+    px = spec.input_pixels_per_frame()
+    total = sum(times)
+    v = px * len(times) / total / 1e6
+    line = {
+        "impl": "reference", "metric": METRIC, "value": round(v, 2), "unit": "Mpx/s", "n_gpus": args.gpus, "steps": len(times),
+        "warmup": max(args.warmup, 1), "ms_per_step": round(1e3 * total / len(times), 3), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": f"{args.config}: {cfg['desc']}", "engine": "reference CPU path on host cores"},
+        "cpu_baseline": {"value": round(v, 2), "unit": "Mpx/s", "cores": cores, "kind": kind, "sample": sample,
+                         "best_ms_per_step": round(1e3 * min(times), 3)},
+        "e2e": {"value": round(v, 2), "unit": "Mpx/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--config", default="cfg2", choices=sorted(CONFIGS))
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the host-pointer leg (default min(steps, 100))")
+    ap.add_argument("--skip-e2e", action="store_true")
+    ap.add_argument("--skip-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-steps", type=int, default=12)
+    args = ap.parse_args()
+    cfg = CONFIGS[args.config]
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    args.warmup = max(args.warmup, 3)
+
+    if args.impl == "reference":
+        run_reference_arm(args, cfg, rank)
+        return
+
+    import numpy as np
+    import torch
+    import transform360_b200 as t360
+    from transform360_b200 import synth
+    from transform360_b200.stream import FrameTransformer, StreamSpec, broadcast_parameters
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product has no CPU fallback; use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    if world != args.gpus and rank == 0:
+        print(f"bench.py: note: WORLD_SIZE={world} but --gpus {args.gpus}; using WORLD_SIZE", file=sys.stderr)
+
+    # ---- parameters: rank 0 decides, one NCCL broadcast of 112 + 28 bytes (the path's only collective) -----
+    ctx = spec = None
+    if rank == 0:
+        ctx = t360.make_context(**cfg["ov"])
+        spec = StreamSpec(cfg["inp"][0], cfg["inp"][1], cfg["out"][0], cfg["out"][1])
+    ctx, spec = broadcast_parameters(ctx, spec, rank, world, device=dev)
+    t_plan = time.perf_counter()
+    ft = FrameTransformer(ctx, spec)
+    plan_seconds = time.perf_counter() - t_plan
+    in_px, out_px = spec.input_pixels_per_frame(), spec.output_pixels_per_frame()
+
+    # ---- device-resident ring of frames, larger than L2 (126 MB) so that every step streams from HBM ----------
+    frame_bytes = in_px
+    ring = max(4, -(-200_000_000 // frame_bytes))
+    pitch = lambda w: (w + 255) // 256 * 256
+    d_in, d_out = [], []
+    for f in range(ring):
+        gframe = rank + f * world  # global frame index handled by this rank (round-robin sharding)
+        planes = []
+        for p in range(3):
+            iw, ih, ow, oh, _ = spec.plane_dims(p)
+            planes.append(synth.noise_plane_torch(iw, ih, plane=p, frame=gframe, device=dev, pitch=pitch(iw)))
+        d_in.append(planes)
+    for f in range(2):
+        d_out.append([torch.zeros((spec.plane_dims(p)[3], pitch(spec.plane_dims(p)[2])), dtype=torch.uint8, device=dev) for p in range(3)])
+    in_args = [[(t.data_ptr(), t.stride(0)) for t in fr] for fr in d_in]
+    out_args = [[(t.data_ptr(), t.stride(0)) for t in fr] for fr in d_out]
+    # a real (non-default) stream: handle 0 would make the library fall back to its own stream and the events
+    # below would not bracket the kernels
+    tstream = torch.cuda.Stream(device=dev)
+    stream = tstream.cuda_stream
+    assert stream != 0
+    liw, lih, low, loh, _ = spec.plane_dims(0)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def step_device(i, ev=None):
+        fin, fout = in_args[i % ring], out_args[i % 2]
+        if ev is not None:
+            ev[0].record(tstream)
+        if not ft.vft.transform_plane_async(fin[0][0], fout[0][0], liw, lih, fin[0][1], low, loh, fout[0][1], 0, stream):
+            raise RuntimeError("luma plane failed")
+        if ev is not None:
+            ev[1].record(tstream)
+        for p in (1, 2):
+            iw, ih, ow, oh, idx = spec.plane_dims(p)
+            if not ft.vft.transform_plane_async(fin[p][0], fout[p][0], iw, ih, fin[p][1], ow, oh, fout[p][1], idx, stream):
+                raise RuntimeError("chroma plane failed")
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    torch.cuda.synchronize()  # the ring was filled on torch's default stream
+    for i in range(args.warmup):
+        step_device(i)
+    barrier()
+    K = args.steps
+    luma_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = t360.kernel_launch_count()
+    e0.record(tstream)
+    for i in range(K):
+        step_device(i, luma_ev[i])
+    e1.record(tstream)
+    barrier()
+    launches = t360.kernel_launch_count() - launches0
+    ms_total = e0.elapsed_time(e1)
+    luma_ms = [a.elapsed_time(b) for a, b in luma_ev]
+    t_max = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_max, op=dist.ReduceOp.MAX)
+    ms_total_max = float(t_max.item())
+    value = in_px * K * world / (ms_total_max * 1e-3) / 1e6
+
+    # ---- end to end through the reference-facing C-ABI with pinned host planes ------------------------------------
+    e2e = None
+    if not args.skip_e2e:
+        Ke = args.e2e_steps or min(K, 100)
+        h_ring = 2
+        h_in = [[torch.empty((spec.plane_dims(p)[1], spec.plane_dims(p)[0]), dtype=torch.uint8).pin_memory() for p in range(3)]
+                for _ in range(h_ring)]
+        for f in range(h_ring):
+            for p in range(3):
+                h_in[f][p].copy_(d_in[f][p][:, :spec.plane_dims(p)[0]].cpu())
+        h_out = [[torch.empty((spec.plane_dims(p)[3], spec.plane_dims(p)[2]), dtype=torch.uint8).pin_memory() for p in range(3)]
+                 for _ in range(h_ring)]
+        hin_args = [[(t.data_ptr(), t.stride(0)) for t in fr] for fr in h_in]
+        hout_args = [[(t.data_ptr(), t.stride(0)) for t in fr] for fr in h_out]
+        lib_stream = torch.cuda.ExternalStream(ft.vft.stream, device=dev)
+        for i in range(3):
+            ft.transform_frame_host(hin_args[i % h_ring], hout_args[i % h_ring])
+        barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        w0 = time.perf_counter()
+        s0.record(lib_stream)
+        for i in range(Ke):
+            ft.transform_frame_host(hin_args[i % h_ring], hout_args[i % h_ring])
+        s1.record(lib_stream)
+        barrier()
+        wall_ms = (time.perf_counter() - w0) * 1e3
+        ms_e2e = max(s0.elapsed_time(s1), 0.0)
+        ms_e2e = max(ms_e2e, wall_ms * 0.5) if ms_e2e <= 0 else ms_e2e
+        t2 = torch.tensor([ms_e2e, wall_ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+        ms_e2e, wall_ms = float(t2[0].item()), float(t2[1].item())
+        e2e = {"value": round(in_px * Ke * world / (ms_e2e * 1e-3) / 1e6, 1), "unit": "Mpx/s", "steps": Ke,
+               "ms_per_step": round(ms_e2e / Ke, 4), "wall_ms_per_step": round(wall_ms / Ke, 4),
+               "h2d_bytes_per_step": in_px, "d2h_bytes_per_step": out_px,
+               "api": "VideoFrameTransform_transformFramePlane x3 planes, pinned host planes, synchronous"}
+        # sanity: the host path and the device path produce the same bytes for the same frame
+        ft.transform_frame_host(hin_args[0], hout_args[0])
+        step_device(0)
+        torch.cuda.synchronize()
+        same = all(torch.equal(h_out[0][p], d_out[0][p][:, :spec.plane_dims(p)[2]].cpu()) for p in range(3))
+        e2e["matches_device_leg"] = bool(same)
+    clocks = sampler.stop() if sampler else None
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (luma gather) --------------------------------------------------------------
+    peak, peak_src = measured_hbm_peak()
+    luma_bytes = liw * lih + low * loh
+    luma_avg_ms = statistics.mean(luma_ms)
+    achieved = luma_bytes / (luma_avg_ms * 1e-3) / 1e9
+    traffic = None
+    tp = ROOT / "profiles" / "traffic.json"
+    if tp.exists():
+        try:
+            traffic = json.loads(tp.read_text()).get(args.config, {}).get("luma_gather_dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "kernel": "gatherKernel (luma plane)" if not cfg["ov"].get("enable_low_pass_filter") else "blurTileKernel + gatherKernel (luma plane)",
+                "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
+                "traffic": traffic, "algorithmic_bytes_per_launch": luma_bytes, "avg_launch_ms": round(luma_avg_ms, 5),
+                "median_launch_ms": round(statistics.median(luma_ms), 5),
+                "read_only_frac": round(liw * lih / (luma_avg_ms * 1e-3) / 1e9 / peak, 4), "peak_source": peak_src}
+
+    cpu_baseline = None
+    if world == 1 and not args.skip_cpu_baseline:
+        times, kind, cores, sample = reference_cpu_run(cfg, args.cpu_steps, 2, budget_s=30.0)
+        cpu_baseline = {"value": round(in_px * len(times) / sum(times) / 1e6, 1), "unit": "Mpx/s", "cores": cores, "kind": kind,
+                        "sample": sample, "best": round(in_px / min(times) / 1e6, 1)}
+
+    line = {
+        "metric": METRIC, "value": round(value, 1), "unit": "Mpx/s", "n_gpus": world, "steps": K, "warmup": args.warmup,
+        "ms_per_step": round(ms_total_max / K, 5), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u8", "data": "synthetic",
+        "config": {"workload": f"{args.config}: {cfg['desc']}", "frames_resident_ring": ring,
+                   "l2": f"inputs larger than L2: ring of {ring} x {frame_bytes / 1e6:.1f} MB frames per GPU",
+                   "sharding": "frames round-robin over ranks; one NCCL broadcast of context+dims; no pixel traffic",
+                   "output_mpx_per_s": round(out_px * K * world / (ms_total_max * 1e-3) / 1e6, 1),
+                   "frames_per_s": round(K * world / (ms_total_max * 1e-3), 1), "plan_seconds": round(plan_seconds, 3),
+                   "tiles_luma[tma_staged,general,lowpass_smem,lowpass_direct]": list(ft.vft.plan_tile_counts(0)),
+                   "tiles_chroma": list(ft.vft.plan_tile_counts(1))},
+        "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -142,12 +142,11 @@ def _remap_hook(src, srows, scols, sstep, dst, drows, dcols, dstep, mp, mstep, i
         mbuf = (C.c_float * ((mstep // 4) * (drows - 1) + dcols * 2)).from_address(mp)
         m = np.lib.stride_tricks.as_strided(np.frombuffer(mbuf, np.float32), shape=(drows, dcols, 2),
                                             strides=(mstep, 8, 4))
-        if border == 5:  # BORDER_TRANSPARENT: dst keeps its previous content where unmapped
-            out = np.ascontiguousarray(d)
-            cv2.remap(np.ascontiguousarray(s), np.ascontiguousarray(m), None, interp, dst=out, borderMode=border)
-        else:
-            out = cv2.remap(np.ascontiguousarray(s), np.ascontiguousarray(m), None, interp, borderMode=border)
-        d[...] = out
+        # write straight into the caller's plane (a strided view is a valid cv::Mat); under
+        # BORDER_TRANSPARENT dst keeps its previous content where unmapped
+        out = cv2.remap(s, m, None, interp, dst=d, borderMode=border)
+        if not np.shares_memory(out, d):
+            d[...] = out
         return 0
     except Exception as e:  # pragma: no cover
         print("remap hook error:", e)

@@ -1,23 +1,33 @@
 // sm_100a kernels of the projection-remap hot path.
 //
-//   gatherKernel<K>   replaces cv::remap as the reference calls it (VideoFrameTransform.cpp:748-754):
-//                     per output pixel a K x K window of the 8-bit source is weighted with OpenCV's
-//                     15-bit fixed-point table and rounded with (sum + 16384) >> 15.  Bit-exact by
-//                     construction: same table (host-built, sampling.cpp), same integer arithmetic.
-//   blurTileKernel    replaces cv::sepFilter2D over the reference's tiles (cpp:173-204, 579-704):
-//                     separable Gaussian, float32, fused multiply-add chain in the order cv2 4.13 uses
-//                     (see oracle/t360_oracle.c for the model and its pin), round-half-even, u8.
+//   gatherStagedKernel<K>  replaces cv::remap as the reference calls it (VideoFrameTransform.cpp:748-754):
+//   gatherKernel<K>        per output pixel a K x K window of the 8-bit source is weighted with OpenCV's
+//                          15-bit fixed-point table and rounded with (sum + 16384) >> 15.  Bit-exact by
+//                          construction: same table (host-built, sampling.cpp), same integer arithmetic.
+//   blurTileKernel         replaces cv::sepFilter2D over the reference's tiles (cpp:173-204, 579-704):
+//                          separable Gaussian, float32, fused multiply-add chain in the order cv2 4.13 uses
+//                          (see oracle/t360_oracle.c for the model and its pin), round-half-even, u8.
 //
-// This is an HBM / issue-bound gather, not a contraction: no tensor cores.  What matters here is
-//   * coalescing: a warp owns 128 consecutive output pixels of one row, a thread 4 of them: one 128-bit
-//     read of the sampling plan and one 32-bit store per thread, 128 B per warp;
-//   * word-wide taps: the K source bytes of one window row are fetched as 2 (K<=4) or 3 (K=8) aligned
-//     32-bit words through the read-only path and aligned with a funnel shift, then folded with IDP.2A
-//     (two s16 x u8 MACs per instruction);
-//   * the weight table lives in shared memory, transposed so that random phases spread over banks;
-//   * a persistent grid (multiple of the SM count) loads that table once per CTA.
+// This is a gather, not a contraction: no tensor cores.  What the design is built around:
+//   * A warp owns 32 adjacent output columns x 4 rows; lane L computes column L one row at a time, so a
+//     warp-wide tap read covers ~48 contiguous source bytes per source row.  Plan reads are 8 B per lane
+//     (256 contiguous bytes per warp), stores 1 B per lane (one full 32-byte sector per warp).
+//   * Staged path (the bulk of every plane): the source window of a 32 x 32 (K=8: 32 x 64) output tile is
+//     brought into shared memory by ONE cp.async.bulk.tensor.2d (TMA) box load from the pitch-linear
+//     plane, double-buffered against the arithmetic through mbarriers; taps are then read as aligned
+//     32-bit shared-memory words (bank-granular, no 32-byte-sector waste: the same reads through L1
+//     measured 13-26 sectors per request) and aligned with a funnel shift.
+//   * Every window row is folded with IDP.2A: two s16 x u8 multiply-adds per instruction.
+//   * The 1024-phase weight table sits in shared memory, transposed so that unrelated phases spread
+//     over bank groups; persistent CTAs (grid = multiple of the SM count) stage it once.
+//   * Tiles whose window does not fit the box, touches a plane border (BORDER_WRAP wraps rows AND
+//     columns, cpp:719) or belongs to a BORDER_TRANSPARENT plan go through gatherKernel, which reads taps
+//     through L1 and handles every border case.
 #include "kernels.cuh"
 
+#include <cuda.h>  // CUtensorMap (type only; no libcuda symbol is referenced)
+
+#include <algorithm>
 #include <atomic>
 
 namespace t360 {
@@ -26,8 +36,7 @@ namespace {
 
 std::atomic<unsigned long long> gLaunches{0};
 
-constexpr int kGatherPxPerThread = 4;
-constexpr int kGatherTileW = 32 * kGatherPxPerThread;  // one warp row
+constexpr int kRowsPerThread = 4;
 
 __device__ __forceinline__ int dp2aLo(uint32_t w, uint32_t b, int acc) {
   int d;
@@ -41,10 +50,9 @@ __device__ __forceinline__ int dp2aHi(uint32_t w, uint32_t b, int acc) {
 }
 
 // the sampling plan is streamed once per frame: read-only path, do not allocate in L1
-__device__ __forceinline__ int4 loadPlan(const int4* p) {
-  int4 r;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0, %1, %2, %3}, [%4];"
-               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+__device__ __forceinline__ int2 loadPlan(const int2* p) {
+  int2 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.s32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
   return r;
 }
 
@@ -60,25 +68,13 @@ __device__ __forceinline__ int reflect101(int p, int n) {  // what remap uses fo
 }
 
 template <int K>
-struct SmemTable;
-template <>
-struct SmemTable<2> {
-  static constexpr int kBytes = 1024 * 8;
-};
-template <>
-struct SmemTable<4> {
-  static constexpr int kBytes = 1024 * 32;
-};
-template <>
-struct SmemTable<8> {
-  static constexpr int kBytes = 1024 * 128;
-};
+__host__ __device__ constexpr int weightBytes() { return 1024 * K * K * 2; }
 
 // Copies the [1024][K][K] int16 table into shared memory as [K*K/8][1024] 16-byte vectors (K >= 4) or
-// [1024] 8-byte vectors (K == 2), so that lanes with unrelated phases hit different banks.
+// [1024] 8-byte vectors (K == 2), so that lanes with unrelated phases hit different bank groups.
 template <int K>
 __device__ __forceinline__ void stageWeights(const int16_t* __restrict__ g, unsigned char* smem) {
-  if (K == 2) {
+  if constexpr (K == 2) {
     const uint2* src = reinterpret_cast<const uint2*>(g);
     uint2* dst = reinterpret_cast<uint2*>(smem);
     for (int i = threadIdx.x; i < 1024; i += blockDim.x) dst[i] = __ldg(src + i);
@@ -90,6 +86,55 @@ __device__ __forceinline__ void stageWeights(const int16_t* __restrict__ g, unsi
   }
 }
 
+// K x K window whose rows are `pitch` bytes apart starting at byte offset `off` of a 4-byte aligned base
+// (global through the read-only path, or shared).  No bounds handling: the caller guarantees the window
+// (plus the tail of its last aligned word) is readable.
+template <int K, bool SHARED>
+__device__ __forceinline__ int foldWindow(const uint32_t* __restrict__ words, int off, int pitch,
+                                          const unsigned char* wsmem, int phase) {
+  auto ld = [&](int wordIndex) -> uint32_t { return SHARED ? words[wordIndex] : __ldg(words + wordIndex); };
+  int acc = 0;
+  if constexpr (K == 2) {
+    const uint2 wt = reinterpret_cast<const uint2*>(wsmem)[phase];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const uint32_t b = __funnelshift_r(ld(off >> 2), ld((off >> 2) + 1), (off & 3) * 8);
+      acc = dp2aLo(r == 0 ? wt.x : wt.y, b, acc);
+      off += pitch;
+    }
+  } else if constexpr (K == 4) {
+    const uint4* tab = reinterpret_cast<const uint4*>(wsmem);
+    const uint4 wa = tab[phase], wb = tab[1024 + phase];
+    const uint32_t w01[4] = {wa.x, wa.z, wb.x, wb.z}, w23[4] = {wa.y, wa.w, wb.y, wb.w};
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const uint32_t b = __funnelshift_r(ld(off >> 2), ld((off >> 2) + 1), (off & 3) * 8);
+      acc = dp2aLo(w01[r], b, acc);
+      acc = dp2aHi(w23[r], b, acc);
+      off += pitch;
+    }
+  } else {
+    const uint4* tab = reinterpret_cast<const uint4*>(wsmem);
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const uint4 wt = tab[r * 1024 + phase];
+      const uint32_t q0 = ld(off >> 2), q1 = ld((off >> 2) + 1), q2 = ld((off >> 2) + 2);
+      const int sh = (off & 3) * 8;
+      const uint32_t b0 = __funnelshift_r(q0, q1, sh), b1 = __funnelshift_r(q1, q2, sh);
+      acc = dp2aLo(wt.x, b0, acc);
+      acc = dp2aHi(wt.y, b0, acc);
+      acc = dp2aLo(wt.z, b1, acc);
+      acc = dp2aHi(wt.w, b1, acc);
+      off += pitch;
+    }
+  }
+  return acc;
+}
+
+__device__ __forceinline__ int roundToByte(int acc) {  // FixedPtCast<int, uchar, 15>
+  return min(max((acc + (1 << 14)) >> 15, 0), 255);
+}
+
 struct SrcView {
   const uint32_t* words;  // source plane base rounded down to 4 bytes
   const uint8_t* bytes;   // true base
@@ -97,94 +142,43 @@ struct SrcView {
   int w, h, pitch;
 };
 
-// One output pixel.  Returns the 8-bit value, or -1 when BORDER_TRANSPARENT leaves the pixel untouched.
+// One output pixel through L1, any border case.  Returns the 8-bit value, or -1 when BORDER_TRANSPARENT
+// leaves the pixel untouched.
 template <int K, bool TRANSPARENT>
-__device__ __forceinline__ int gatherPixel(const SrcView& s, const unsigned char* smem, int col0, int rowPhase) {
+__device__ __forceinline__ int gatherPixel(const SrcView& s, const unsigned char* wsmem, int col0, int rowPhase) {
   const int row0 = rowPhase >> 10, phase = rowPhase & 1023;
-  int acc = 0;
   // interior: no wrapping, and the aligned word reads stay inside the row (col0 + K + 3 <= w)
   const bool interior = col0 >= 0 && row0 >= 0 && col0 + K + 3 <= s.w && row0 + K <= s.h;
-  if (interior) {
-    int off = row0 * s.pitch + col0 + s.misalign;
-    if (K == 2) {
-      const uint2 wt = reinterpret_cast<const uint2*>(smem)[phase];
-#pragma unroll
-      for (int r = 0; r < 2; ++r) {
-        const uint32_t* p = s.words + (off >> 2);
-        const uint32_t b = __funnelshift_r(__ldg(p), __ldg(p + 1), (off & 3) * 8);
-        acc = dp2aLo(r == 0 ? wt.x : wt.y, b, acc);
-        off += s.pitch;
-      }
-    } else if (K == 4) {
-      const uint4* tab = reinterpret_cast<const uint4*>(smem);
-      const uint4 wa = tab[phase], wb = tab[1024 + phase];
-      const uint32_t w01[4] = {wa.x, wa.z, wb.x, wb.z}, w23[4] = {wa.y, wa.w, wb.y, wb.w};
-#pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        const uint32_t* p = s.words + (off >> 2);
-        const uint32_t b = __funnelshift_r(__ldg(p), __ldg(p + 1), (off & 3) * 8);
-        acc = dp2aLo(w01[r], b, acc);
-        acc = dp2aHi(w23[r], b, acc);
-        off += s.pitch;
-      }
-    } else {
-      const uint4* tab = reinterpret_cast<const uint4*>(smem);
-#pragma unroll
-      for (int r = 0; r < 8; ++r) {
-        const uint4 wt = tab[r * 1024 + phase];
-        const uint32_t* p = s.words + (off >> 2);
-        const uint32_t q0 = __ldg(p), q1 = __ldg(p + 1), q2 = __ldg(p + 2);
-        const int sh = (off & 3) * 8;
-        const uint32_t b0 = __funnelshift_r(q0, q1, sh), b1 = __funnelshift_r(q1, q2, sh);
-        acc = dp2aLo(wt.x, b0, acc);
-        acc = dp2aHi(wt.y, b0, acc);
-        acc = dp2aLo(wt.z, b1, acc);
-        acc = dp2aHi(wt.w, b1, acc);
-        off += s.pitch;
-      }
-    }
-  } else {
-    // window touches an edge: per-tap addressing.  BORDER_WRAP wraps columns AND rows (reference cpp:719).
-    if (TRANSPARENT) {
-      const bool inlier = col0 >= 0 && row0 >= 0 && col0 + K <= s.w && row0 + K <= s.h;
-      if (K == 2 && !inlier) return -1;  // remapBilinear leaves every non-inlier alone
-      const int ax = col0 + (K / 2 - 1), ay = row0 + (K / 2 - 1);
-      if ((unsigned)ax >= (unsigned)s.w || (unsigned)ay >= (unsigned)s.h) return -1;
-    }
-    const int16_t* wt;
-    int strideR, strideC;  // in int16 units, matching the transposed shared layout
-    if (K == 2) {
-      wt = reinterpret_cast<const int16_t*>(smem) + phase * 4;
-      strideR = 2; strideC = 1;
-    } else {
-      wt = reinterpret_cast<const int16_t*>(smem) + phase * 8;
-      strideR = 0; strideC = 0;  // handled below
-    }
+  if (interior)
+    return roundToByte(foldWindow<K, false>(s.words, row0 * s.pitch + col0 + s.misalign, s.pitch, wsmem, phase));
+
+  // window touches an edge: per-tap addressing.  BORDER_WRAP wraps columns AND rows (reference cpp:719).
+  if (TRANSPARENT) {
+    const bool inlier = col0 >= 0 && row0 >= 0 && col0 + K <= s.w && row0 + K <= s.h;
+    if (K == 2 && !inlier) return -1;  // remapBilinear leaves every non-inlier alone
+    const int ax = col0 + (K / 2 - 1), ay = row0 + (K / 2 - 1);
+    if ((unsigned)ax >= (unsigned)s.w || (unsigned)ay >= (unsigned)s.h) return -1;
+  }
+  const int16_t* wt = reinterpret_cast<const int16_t*>(wsmem) + phase * (K == 2 ? 4 : 8);
+  int acc = 0;
 #pragma unroll 1
-    for (int r = 0; r < K; ++r) {
-      const int yy = TRANSPARENT ? reflect101(row0 + r, s.h) : wrapIndex(row0 + r, s.h);
-      const uint8_t* rowp = s.bytes + (size_t)yy * s.pitch;
+  for (int r = 0; r < K; ++r) {
+    const int yy = TRANSPARENT ? reflect101(row0 + r, s.h) : wrapIndex(row0 + r, s.h);
+    const uint8_t* rowp = s.bytes + (size_t)yy * s.pitch;
 #pragma unroll 1
-      for (int c = 0; c < K; ++c) {
-        const int xx = TRANSPARENT ? reflect101(col0 + c, s.w) : wrapIndex(col0 + c, s.w);
-        int w;
-        if (K == 2) {
-          w = wt[r * strideR + c * strideC];
-        } else {
-          // element (r, c) of the phase lives in vector v = (r*K + c) / 8, lane (r*K + c) % 8
-          const int e = r * K + c;
-          w = wt[(e >> 3) * 1024 * 8 + (e & 7)];
-        }
-        acc += w * (int)__ldg(rowp + xx);
-      }
+    for (int c = 0; c < K; ++c) {
+      const int xx = TRANSPARENT ? reflect101(col0 + c, s.w) : wrapIndex(col0 + c, s.w);
+      const int e = r * K + c;  // element (r, c) lives in vector e / 8, lane e % 8 of the transposed table
+      const int w = K == 2 ? wt[e] : wt[(e >> 3) * 1024 * 8 + (e & 7)];
+      acc += w * (int)__ldg(rowp + xx);
     }
   }
-  const int v = (acc + (1 << 14)) >> 15;
-  return min(max(v, 0), 255);
+  return roundToByte(acc);
 }
 
 template <int K, bool TRANSPARENT>
-__global__ void __launch_bounds__(K == 8 ? 512 : 256) gatherKernel(GatherParams p, int tilesX, int numTiles) {
+__global__ void __launch_bounds__(gatherThreads(K), K == 8 ? 1 : 4)
+gatherKernel(GatherParams p, const int* __restrict__ tileList, int tilesX, int numTiles) {
   extern __shared__ __align__(16) unsigned char smem[];
   stageWeights<K>(p.weights, smem);
   __syncthreads();
@@ -194,66 +188,135 @@ __global__ void __launch_bounds__(K == 8 ? 512 : 256) gatherKernel(GatherParams 
   s.misalign = (int)(reinterpret_cast<uintptr_t>(p.src) & 3);
   s.words = reinterpret_cast<const uint32_t*>(p.src - s.misalign);
   s.w = p.srcW; s.h = p.srcH; s.pitch = p.srcPitch;
-
-  const int rowsPerTile = blockDim.x >> 5;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const bool dstWordAligned = ((reinterpret_cast<uintptr_t>(p.dst) | (unsigned)p.dstPitch) & 3) == 0;
 
-  for (int tile = blockIdx.x; tile < numTiles; tile += gridDim.x) {
+  for (int i = blockIdx.x; i < numTiles; i += gridDim.x) {
+    const int tile = tileList ? tileList[i] : i;
     const int ty = tile / tilesX, tx = tile - ty * tilesX;
-    const int y = ty * rowsPerTile + warp;
-    const int x = tx * kGatherTileW + lane * kGatherPxPerThread;
-    if (y >= p.dstH || x >= p.dstW) continue;
-    // 4 sampling records = 32 bytes, two 128-bit loads; the plan is re-read every frame: keep it out of L1
-    const int4* sp = reinterpret_cast<const int4*>(p.samples + (size_t)y * p.samplesPitch + x);
-    const int4 s01 = loadPlan(sp), s23 = loadPlan(sp + 1);
-    const int cols[4] = {s01.x, s01.z, s23.x, s23.z}, rps[4] = {s01.y, s01.w, s23.y, s23.w};
-    int v[4];
+    const int y0 = ty * gatherTileH(K) + warp * kRowsPerThread;
+    const int x = tx * kGatherTileW + lane;
+    if (y0 >= p.dstH || x >= p.dstW) continue;
+    int2 rec[kRowsPerThread];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) v[i] = gatherPixel<K, TRANSPARENT>(s, smem, cols[i], rps[i]);
-    uint8_t* out = p.dst + (size_t)y * p.dstPitch + x;
-    const bool full = x + 3 < p.dstW && (!TRANSPARENT || (v[0] | v[1] | v[2] | v[3]) >= 0);
-    if (full && dstWordAligned) {
-      *reinterpret_cast<uint32_t*>(out) = (uint32_t)v[0] | ((uint32_t)v[1] << 8) | ((uint32_t)v[2] << 16) | ((uint32_t)v[3] << 24);
-    } else {
+    for (int j = 0; j < kRowsPerThread; ++j)
+      rec[j] = y0 + j < p.dstH ? loadPlan(p.samples + (size_t)(y0 + j) * p.samplesPitch + x) : make_int2(0, 0);
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
-        if (x + i < p.dstW && v[i] >= 0) out[i] = (uint8_t)v[i];
+    for (int j = 0; j < kRowsPerThread; ++j) {
+      if (y0 + j >= p.dstH) break;
+      const int v = gatherPixel<K, TRANSPARENT>(s, smem, rec[j].x, rec[j].y);
+      if (!TRANSPARENT || v >= 0) p.dst[(size_t)(y0 + j) * p.dstPitch + x] = (uint8_t)v;
     }
   }
 }
 
 template <bool TRANSPARENT>
-__global__ void __launch_bounds__(256) nearestKernel(GatherParams p, int tilesX, int numTiles) {
-  const int rowsPerTile = blockDim.x >> 5;
+__global__ void __launch_bounds__(256, 4) nearestKernel(GatherParams p, int tilesX, int numTiles) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const bool dstWordAligned = ((reinterpret_cast<uintptr_t>(p.dst) | (unsigned)p.dstPitch) & 3) == 0;
   for (int tile = blockIdx.x; tile < numTiles; tile += gridDim.x) {
     const int ty = tile / tilesX, tx = tile - ty * tilesX;
-    const int y = ty * rowsPerTile + warp;
-    const int x = tx * kGatherTileW + lane * kGatherPxPerThread;
-    if (y >= p.dstH || x >= p.dstW) continue;
-    const int4* sp = reinterpret_cast<const int4*>(p.samples + (size_t)y * p.samplesPitch + x);
-    const int4 s01 = loadPlan(sp), s23 = loadPlan(sp + 1);
-    const int cols[4] = {s01.x, s01.z, s23.x, s23.z}, rows[4] = {s01.y >> 10, s01.w >> 10, s23.y >> 10, s23.w >> 10};
-    int v[4];
+    const int y0 = ty * gatherTileH(1) + warp * kRowsPerThread;
+    const int x = tx * kGatherTileW + lane;
+    if (y0 >= p.dstH || x >= p.dstW) continue;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      int sx = cols[i], sy = rows[i];
+    for (int j = 0; j < kRowsPerThread; ++j) {
+      if (y0 + j >= p.dstH) break;
+      const int2 rec = loadPlan(p.samples + (size_t)(y0 + j) * p.samplesPitch + x);
+      int sx = rec.x, sy = rec.y >> 10;
       const bool inside = (unsigned)sx < (unsigned)p.srcW && (unsigned)sy < (unsigned)p.srcH;
-      if (!inside && TRANSPARENT) { v[i] = -1; continue; }
+      if (!inside && TRANSPARENT) continue;
       if (!inside) { sx = wrapIndex(sx, p.srcW); sy = wrapIndex(sy, p.srcH); }
-      v[i] = __ldg(p.src + (size_t)sy * p.srcPitch + sx);
+      p.dst[(size_t)(y0 + j) * p.dstPitch + x] = __ldg(p.src + (size_t)sy * p.srcPitch + sx);
     }
-    uint8_t* out = p.dst + (size_t)y * p.dstPitch + x;
-    const bool full = x + 3 < p.dstW && (!TRANSPARENT || (v[0] | v[1] | v[2] | v[3]) >= 0);
-    if (full && dstWordAligned) {
-      *reinterpret_cast<uint32_t*>(out) = (uint32_t)v[0] | ((uint32_t)v[1] << 8) | ((uint32_t)v[2] << 16) | ((uint32_t)v[3] << 24);
-    } else {
+  }
+}
+
+// ---- TMA-staged tiles -------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smemAddr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbarInit(uint64_t* bar, uint32_t arrivals) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smemAddr(bar)), "r"(arrivals));
+}
+__device__ __forceinline__ void mbarExpectTx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smemAddr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbarWait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}"
+      ::"r"(smemAddr(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tmaLoadBox(void* dst, const CUtensorMap* map, int x, int y, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(smemAddr(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(x), "r"(y), "r"(smemAddr(bar)) : "memory");
+}
+
+template <int K, int CLS>
+__host__ __device__ constexpr int stageBytes() { return stageBoxW(K, CLS) * stageBoxH(K, CLS) + 128; }  // + slack for the last word over-read
+template <int K, int CLS>
+__host__ __device__ constexpr int stagedSmemBytes() { return weightBytes<K>() + 2 * stageBytes<K, CLS>() + 64; }
+
+template <int K, int CLS>
+__global__ void __launch_bounds__(gatherThreads(K), K == 8 ? 1 : (CLS == 0 ? 3 : 2))
+gatherStagedKernel(GatherParams p, StagedParams sp, const __grid_constant__ CUtensorMap srcMap) {
+  constexpr int kPitch = stageBoxW(K, CLS);
+  extern __shared__ __align__(16) unsigned char smem[];
+  unsigned char* wsmem = smem;
+  unsigned char* stage0 = smem + weightBytes<K>();
+  constexpr int kStage = stageBytes<K, CLS>();
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stage0 + 2 * kStage);
+  constexpr uint32_t kBoxBytes = kPitch * stageBoxH(K, CLS);
+
+  if (threadIdx.x == 0) {
+    mbarInit(&bars[0], 1);
+    mbarInit(&bars[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  stageWeights<K>(p.weights, wsmem);
+  __syncthreads();
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int first = blockIdx.x;
+  if (threadIdx.x == 0 && first < sp.numTiles) {
+    const StagedTile t = sp.tiles[first];
+    mbarExpectTx(&bars[0], kBoxBytes);
+    tmaLoadBox(stage0, &srcMap, t.boxX, t.boxY, &bars[0]);
+  }
+  uint32_t it = 0;
+  for (int i = first; i < sp.numTiles; i += gridDim.x, ++it) {
+    const uint32_t st = it & 1;
+    const int next = i + gridDim.x;
+    if (threadIdx.x == 0 && next < sp.numTiles) {  // prefetch the next tile's box into the other stage
+      const StagedTile t = sp.tiles[next];
+      mbarExpectTx(&bars[st ^ 1], kBoxBytes);
+      tmaLoadBox(stage0 + (st ^ 1) * kStage, &srcMap, t.boxX, t.boxY, &bars[st ^ 1]);
+    }
+    const StagedTile tile = sp.tiles[i];
+    const int y0 = tile.outY + warp * kRowsPerThread;
+    const int x = tile.outX + lane;
+    const bool active = y0 < p.dstH && x < p.dstW;
+    int2 rec[kRowsPerThread];
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
-        if (x + i < p.dstW && v[i] >= 0) out[i] = (uint8_t)v[i];
+    for (int j = 0; j < kRowsPerThread; ++j)
+      rec[j] = (active && y0 + j < p.dstH) ? loadPlan(p.samples + (size_t)(y0 + j) * p.samplesPitch + x) : make_int2(0, 0);
+
+    mbarWait(&bars[st], (it >> 1) & 1);
+    const uint32_t* words = reinterpret_cast<const uint32_t*>(stage0 + st * kStage);
+    if (active) {
+#pragma unroll
+      for (int j = 0; j < kRowsPerThread; ++j) {
+        if (y0 + j >= p.dstH) break;
+        const int row0 = rec[j].y >> 10, phase = rec[j].y & 1023;
+        const int off = (row0 - tile.boxY) * kPitch + (rec[j].x - tile.boxX);
+        const int acc = foldWindow<K, true>(words, off, kPitch, wsmem, phase);
+        p.dst[(size_t)(y0 + j) * p.dstPitch + x] = (uint8_t)roundToByte(acc);
+      }
     }
+    __syncthreads();  // everyone is done with stage `st` before it is refilled two iterations later
   }
 }
 
@@ -333,50 +396,88 @@ struct LaunchCfg {
 };
 
 template <auto Kern>
-cudaError_t launchPersistent(const GatherParams& p, int threads, int smemBytes, int numSMs, cudaStream_t stream) {
-  static thread_local LaunchCfg cfg;  // one per kernel instantiation (and per host thread / device binding)
-  if (!cfg.ready) {
-    cudaError_t err = cudaSuccess;
-    if (smemBytes > 48 * 1024) {
-      err = cudaFuncSetAttribute(Kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smemBytes);
-      if (err != cudaSuccess) return err;
-    }
-    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cfg.perSM, Kern, threads, smemBytes);
+cudaError_t prepare(LaunchCfg& cfg, int threads, int smemBytes) {
+  if (cfg.ready) return cudaSuccess;
+  cudaError_t err = cudaSuccess;
+  if (smemBytes > 48 * 1024) {
+    err = cudaFuncSetAttribute(Kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smemBytes);
     if (err != cudaSuccess) return err;
-    if (cfg.perSM < 1) return cudaErrorLaunchOutOfResources;
-    cfg.ready = true;
   }
-  const int rowsPerTile = threads / 32;
+  err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cfg.perSM, Kern, threads, smemBytes);
+  if (err != cudaSuccess) return err;
+  if (cfg.perSM < 1) return cudaErrorLaunchOutOfResources;
+  cfg.ready = true;
+  return cudaSuccess;
+}
+
+template <int K, bool T>
+cudaError_t launchGatherK(const GatherParams& p, const int* tileList, int numListed, int numSMs, cudaStream_t stream) {
+  static thread_local LaunchCfg cfg;  // per kernel instantiation (and per host thread / device binding)
+  constexpr int threads = gatherThreads(K), smemBytes = weightBytes<K>();
+  cudaError_t err = prepare<gatherKernel<K, T>>(cfg, threads, smemBytes);
+  if (err != cudaSuccess) return err;
   const int tilesX = (p.dstW + kGatherTileW - 1) / kGatherTileW;
-  const int tilesY = (p.dstH + rowsPerTile - 1) / rowsPerTile;
-  const int numTiles = tilesX * tilesY;
-  int grid = numSMs * cfg.perSM;  // whole waves: a multiple of the SM count
-  if (grid > numTiles) grid = numTiles;
-  Kern<<<grid, threads, smemBytes, stream>>>(p, tilesX, numTiles);
+  const int tilesY = (p.dstH + gatherTileH(K) - 1) / gatherTileH(K);
+  const int numTiles = tileList ? numListed : tilesX * tilesY;
+  if (numTiles <= 0) return cudaSuccess;
+  const int grid = std::min(numSMs * cfg.perSM, numTiles);  // whole waves: a multiple of the SM count
+  gatherKernel<K, T><<<grid, threads, smemBytes, stream>>>(p, tileList, tilesX, numTiles);
+  gLaunches.fetch_add(1, std::memory_order_relaxed);
+  return cudaGetLastError();
+}
+
+template <bool T>
+cudaError_t launchNearest(const GatherParams& p, int numSMs, cudaStream_t stream) {
+  static thread_local LaunchCfg cfg;
+  cudaError_t err = prepare<nearestKernel<T>>(cfg, 256, 0);
+  if (err != cudaSuccess) return err;
+  const int tilesX = (p.dstW + kGatherTileW - 1) / kGatherTileW;
+  const int tilesY = (p.dstH + gatherTileH(1) - 1) / gatherTileH(1);
+  const int grid = std::min(numSMs * cfg.perSM, tilesX * tilesY);
+  nearestKernel<T><<<grid, 256, 0, stream>>>(p, tilesX, tilesX * tilesY);
+  gLaunches.fetch_add(1, std::memory_order_relaxed);
+  return cudaGetLastError();
+}
+
+template <int K, int CLS>
+cudaError_t launchStagedK(const GatherParams& p, const StagedParams& sp, const CUtensorMap& map, int numSMs, cudaStream_t stream) {
+  static thread_local LaunchCfg cfg;
+  constexpr int threads = gatherThreads(K), smemBytes = stagedSmemBytes<K, CLS>();
+  cudaError_t err = prepare<gatherStagedKernel<K, CLS>>(cfg, threads, smemBytes);
+  if (err != cudaSuccess) return err;
+  const int grid = std::min(numSMs * cfg.perSM, sp.numTiles);
+  gatherStagedKernel<K, CLS><<<grid, threads, smemBytes, stream>>>(p, sp, map);
   gLaunches.fetch_add(1, std::memory_order_relaxed);
   return cudaGetLastError();
 }
 
 }  // namespace
 
-cudaError_t launchGather(const GatherParams& p, int numSMs, cudaStream_t stream) {
+cudaError_t launchGather(const GatherParams& p, const int* tileList, int numListed, int numSMs, cudaStream_t stream) {
   if (p.dstW <= 0 || p.dstH <= 0) return cudaSuccess;
   const bool t = p.transparent != 0;
   switch (p.kernelSize) {
-    case 1:
-      return t ? launchPersistent<nearestKernel<true>>(p, 256, 0, numSMs, stream)
-               : launchPersistent<nearestKernel<false>>(p, 256, 0, numSMs, stream);
-    case 2:
-      return t ? launchPersistent<gatherKernel<2, true>>(p, 256, SmemTable<2>::kBytes, numSMs, stream)
-               : launchPersistent<gatherKernel<2, false>>(p, 256, SmemTable<2>::kBytes, numSMs, stream);
-    case 4:
-      return t ? launchPersistent<gatherKernel<4, true>>(p, 256, SmemTable<4>::kBytes, numSMs, stream)
-               : launchPersistent<gatherKernel<4, false>>(p, 256, SmemTable<4>::kBytes, numSMs, stream);
-    case 8:
-      return t ? launchPersistent<gatherKernel<8, true>>(p, 512, SmemTable<8>::kBytes, numSMs, stream)
-               : launchPersistent<gatherKernel<8, false>>(p, 512, SmemTable<8>::kBytes, numSMs, stream);
-    default:
-      return cudaErrorInvalidValue;
+    case 1: return t ? launchNearest<true>(p, numSMs, stream) : launchNearest<false>(p, numSMs, stream);
+    case 2: return t ? launchGatherK<2, true>(p, tileList, numListed, numSMs, stream) : launchGatherK<2, false>(p, tileList, numListed, numSMs, stream);
+    case 4: return t ? launchGatherK<4, true>(p, tileList, numListed, numSMs, stream) : launchGatherK<4, false>(p, tileList, numListed, numSMs, stream);
+    case 8: return t ? launchGatherK<8, true>(p, tileList, numListed, numSMs, stream) : launchGatherK<8, false>(p, tileList, numListed, numSMs, stream);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+cudaError_t launchGatherStaged(const GatherParams& p, const StagedParams& sp, const void* tensorMap, int boxClass,
+                               int numSMs, cudaStream_t stream) {
+  if (sp.numTiles <= 0) return cudaSuccess;
+  if (p.transparent || boxClass < 0 || boxClass >= kNumBoxClasses) return cudaErrorInvalidValue;
+  const CUtensorMap& map = *static_cast<const CUtensorMap*>(tensorMap);
+  switch (p.kernelSize * 2 + boxClass) {
+    case 4: return launchStagedK<2, 0>(p, sp, map, numSMs, stream);
+    case 5: return launchStagedK<2, 1>(p, sp, map, numSMs, stream);
+    case 8: return launchStagedK<4, 0>(p, sp, map, numSMs, stream);
+    case 9: return launchStagedK<4, 1>(p, sp, map, numSMs, stream);
+    case 16: return launchStagedK<8, 0>(p, sp, map, numSMs, stream);
+    case 17: return launchStagedK<8, 1>(p, sp, map, numSMs, stream);
+    default: return cudaErrorInvalidValue;
   }
 }
 

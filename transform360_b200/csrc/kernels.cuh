@@ -20,6 +20,28 @@ struct GatherParams {
   int transparent;         // BORDER_TRANSPARENT (barrel layouts) instead of BORDER_WRAP
 };
 
+// One tile of the TMA-staged gather: a gatherTileW x gatherTileH block of output pixels whose whole source
+// window fits the fixed staging box placed at (boxX, boxY) of the source plane (boxX % 16 == 0).
+struct StagedTile {
+  int outX, outY, boxX, boxY;
+};
+
+constexpr int kGatherTileW = 32;                                   // one warp = 32 adjacent columns
+__host__ __device__ constexpr int gatherThreads(int k) { return k == 8 ? 512 : 256; }
+__host__ __device__ constexpr int gatherTileH(int k) { return gatherThreads(k) / 32 * 4; }  // 4 rows per thread
+// Staging boxes (bytes x rows), two classes per kernel size: the common one, and a larger one for tiles whose
+// source window is wide (towards the poles).  Shared-memory row pitch = box width (TMA writes dense rows):
+// 192 B = 48 words puts consecutive rows 16 banks apart, so a warp whose 32 adjacent pixels drift over 2-4
+// source rows still reads conflict-free; 240 B = 60 words puts them 28 banks apart.
+constexpr int kNumBoxClasses = 2;
+__host__ __device__ constexpr int stageBoxW(int /*k*/, int cls) { return cls == 0 ? 192 : 240; }
+__host__ __device__ constexpr int stageBoxH(int k, int cls) { return k == 8 ? (cls == 0 ? 112 : 144) : (cls == 0 ? 64 : 96); }
+
+struct StagedParams {
+  const StagedTile* tiles;  // device list
+  int numTiles;
+};
+
 // One tile of the segmented low-pass: output rectangle and the taps to use.
 struct BlurJob {
   int x0, y0, w, h;  // output rectangle (inside one plan segment)
@@ -40,7 +62,12 @@ constexpr int kBlurTileW = 64, kBlurTileH = 32;
 constexpr int kBlurMaxSmem = 96 * 1024;
 
 // Launchers: enqueue on `stream`, return the CUDA status of the launch.  Each counts the kernels it launches.
-cudaError_t launchGather(const GatherParams& p, int numSMs, cudaStream_t stream);
+// tileList == nullptr: every tile of the plane; otherwise only the listed tile indices (row-major, tilesX wide)
+cudaError_t launchGather(const GatherParams& p, const int* tileList, int numListed, int numSMs, cudaStream_t stream);
+// TMA-staged tiles of one box class.  tensorMap: a CUtensorMap (128 bytes, by value) describing the source plane
+// with the staging box of (p.kernelSize, boxClass).  BORDER_WRAP only (tiles touching a border are never staged).
+cudaError_t launchGatherStaged(const GatherParams& p, const StagedParams& sp, const void* tensorMap, int boxClass,
+                               int numSMs, cudaStream_t stream);
 cudaError_t launchBlur(const BlurParams& p, cudaStream_t stream);        // shared-memory tiles
 cudaError_t launchBlurDirect(const BlurParams& p, cudaStream_t stream);  // any kernel size, slow
 unsigned long long kernelLaunchCount();

@@ -5,9 +5,11 @@
 // stdout.  Everything behind it is new: the host planner (geometry.cpp, lowpass_plan.cpp, sampling.cpp)
 // produces the plan, it is uploaded once, and each frame plane is two kernel launches at most
 // (segmented low-pass, gather).  There is no CPU pixel path: if CUDA is unavailable the calls fail.
+#include <cuda.h>  // CUtensorMap types; the encoder is looked up at run time, libcuda is not linked
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <climits>
 #include <cstdio>
 #include <cstring>
 #include <map>
@@ -27,6 +29,7 @@ namespace {
 
 using t360::BlurJob;
 using t360::HostPlan;
+using t360::StagedTile;
 
 struct CudaFail {
   cudaError_t err;
@@ -74,11 +77,51 @@ struct DevicePlan {
   bool transparent = false, lowPass = false, blurNeedsClear = false;
   DeviceBuffer<int2> samples;
   int samplesPitch = 0;
+  // gather tiles: those whose source window fits the TMA staging box, and the rest (by tile index)
+  DeviceBuffer<StagedTile> stagedTiles[t360::kNumBoxClasses];
+  DeviceBuffer<int> fallbackTiles;
+  int numStaged[t360::kNumBoxClasses] = {}, numFallback = 0;
+  int totalStaged() const { int n = 0; for (int c : numStaged) n += c; return n; }
   DeviceBuffer<BlurJob> tileJobs, directJobs;
   int numTileJobs = 0, numDirectJobs = 0, tileSmem = 0;
   DeviceBuffer<float> taps;
-  size_t deviceBytes() const { return samples.bytes() + tileJobs.bytes() + directJobs.bytes() + taps.bytes(); }
+  size_t deviceBytes() const {
+    return samples.bytes() + stagedTiles[0].bytes() + stagedTiles[1].bytes() + fallbackTiles.bytes() + tileJobs.bytes() + directJobs.bytes() + taps.bytes();
+  }
 };
+
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point table: the library must still dlopen()
+// on a machine without libcuda.so (CPU-only planning, tests), so libcuda is never linked.
+EncodeTiledFn tensorMapEncoder() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q{};
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
+      cudaGetLastError();
+      p = nullptr;
+    }
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+
+// Describes a pitch-linear 8-bit plane to the TMA unit with the staging box of kernel size k.
+bool encodePlaneMap(CUtensorMap* map, const uint8_t* base, int w, int h, int pitch, int k, int cls) {
+  EncodeTiledFn enc = tensorMapEncoder();
+  if (!enc) return false;
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || (pitch & 15)) return false;
+  const cuuint64_t dims[2] = {static_cast<cuuint64_t>(w), static_cast<cuuint64_t>(h)};
+  const cuuint64_t strides[1] = {static_cast<cuuint64_t>(pitch)};
+  const cuuint32_t box[2] = {static_cast<cuuint32_t>(t360::stageBoxW(k, cls)), static_cast<cuuint32_t>(t360::stageBoxH(k, cls))};
+  const cuuint32_t elem[2] = {1, 1};
+  return enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<uint8_t*>(base), dims, strides, box, elem,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
 
 constexpr int kPitchAlign = 256;
 inline int alignedPitch(int w) { return (w + kPitchAlign - 1) / kPitchAlign * kPitchAlign; }
@@ -214,6 +257,14 @@ class VideoFrameTransform {
     try { ensureDevice(); } catch (...) { return nullptr; }
     return stream_;
   }
+  bool tileCounts(int planIndex, int counts[4]) {
+    std::lock_guard<std::mutex> lock(mu_);
+    auto it = plans_.find(planIndex);
+    if (it == plans_.end()) return false;
+    counts[0] = it->second.totalStaged(); counts[1] = it->second.numFallback;
+    counts[2] = it->second.numTileJobs; counts[3] = it->second.numDirectJobs;
+    return true;
+  }
   size_t planBytes(int planIndex) {
     std::lock_guard<std::mutex> lock(mu_);
     auto it = plans_.find(planIndex);
@@ -282,10 +333,52 @@ class VideoFrameTransform {
                     static_cast<size_t>(h.mapW) * sizeof(int2));
       d.samples.reserve(padded.size());
       CU(cudaMemcpy(d.samples.ptr, padded.data(), padded.size() * sizeof(int2), cudaMemcpyHostToDevice));
+      if (d.kernelSize >= 2 && !d.transparent) buildGatherTiles(h, d);
     }
     d.lowPass = ctx_.enable_low_pass_filter != 0;
     if (d.lowPass) buildBlurJobs(h, d);
     return d;
+  }
+
+  // Splits the output plane into CTA tiles and finds, per tile, the bounding box of all source windows.  A tile is
+  // "staged" when that box lies inside the plane (no BORDER_WRAP needed) and fits the fixed TMA box; its box is
+  // anchored at a 16-byte aligned column.  Everything else is listed for the general (L1) kernel.
+  void buildGatherTiles(const HostPlan& h, DevicePlan& d) {
+    const int k = h.kernelSize, tw = t360::kGatherTileW, th = t360::gatherTileH(k);
+    const int tilesX = (h.mapW + tw - 1) / tw, tilesY = (h.mapH + th - 1) / th;
+    std::vector<StagedTile> staged[t360::kNumBoxClasses];
+    std::vector<int> fallback;
+    for (int ty = 0; ty < tilesY; ++ty)
+      for (int tx = 0; tx < tilesX; ++tx) {
+        int minC = INT32_MAX, maxC = INT32_MIN, minR = INT32_MAX, maxR = INT32_MIN;
+        const int y1 = std::min(h.mapH, (ty + 1) * th), x1 = std::min(h.mapW, (tx + 1) * tw);
+        for (int y = ty * th; y < y1; ++y) {
+          const t360::SamplePoint* row = &h.samples[static_cast<size_t>(y) * h.mapW];
+          for (int x = tx * tw; x < x1; ++x) {
+            const int c = row[x].col0, r = row[x].rowPhase >> 10;
+            minC = std::min(minC, c); maxC = std::max(maxC, c);
+            minR = std::min(minR, r); maxR = std::max(maxR, r);
+          }
+        }
+        const int boxX = minC >= 0 ? (minC & ~15) : -1;
+        const bool inPlane = minC >= 0 && minR >= 0 && maxC + k <= h.inW && maxR + k <= h.inH;
+        int cls = -1;
+        for (int c = 0; c < t360::kNumBoxClasses && inPlane && cls < 0; ++c)
+          if (maxC + k - boxX <= t360::stageBoxW(k, c) && maxR + k - minR <= t360::stageBoxH(k, c)) cls = c;
+        if (cls >= 0) staged[cls].push_back(StagedTile{tx * tw, ty * th, boxX, minR});
+        else fallback.push_back(ty * tilesX + tx);
+      }
+    for (int c = 0; c < t360::kNumBoxClasses; ++c) {
+      d.numStaged[c] = static_cast<int>(staged[c].size());
+      if (staged[c].empty()) continue;
+      d.stagedTiles[c].reserve(staged[c].size());
+      CU(cudaMemcpy(d.stagedTiles[c].ptr, staged[c].data(), staged[c].size() * sizeof(StagedTile), cudaMemcpyHostToDevice));
+    }
+    d.numFallback = static_cast<int>(fallback.size());
+    if (!fallback.empty()) {
+      d.fallbackTiles.reserve(fallback.size());
+      CU(cudaMemcpy(d.fallbackTiles.ptr, fallback.data(), fallback.size() * sizeof(int), cudaMemcpyHostToDevice));
+    }
   }
 
   // Tiles of the plan, applied once (mono) or to both halves of a stereo frame (reference cpp:630-691), cut
@@ -374,7 +467,22 @@ class VideoFrameTransform {
     }
     t360::GatherParams gp{src, inW, inH, srcPitch, dOut, outW, outH, outPitch, plan.samples.ptr, plan.samplesPitch,
                           weights_[plan.kernelSize].ptr, plan.kernelSize, plan.transparent ? 1 : 0};
-    CU(t360::launchGather(gp, numSMs_, s));
+    // staged tiles need the plane the plan was made for (their windows were proven in-bounds for it) and a
+    // TMA-describable layout (16-byte aligned base and pitch); otherwise every tile takes the general kernel
+    bool stage = plan.totalStaged() > 0 && inW == plan.inW && inH == plan.inH;
+    CUtensorMap maps[t360::kNumBoxClasses];
+    for (int c = 0; c < t360::kNumBoxClasses && stage; ++c)
+      if (plan.numStaged[c]) stage = encodePlaneMap(&maps[c], src, inW, inH, srcPitch, plan.kernelSize, c);
+    if (stage) {
+      for (int c = 0; c < t360::kNumBoxClasses; ++c) {
+        if (!plan.numStaged[c]) continue;
+        t360::StagedParams sp{plan.stagedTiles[c].ptr, plan.numStaged[c]};
+        CU(t360::launchGatherStaged(gp, sp, &maps[c], c, numSMs_, s));
+      }
+      if (plan.numFallback) CU(t360::launchGather(gp, plan.fallbackTiles.ptr, plan.numFallback, numSMs_, s));
+    } else {
+      CU(t360::launchGather(gp, nullptr, 0, numSMs_, s));
+    }
     return true;
   }
 
@@ -475,6 +583,9 @@ T360_API int T360B200_synchronize(VideoFrameTransform* t) { return t ? t->synchr
 T360_API void* T360B200_stream(VideoFrameTransform* t) { return t ? t->stream() : nullptr; }
 T360_API unsigned long long T360B200_kernelLaunchCount(void) { return t360::kernelLaunchCount(); }
 T360_API unsigned long long T360B200_planDeviceBytes(VideoFrameTransform* t, int planIndex) { return t ? t->planBytes(planIndex) : 0; }
+T360_API int T360B200_planTileCounts(VideoFrameTransform* t, int planIndex, int counts[4]) {
+  return t && counts ? t->tileCounts(planIndex, counts) : 0;
+}
 T360_API int T360B200_deviceCount(void) {
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess) {

@@ -109,6 +109,8 @@ def load(path: os.PathLike | None = None):
     L.T360B200_kernelLaunchCount.restype = C.c_ulonglong
     L.T360B200_planDeviceBytes.restype = C.c_ulonglong
     L.T360B200_planDeviceBytes.argtypes = [vp, ci]
+    L.T360B200_planTileCounts.restype = ci
+    L.T360B200_planTileCounts.argtypes = [vp, ci, C.POINTER(ci)]
     L.T360B200_deviceCount.restype = ci
     L.T360B200_version.restype = C.c_char_p
     if path is None:
@@ -122,7 +124,7 @@ EXPORTED_SYMBOLS = [
     "T360B200_hostPlanInfo", "T360B200_hostPlanMap", "T360B200_hostPlanSamples", "T360B200_hostPlanSegment",
     "T360B200_remapTable", "T360B200_transformFramePlaneAsync", "T360B200_lowPassPlaneAsync",
     "T360B200_synchronize", "T360B200_stream", "T360B200_kernelLaunchCount", "T360B200_planDeviceBytes",
-    "T360B200_deviceCount", "T360B200_version",
+    "T360B200_planTileCounts", "T360B200_deviceCount", "T360B200_version",
 ]
 
 
@@ -191,6 +193,13 @@ class VideoFrameTransform:
     @property
     def stream(self) -> int:
         return self._lib.T360B200_stream(self._h) or 0
+
+    def plan_tile_counts(self, plan_index):
+        """(gather tiles staged via TMA, gather tiles on the general path, low-pass smem jobs, low-pass direct jobs)"""
+        c = (C.c_int * 4)()
+        if not self._lib.T360B200_planTileCounts(self._h, plan_index, c):
+            raise KeyError(plan_index)
+        return tuple(c)
 
     def plan_device_bytes(self, plan_index) -> int:
         return int(self._lib.T360B200_planDeviceBytes(self._h, plan_index))
