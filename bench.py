@@ -381,7 +381,7 @@ def main():
                    "sharding": "frames round-robin over ranks; one NCCL broadcast of context+dims; no pixel traffic",
                    "output_mpx_per_s": round(out_px * K * world / (ms_total_max * 1e-3) / 1e6, 1),
                    "frames_per_s": round(K * world / (ms_total_max * 1e-3), 1), "plan_seconds": round(plan_seconds, 3),
-                   "tiles_luma[tma_staged,general,lowpass_smem,lowpass_direct]": list(ft.vft.plan_tile_counts(0)),
+                   "tiles_luma[gather_tma_staged,gather_general,lowpass_strip_jobs,lowpass_general_jobs]": list(ft.vft.plan_tile_counts(0)),
                    "tiles_chroma": list(ft.vft.plan_tile_counts(1))},
         "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks,
     }

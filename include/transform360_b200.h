@@ -58,7 +58,8 @@ unsigned long long T360B200_kernelLaunchCount(void);
 /* Bytes of device memory held by the plan of one index (sampling plan + low-pass tables). */
 unsigned long long T360B200_planDeviceBytes(VideoFrameTransform* transform, int transformMatPlaneIndex);
 /* counts[0] = gather tiles staged through TMA into shared memory, counts[1] = tiles on the general (L1) path,
- * counts[2] = low-pass jobs using shared-memory tiles, counts[3] = low-pass jobs on the direct path. */
+ * counts[2] = low-pass warp-jobs on the register-resident strip kernel, counts[3] = low-pass jobs on the general
+ * (large vertical kernel) paths. */
 int T360B200_planTileCounts(VideoFrameTransform* transform, int transformMatPlaneIndex, int counts[4]);
 /* CUDA devices visible (0 when there is none or the driver is absent). */
 int T360B200_deviceCount(void);

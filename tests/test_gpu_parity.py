@@ -111,10 +111,23 @@ def test_device_pointer_path_with_unaligned_pitch(name, torch_cuda):
     assert np.array_equal(got2, got)
 
 
-@pytest.mark.parametrize("name", ["lp_default", "lp_tiles", "lp_even_segments", "lp_big_kernels", "lr_stereo", "eac_tb_lanczos", "offcenter_adjust"])
+EXTRA_LP = {
+    # vertical sigma 0.25 -> a single vertical tap (hy = 0), horizontal kernels of every size up to the pole
+    "lp_single_vertical_tap": dict(ov=dict(min_kernel_half_height=0.5, num_vertical_segments=9, num_horizontal_segments=1),
+                                   inp=(328, 164), out=(480, 320)),
+    # odd plane width, tiles narrower than a strip, kernels differing per tile (off-centre): unaligned byte stores
+    "lp_odd_offcentre": dict(ov=dict(fixed_cube_offcenter_z=-0.25, num_vertical_segments=7, num_horizontal_segments=5),
+                             inp=(1003, 501), out=(384, 256)),
+    # wide plane: interior strips (aligned word loads) and edge strips (clamped loads) in the same launch
+    "lp_wide": dict(ov=dict(num_vertical_segments=15, num_horizontal_segments=32), inp=(3840, 480), out=(1536, 256)),
+}
+
+
+@pytest.mark.parametrize("name", ["lp_default", "lp_tiles", "lp_even_segments", "lp_big_kernels", "lr_stereo", "eac_tb_lanczos",
+                                  "offcenter_adjust"] + sorted(EXTRA_LP))
 def test_low_pass_stage_alone(name, torch_cuda):
     torch = torch_cuda
-    case = SMALL[name]
+    case = SMALL.get(name) or EXTRA_LP[name]
     ctx, octx = _ctxs(case)
     iw, ih, ow, oh, idx = plane_dims(case, 0)
     src = co.noise_plane(iw, ih, plane=0, frame=9)
@@ -194,3 +207,58 @@ def test_full_size_cfg3_chroma_and_frame_seeds(torch_cuda):
             assert np.array_equal(got, co.transform_plane(octx, plan, src, ow, oh, map_index=1))
             outs.append(got)
         assert np.array_equal(outs[0], outs[3])
+
+
+def _rank_worker(rank, world, port, q):
+    import os
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from transform360_b200.stream import FrameTransformer, StreamSpec, broadcast_parameters, frames_for_rank
+        ctx = spec = None
+        if rank == 0:
+            ctx = t360.make_context(interpolation_alg=t360.CUBIC, num_vertical_segments=15, num_horizontal_segments=8)
+            spec = StreamSpec(960, 480, 384, 256)
+        ctx, spec = broadcast_parameters(ctx, spec, rank, world, device=torch.device("cuda", rank))
+        ft = FrameTransformer(ctx, spec)
+        out = {}
+        for k in list(frames_for_rank(6, rank, world)) + [5 - rank]:  # own frames + one frame of the other rank
+            planes = []
+            for p in range(3):
+                iw, ih, ow, oh, idx = spec.plane_dims(p)
+                src = co.noise_plane(iw, ih, plane=p, frame=k)
+                planes.append(rh.sha16(ft.vft.transform_plane(src, ow, oh, idx, image_plane=p)))
+            out[k] = planes
+        q.put((rank, out))
+        ft.close()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_frame_bytes_do_not_depend_on_the_gpu(torch_cuda):
+    """frame k gives identical planes whichever rank (GPU) processes it."""
+    torch = torch_cuda
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    import socket
+    import torch.multiprocessing as mp
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctxm = mp.get_context("spawn")
+    q = ctxm.Queue()
+    procs = [ctxm.Process(target=_rank_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=300) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    shared = set(res[0]) & set(res[1])
+    assert shared, "test must compare at least one frame processed on both GPUs"
+    for k in shared:
+        assert res[0][k] == res[1][k], f"frame {k} differs between GPUs"

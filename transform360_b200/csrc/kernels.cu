@@ -70,19 +70,31 @@ __device__ __forceinline__ int reflect101(int p, int n) {  // what remap uses fo
 template <int K>
 __host__ __device__ constexpr int weightBytes() { return 1024 * K * K * 2; }
 
+// Where the weights of phase a = (fracY << 5) | fracX live in the shared table.  A 128-bit shared load is
+// served 8 lanes at a time from 8 bank groups of 16 bytes (a 64-bit one 16 lanes from 16 groups); the group
+// is the low bits of the slot index.  Adjacent output pixels step fracX by a near-constant amount (48/32 px
+// for the 8K -> 1280-face case, i.e. 16 mod 32) while fracY drifts slowly, so indexing by fracX alone would
+// put the 8 different phases of a quarter-warp into the same group.  Rotating the group by fracY spreads
+// them (measured: see DESIGN.md).
+template <int K>
+__device__ __forceinline__ int weightSlot(int phase) {
+  constexpr int kMask = K == 2 ? 15 : 7;
+  return (phase & ~kMask) | ((phase + (phase >> 5)) & kMask);
+}
+
 // Copies the [1024][K][K] int16 table into shared memory as [K*K/8][1024] 16-byte vectors (K >= 4) or
-// [1024] 8-byte vectors (K == 2), so that lanes with unrelated phases hit different bank groups.
+// [1024] 8-byte vectors (K == 2), slot-permuted by weightSlot().
 template <int K>
 __device__ __forceinline__ void stageWeights(const int16_t* __restrict__ g, unsigned char* smem) {
   if constexpr (K == 2) {
     const uint2* src = reinterpret_cast<const uint2*>(g);
     uint2* dst = reinterpret_cast<uint2*>(smem);
-    for (int i = threadIdx.x; i < 1024; i += blockDim.x) dst[i] = __ldg(src + i);
+    for (int i = threadIdx.x; i < 1024; i += blockDim.x) dst[weightSlot<K>(i)] = __ldg(src + i);
   } else {
     constexpr int kVec = K * K / 8;  // uint4 per phase
     const uint4* src = reinterpret_cast<const uint4*>(g);
     uint4* dst = reinterpret_cast<uint4*>(smem);
-    for (int i = threadIdx.x; i < 1024 * kVec; i += blockDim.x) dst[(i % kVec) * 1024 + i / kVec] = __ldg(src + i);
+    for (int i = threadIdx.x; i < 1024 * kVec; i += blockDim.x) dst[(i % kVec) * 1024 + weightSlot<K>(i / kVec)] = __ldg(src + i);
   }
 }
 
@@ -92,6 +104,7 @@ __device__ __forceinline__ void stageWeights(const int16_t* __restrict__ g, unsi
 template <int K, bool SHARED>
 __device__ __forceinline__ int foldWindow(const uint32_t* __restrict__ words, int off, int pitch,
                                           const unsigned char* wsmem, int phase) {
+  phase = weightSlot<K>(phase);
   auto ld = [&](int wordIndex) -> uint32_t { return SHARED ? words[wordIndex] : __ldg(words + wordIndex); };
   int acc = 0;
   if constexpr (K == 2) {
@@ -159,7 +172,7 @@ __device__ __forceinline__ int gatherPixel(const SrcView& s, const unsigned char
     const int ax = col0 + (K / 2 - 1), ay = row0 + (K / 2 - 1);
     if ((unsigned)ax >= (unsigned)s.w || (unsigned)ay >= (unsigned)s.h) return -1;
   }
-  const int16_t* wt = reinterpret_cast<const int16_t*>(wsmem) + phase * (K == 2 ? 4 : 8);
+  const int16_t* wt = reinterpret_cast<const int16_t*>(wsmem) + weightSlot<K>(phase) * (K == 2 ? 4 : 8);
   int acc = 0;
 #pragma unroll 1
   for (int r = 0; r < K; ++r) {
@@ -280,12 +293,24 @@ gatherStagedKernel(GatherParams p, StagedParams sp, const __grid_constant__ CUte
   __syncthreads();
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  int first = blockIdx.x;
+  const int first = blockIdx.x;
   if (threadIdx.x == 0 && first < sp.numTiles) {
     const StagedTile t = sp.tiles[first];
     mbarExpectTx(&bars[0], kBoxBytes);
     tmaLoadBox(stage0, &srcMap, t.boxX, t.boxY, &bars[0]);
   }
+  // software pipeline: the plan records (and tile header) of tile n+1 are fetched while tile n is computed
+  auto fetch = [&](int i, StagedTile& t, int2 (&rec)[kRowsPerThread]) {
+    t = sp.tiles[i];
+    const int y0 = t.outY + warp * kRowsPerThread, x = t.outX + lane;
+#pragma unroll
+    for (int j = 0; j < kRowsPerThread; ++j)
+      rec[j] = (x < p.dstW && y0 + j < p.dstH) ? loadPlan(p.samples + (size_t)(y0 + j) * p.samplesPitch + x) : make_int2(0, 0);
+  };
+  StagedTile tile{};
+  int2 rec[kRowsPerThread] = {};
+  if (first < sp.numTiles) fetch(first, tile, rec);
+
   uint32_t it = 0;
   for (int i = first; i < sp.numTiles; i += gridDim.x, ++it) {
     const uint32_t st = it & 1;
@@ -295,18 +320,15 @@ gatherStagedKernel(GatherParams p, StagedParams sp, const __grid_constant__ CUte
       mbarExpectTx(&bars[st ^ 1], kBoxBytes);
       tmaLoadBox(stage0 + (st ^ 1) * kStage, &srcMap, t.boxX, t.boxY, &bars[st ^ 1]);
     }
-    const StagedTile tile = sp.tiles[i];
+    StagedTile tileNext{};
+    int2 recNext[kRowsPerThread] = {};
+    if (next < sp.numTiles) fetch(next, tileNext, recNext);
+
     const int y0 = tile.outY + warp * kRowsPerThread;
     const int x = tile.outX + lane;
-    const bool active = y0 < p.dstH && x < p.dstW;
-    int2 rec[kRowsPerThread];
-#pragma unroll
-    for (int j = 0; j < kRowsPerThread; ++j)
-      rec[j] = (active && y0 + j < p.dstH) ? loadPlan(p.samples + (size_t)(y0 + j) * p.samplesPitch + x) : make_int2(0, 0);
-
     mbarWait(&bars[st], (it >> 1) & 1);
     const uint32_t* words = reinterpret_cast<const uint32_t*>(stage0 + st * kStage);
-    if (active) {
+    if (x < p.dstW) {
 #pragma unroll
       for (int j = 0; j < kRowsPerThread; ++j) {
         if (y0 + j >= p.dstH) break;
@@ -317,6 +339,9 @@ gatherStagedKernel(GatherParams p, StagedParams sp, const __grid_constant__ CUte
       }
     }
     __syncthreads();  // everyone is done with stage `st` before it is refilled two iterations later
+    tile = tileNext;
+#pragma unroll
+    for (int j = 0; j < kRowsPerThread; ++j) rec[j] = recNext[j];
   }
 }
 
@@ -365,6 +390,171 @@ __global__ void __launch_bounds__(256) blurTileKernel(BlurParams p) {
     const int v = __float2int_rn(s);
     p.dst[(size_t)(job.y0 + y) * p.dstPitch + job.x0 + x] = (uint8_t)min(max(v, 0), 255);
   }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Register-resident low-pass (the fast path; vertical half-size HY <= 3, any horizontal size).
+// One WARP per job, no shared memory, no barriers.  Lane L owns columns x0 + 8L .. x0 + 8L + 7 and marches
+// down the rows of the strip:
+//   horizontal: the 8 running sums advance together through the taps in chunks of 4; the source bytes they
+//     need form a sliding window kept as floats in a 12-register ring (3 groups of 4).  Each chunk issues
+//     32 FMAs, converts one new group of 4 bytes (PRMT into the mantissa of 2^23, minus 2^23: exact) fetched
+//     as one aligned 32-bit word and aligned with a funnel shift, and reads 4 taps as one 128-bit uniform load.
+//     Tap arrays are zero-padded to a multiple of 4: fma(0, p, s) == s exactly, and starting the chain from
+//     +0 makes the first fma equal the reference's plain multiply, so the bits match the oracle's order.
+//   vertical: the last 2*HY+1 row results stay in a register ring; the symmetric-pair FMA chain of the oracle
+//     produces one output row per input row; rounding is the 1.5*2^23 magic add (round-half-even), and the low
+//     mantissa bytes of 8 results are packed into one 64-bit store.
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float byteToFloat(uint32_t word, int k) {
+  // (float)byte k of word: place it in the low mantissa byte of 8388608.0f, subtract 8388608.0f
+  return __uint_as_float(__byte_perm(word, 0x4B000000u, 0x7440 | k)) - 8388608.0f;
+}
+
+// Source bytes of one strip row as seen by one lane.  Interior strips read aligned 32-bit words through the
+// read-only path; edge strips replicate the plane's left/right border byte by byte (BORDER_REPLICATE against the
+// parent plane, reference cpp:197).
+template <bool EDGE>
+struct StripRowReader {
+  const uint8_t* rowBytes;
+  const uint32_t* rowWords;
+  int firstByte, sh, width;
+
+  __device__ __forceinline__ StripRowReader(const StripParams& p, int y, int firstByte_) : firstByte(firstByte_), width(p.width) {
+    rowBytes = p.src + (size_t)min(max(y, 0), p.height - 1) * p.srcPitch;
+    const uintptr_t a = reinterpret_cast<uintptr_t>(rowBytes) + firstByte;
+    rowWords = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
+    sh = (int)(a & 3) * 8;
+  }
+  // raw[0..3]: what the first three groups (window positions 0..11) are made of
+  __device__ __forceinline__ void head(uint32_t (&raw)[4]) const {
+    if (EDGE) {
+#pragma unroll
+      for (int g = 0; g < 3; ++g) raw[g] = bytes(g);
+      raw[3] = 0;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) raw[i] = __ldg(rowWords + i);
+    }
+  }
+  __device__ __forceinline__ uint32_t bytes(int group) const {
+    uint32_t g = 0;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) g |= (uint32_t)__ldg(rowBytes + min(max(firstByte + group * 4 + b, 0), width - 1)) << (8 * b);
+    return g;
+  }
+  // group `group` (>= 3) given the previous aligned word
+  __device__ __forceinline__ uint32_t next(int group, uint32_t& prevWord) const {
+    if (EDGE) return bytes(group);
+    const uint32_t w = __ldg(rowWords + group + 1);
+    const uint32_t g = __funnelshift_r(prevWord, w, sh);
+    prevWord = w;
+    return g;
+  }
+};
+
+template <bool EDGE>
+__device__ __forceinline__ void stripRow(const StripParams& p, const StripJob& job, const StripRowReader<EDGE>& rd,
+                                         const uint32_t (&raw)[4], float (&s)[8]) {
+  float ring[12];
+#pragma unroll
+  for (int g = 0; g < 3; ++g) {
+    const uint32_t grp = EDGE ? raw[g] : __funnelshift_r(raw[g], raw[g + 1], rd.sh);
+#pragma unroll
+    for (int b = 0; b < 4; ++b) ring[g * 4 + b] = byteToFloat(grp, b);
+  }
+  uint32_t prev = raw[3];
+#pragma unroll
+  for (int m = 0; m < 8; ++m) s[m] = 0.0f;
+  const float4* taps = reinterpret_cast<const float4*>(p.taps + job.kxOffset);
+  for (int c = 0; c < job.kxChunks; c += 3) {
+#pragma unroll
+    for (int u = 0; u < 3; ++u) {
+      if (c + u < job.kxChunks) {
+        const float4 k4 = __ldg(taps + c + u);
+        // the group that replaces ring slots 4u..4u+3 is only needed if another chunk follows
+        const uint32_t grp = c + u + 1 < job.kxChunks ? rd.next(c + u + 3, prev) : 0u;
+        const float k[4] = {k4.x, k4.y, k4.z, k4.w};
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+#pragma unroll
+          for (int m = 0; m < 8; ++m) s[m] = __fmaf_rn(k[t], ring[(4 * u + m + t) % 12], s[m]);
+#pragma unroll
+        for (int b = 0; b < 4; ++b) ring[4 * u + b] = byteToFloat(grp, b);
+      }
+    }
+  }
+}
+
+template <int HY, bool EDGE>
+__device__ __forceinline__ void stripBody(const StripParams& p, const StripJob& job, int lane) {
+  constexpr int L = 2 * HY + 1;
+  const int hx = job.kxCount >> 1;
+  const int lx = job.x0 + lane * kStripLanePx;
+  if (lane * kStripLanePx >= job.w) return;
+  const int firstByte = lx - hx;  // column of window position 0
+  const float* __restrict__ ky = p.taps + job.kyOffset;
+  float kv[HY + 1];
+#pragma unroll
+  for (int i = 0; i <= HY; ++i) kv[i] = __ldg(ky + HY + i);
+  const int nValid = min(kStripLanePx, job.w - lane * kStripLanePx);
+  const bool wide = nValid == 8 && ((reinterpret_cast<uintptr_t>(p.dst) | (unsigned)p.dstPitch | (unsigned)lx) & 7) == 0;
+
+  float R[L][8];
+  const int rowsTotal = job.h + 2 * HY;
+  // software pipeline over rows: the head of row j+1 is requested before row j is computed (rows are first
+  // touches of DRAM lines; without this every row start exposes the full memory latency)
+  uint32_t rawNext[4];
+  StripRowReader<EDGE>(p, job.y0 - HY, firstByte).head(rawNext);
+  for (int jb = 0; jb < rowsTotal; jb += L) {
+#pragma unroll
+    for (int u = 0; u < L; ++u) {
+      const int j = jb + u;
+      if (j < rowsTotal) {
+        const StripRowReader<EDGE> rd(p, job.y0 - HY + j, firstByte);
+        uint32_t raw[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) raw[i] = rawNext[i];
+        if (j + 1 < rowsTotal) StripRowReader<EDGE>(p, job.y0 - HY + j + 1, firstByte).head(rawNext);
+        stripRow<EDGE>(p, job, rd, raw, R[u]);
+        if (j >= 2 * HY) {
+          // centre row is the one computed HY steps ago: ring slot (u - HY) mod L
+          constexpr int kBig = 4 * L;
+          float o[8];
+#pragma unroll
+          for (int m = 0; m < 8; ++m) {
+            float acc = __fmul_rn(kv[0], R[(u - HY + kBig) % L][m]);
+#pragma unroll
+            for (int i = 1; i <= HY; ++i)
+              acc = __fmaf_rn(kv[i], __fadd_rn(R[(u - HY + i + kBig) % L][m], R[(u - HY - i + kBig) % L][m]), acc);
+            o[m] = __fadd_rn(acc, 12582912.0f);  // low mantissa byte = rint(acc), half-even
+          }
+          const int y = job.y0 + j - 2 * HY;
+          uint8_t* out = p.dst + (size_t)y * p.dstPitch + lx;
+          const uint32_t lo = __byte_perm(__byte_perm(__float_as_uint(o[0]), __float_as_uint(o[1]), 0x0040),
+                                          __byte_perm(__float_as_uint(o[2]), __float_as_uint(o[3]), 0x0040), 0x5410);
+          const uint32_t hi = __byte_perm(__byte_perm(__float_as_uint(o[4]), __float_as_uint(o[5]), 0x0040),
+                                          __byte_perm(__float_as_uint(o[6]), __float_as_uint(o[7]), 0x0040), 0x5410);
+          if (wide) {
+            *reinterpret_cast<uint2*>(out) = make_uint2(lo, hi);
+          } else {
+#pragma unroll
+            for (int m = 0; m < 8; ++m)
+              if (m < nValid) out[m] = (uint8_t)((m < 4 ? lo >> (8 * m) : hi >> (8 * (m - 4))) & 0xFF);
+          }
+        }
+      }
+    }
+  }
+}
+
+template <int HY>
+__global__ void __launch_bounds__(128, 3) blurStripKernel(StripParams p) {
+  const int job = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (job >= p.numJobs) return;
+  const StripJob j = p.jobs[job];
+  if (j.edge) stripBody<HY, true>(p, j, threadIdx.x & 31);
+  else stripBody<HY, false>(p, j, threadIdx.x & 31);
 }
 
 // Fallback for kernels too large for a shared-memory tile (sigma can reach half the plane width):
@@ -479,6 +669,19 @@ cudaError_t launchGatherStaged(const GatherParams& p, const StagedParams& sp, co
     case 17: return launchStagedK<8, 1>(p, sp, map, numSMs, stream);
     default: return cudaErrorInvalidValue;
   }
+}
+
+cudaError_t launchBlurStrips(const StripParams& p, int hy, cudaStream_t stream) {
+  if (p.numJobs <= 0) return cudaSuccess;
+  const int grid = (p.numJobs + 3) / 4;
+  switch (hy) {
+    case 0: case 1: blurStripKernel<1><<<grid, 128, 0, stream>>>(p); break;  // hy == 0: one tap, padded with two zeros
+    case 2: blurStripKernel<2><<<grid, 128, 0, stream>>>(p); break;
+    case 3: blurStripKernel<3><<<grid, 128, 0, stream>>>(p); break;
+    default: return cudaErrorInvalidValue;
+  }
+  gLaunches.fetch_add(1, std::memory_order_relaxed);
+  return cudaGetLastError();
 }
 
 cudaError_t launchBlur(const BlurParams& p, cudaStream_t stream) {

@@ -58,6 +58,26 @@ struct BlurParams {
   int tileSmemBytes;  // dynamic shared memory each block needs (max over jobs)
 };
 
+// One warp-job of the register-resident low-pass: a strip of up to 256 columns (8 per lane) x h rows inside one
+// plan segment.  kxOffset points at the segment's horizontal taps zero-padded to kxChunks * 4 floats (16-byte
+// aligned); kyOffset at the 2*hy+1 vertical taps.
+struct StripJob {
+  int x0, y0, w, h;
+  int kxOffset, kxChunks, kxCount, kyOffset;
+  int edge;  // 1: the strip's reads would cross the plane's left/right border -> clamped byte loads
+};
+
+struct StripParams {
+  const uint8_t* src;
+  uint8_t* dst;
+  int width, height, srcPitch, dstPitch;
+  const StripJob* jobs;
+  int numJobs;
+  const float* taps;
+};
+
+constexpr int kStripLanePx = 8, kStripW = 32 * kStripLanePx, kStripMaxHy = 3;
+
 constexpr int kBlurTileW = 64, kBlurTileH = 32;
 constexpr int kBlurMaxSmem = 96 * 1024;
 
@@ -68,6 +88,7 @@ cudaError_t launchGather(const GatherParams& p, const int* tileList, int numList
 // with the staging box of (p.kernelSize, boxClass).  BORDER_WRAP only (tiles touching a border are never staged).
 cudaError_t launchGatherStaged(const GatherParams& p, const StagedParams& sp, const void* tensorMap, int boxClass,
                                int numSMs, cudaStream_t stream);
+cudaError_t launchBlurStrips(const StripParams& p, int hy, cudaStream_t stream);  // register-resident, hy <= kStripMaxHy
 cudaError_t launchBlur(const BlurParams& p, cudaStream_t stream);        // shared-memory tiles
 cudaError_t launchBlurDirect(const BlurParams& p, cudaStream_t stream);  // any kernel size, slow
 unsigned long long kernelLaunchCount();

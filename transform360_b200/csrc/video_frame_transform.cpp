@@ -30,6 +30,7 @@ namespace {
 using t360::BlurJob;
 using t360::HostPlan;
 using t360::StagedTile;
+using t360::StripJob;
 
 struct CudaFail {
   cudaError_t err;
@@ -82,11 +83,14 @@ struct DevicePlan {
   DeviceBuffer<int> fallbackTiles;
   int numStaged[t360::kNumBoxClasses] = {}, numFallback = 0;
   int totalStaged() const { int n = 0; for (int c : numStaged) n += c; return n; }
+  // low-pass: register-resident strip jobs grouped by vertical half-size 1..3, and the rest (large vertical kernels)
+  DeviceBuffer<StripJob> stripJobs[t360::kStripMaxHy];
+  int numStripJobs[t360::kStripMaxHy] = {};
   DeviceBuffer<BlurJob> tileJobs, directJobs;
   int numTileJobs = 0, numDirectJobs = 0, tileSmem = 0;
   DeviceBuffer<float> taps;
   size_t deviceBytes() const {
-    return samples.bytes() + stagedTiles[0].bytes() + stagedTiles[1].bytes() + fallbackTiles.bytes() + tileJobs.bytes() + directJobs.bytes() + taps.bytes();
+    return samples.bytes() + stagedTiles[0].bytes() + stagedTiles[1].bytes() + fallbackTiles.bytes() + stripJobs[0].bytes() + stripJobs[1].bytes() + stripJobs[2].bytes() + tileJobs.bytes() + directJobs.bytes() + taps.bytes();
   }
 };
 
@@ -138,6 +142,8 @@ class VideoFrameTransform {
       plans_.clear();
       for (auto& w : weights_) w.release();
       stagingIn_.release(); stagingOut_.release(); blurred_.release();
+      for (auto& st : side_) if (st) cudaStreamDestroy(st);
+      for (auto& e : forkJoin_) if (e) cudaEventDestroy(e);
       if (stream_) cudaStreamDestroy(stream_);
     }
   }
@@ -262,7 +268,8 @@ class VideoFrameTransform {
     auto it = plans_.find(planIndex);
     if (it == plans_.end()) return false;
     counts[0] = it->second.totalStaged(); counts[1] = it->second.numFallback;
-    counts[2] = it->second.numTileJobs; counts[3] = it->second.numDirectJobs;
+    counts[2] = it->second.numStripJobs[0] + it->second.numStripJobs[1] + it->second.numStripJobs[2];
+    counts[3] = it->second.numTileJobs + it->second.numDirectJobs;
     return true;
   }
   size_t planBytes(int planIndex) {
@@ -285,6 +292,8 @@ class VideoFrameTransform {
     CU(cudaGetDeviceProperties(&prop, device_));
     numSMs_ = prop.multiProcessorCount;
     CU(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+    for (auto& st : side_) CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    for (auto& e : forkJoin_) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     deviceReady_ = true;
   }
 
@@ -385,30 +394,103 @@ class VideoFrameTransform {
   // into CTA-sized jobs.  Segments that do not fit the plane are dropped, like the reference's caught cv::Exception.
   void buildBlurJobs(const HostPlan& h, DevicePlan& d) {
     std::vector<BlurJob> tiles, direct;
+    std::vector<StripJob> strips[t360::kStripMaxHy];
+    std::vector<float> taps = h.taps;  // original taps first (offsets of the plan stay valid), padded copies appended
     int offX[2] = {0, 0}, offY[2] = {0, 0}, passes = 1;
     if (ctx_.input_stereo_format == STEREO_FORMAT_LR) { passes = 2; offX[1] = static_cast<int>(0.5 * h.inW); }
     else if (ctx_.input_stereo_format == STEREO_FORMAT_TB) { passes = 2; offY[1] = static_cast<int>(0.5 * h.inH); }
     std::vector<uint8_t> covered(static_cast<size_t>(h.inW) * h.inH, 0);
     int tileSmem = 0;
-    for (int pass = 0; pass < passes; ++pass)
-      for (const t360::LowPassSegment& s : h.segments) {
+    // a warp-job covers 256 columns x `rows` rows; keep the grid at several thousand warps even for small planes
+    const long long stripsPerRow = (h.inW + t360::kStripW - 1) / t360::kStripW;
+    // (each job recomputes 2*hy rows of horizontal sums at its top and bottom, so never fewer than 8 rows)
+    const long long wanted = static_cast<long long>(h.inH) * stripsPerRow / 5000;
+    const int rowsBudget = wanted >= 32 ? 32 : (wanted >= 16 ? 16 : 8);
+
+    auto sameTaps = [&](int offA, int nA, int offB, int nB) {
+      return nA == nB && (offA == offB || std::memcmp(&h.taps[offA], &h.taps[offB], sizeof(float) * nA) == 0);
+    };
+    // horizontal taps zero-padded to whole chunks of 4 at a 16-byte aligned offset (fma(0, p, s) == s exactly)
+    std::map<std::pair<int, int>, std::pair<int, int>> paddedKx;
+    auto padKx = [&](int off, int n) {
+      auto it = paddedKx.find({off, n});
+      if (it != paddedKx.end()) return it->second;
+      while (taps.size() % 4) taps.push_back(0.f);
+      const int at = static_cast<int>(taps.size()), chunks = (n + 3) / 4;
+      for (int i = 0; i < chunks * 4; ++i) taps.push_back(i < n ? h.taps[off + i] : 0.f);
+      return paddedKx[{off, n}] = std::make_pair(at, chunks);
+    };
+    std::map<int, int> paddedKy1;  // a single vertical tap k becomes {0, k, 0}
+    auto padKy = [&](int off, int n) {
+      if (n != 1) return off;
+      auto it = paddedKy1.find(off);
+      if (it != paddedKy1.end()) return it->second;
+      const int at = static_cast<int>(taps.size());
+      taps.push_back(0.f); taps.push_back(h.taps[off]); taps.push_back(0.f);
+      return paddedKy1[off] = at;
+    };
+
+    for (int pass = 0; pass < passes; ++pass) {
+      // segments of one band that are horizontally adjacent and carry bit-identical kernels (always the case when
+      // the view-dependent scale is 1, e.g. no off-centre projection) are merged into one wide segment
+      size_t i = 0;
+      while (i < h.segments.size()) {
+        t360::LowPassSegment s = h.segments[i];
+        size_t j = i + 1;
+        while (j < h.segments.size()) {
+          const t360::LowPassSegment& n = h.segments[j];
+          if (n.top != s.top || n.height != s.height || n.left != s.left + s.width ||
+              !sameTaps(n.kxOffset, n.kxCount, s.kxOffset, s.kxCount) || !sameTaps(n.kyOffset, n.kyCount, s.kyOffset, s.kyCount))
+            break;
+          s.width += n.width;
+          ++j;
+        }
+        i = j;
         const int left = s.left + offX[pass], top = s.top + offY[pass];
+        // a segment that does not fit the plane is dropped, like the reference's caught cv::Exception (cpp:183-203)
         if (left < 0 || top < 0 || s.width <= 0 || s.height <= 0 || left + s.width > h.inW || top + s.height > h.inH) continue;
         for (int y = 0; y < s.height; ++y) std::memset(&covered[static_cast<size_t>(top + y) * h.inW + left], 1, s.width);
-        for (int ty = 0; ty < s.height; ty += t360::kBlurTileH)
-          for (int tx = 0; tx < s.width; tx += t360::kBlurTileW) {
-            BlurJob j{left + tx, top + ty, std::min(t360::kBlurTileW, s.width - tx), std::min(t360::kBlurTileH, s.height - ty),
-                      s.kxOffset, s.kxCount, s.kyOffset, s.kyCount};
-            const long long need = static_cast<long long>(t360::blurTileSmem(j.w, j.h, j.kxCount, j.kyCount));
-            if (need <= t360::kBlurMaxSmem) {
-              tiles.push_back(j);
-              tileSmem = std::max(tileSmem, static_cast<int>(need));
-            } else {
-              direct.push_back(j);
+        const int hy = s.kyCount / 2;
+        if (hy <= t360::kStripMaxHy && (s.kyCount & 1) && (s.kxCount & 1)) {
+          const auto kx = padKx(s.kxOffset, s.kxCount);
+          const int kyOff = padKy(s.kyOffset, s.kyCount), hx = s.kxCount / 2;
+          const int rows = std::min(rowsBudget, kx.second <= 3 ? 32 : (kx.second <= 8 ? 16 : 8));
+          for (int ty = 0; ty < s.height; ty += rows)
+            for (int tx = 0; tx < s.width; tx += t360::kStripW) {
+              StripJob j{left + tx, top + ty, std::min(t360::kStripW, s.width - tx), std::min(rows, s.height - ty),
+                         kx.first, kx.second, s.kxCount, kyOff, 0};
+              // interior strips read whole aligned words: first byte - 3 and the last prefetched group must stay in the row
+              const int firstByte = j.x0 - hx, lastByte = j.x0 + t360::kStripW - t360::kStripLanePx - hx + 4 * (kx.second + 3) + 7;
+              j.edge = (firstByte - 4 < 0 || lastByte >= h.inW) ? 1 : 0;
+              strips[std::max(hy, 1) - 1].push_back(j);
             }
-          }
+        } else {
+          for (int ty = 0; ty < s.height; ty += t360::kBlurTileH)
+            for (int tx = 0; tx < s.width; tx += t360::kBlurTileW) {
+              BlurJob j{left + tx, top + ty, std::min(t360::kBlurTileW, s.width - tx), std::min(t360::kBlurTileH, s.height - ty),
+                        s.kxOffset, s.kxCount, s.kyOffset, s.kyCount};
+              const long long need = static_cast<long long>(t360::blurTileSmem(j.w, j.h, j.kxCount, j.kyCount));
+              if (need <= t360::kBlurMaxSmem) {
+                tiles.push_back(j);
+                tileSmem = std::max(tileSmem, static_cast<int>(need));
+              } else {
+                direct.push_back(j);
+              }
+            }
+        }
       }
+    }
     d.blurNeedsClear = std::find(covered.begin(), covered.end(), 0) != covered.end();
+    for (int c = 0; c < t360::kStripMaxHy; ++c) {
+      // heaviest jobs first: the hardware block scheduler then balances the tail
+      std::stable_sort(strips[c].begin(), strips[c].end(), [](const StripJob& a, const StripJob& b) {
+        return static_cast<long long>(a.kxChunks + 2) * a.h * (1 + 3 * a.edge) > static_cast<long long>(b.kxChunks + 2) * b.h * (1 + 3 * b.edge);
+      });
+      d.numStripJobs[c] = static_cast<int>(strips[c].size());
+      if (strips[c].empty()) continue;
+      d.stripJobs[c].reserve(strips[c].size());
+      CU(cudaMemcpy(d.stripJobs[c].ptr, strips[c].data(), strips[c].size() * sizeof(StripJob), cudaMemcpyHostToDevice));
+    }
     d.numTileJobs = static_cast<int>(tiles.size());
     d.numDirectJobs = static_cast<int>(direct.size());
     d.tileSmem = tileSmem;
@@ -420,9 +502,9 @@ class VideoFrameTransform {
       d.directJobs.reserve(direct.size());
       CU(cudaMemcpy(d.directJobs.ptr, direct.data(), direct.size() * sizeof(BlurJob), cudaMemcpyHostToDevice));
     }
-    if (!h.taps.empty()) {
-      d.taps.reserve(h.taps.size());
-      CU(cudaMemcpy(d.taps.ptr, h.taps.data(), h.taps.size() * sizeof(float), cudaMemcpyHostToDevice));
+    if (!taps.empty()) {
+      d.taps.reserve(taps.size());
+      CU(cudaMemcpy(d.taps.ptr, taps.data(), taps.size() * sizeof(float), cudaMemcpyHostToDevice));
     }
   }
 
@@ -434,8 +516,13 @@ class VideoFrameTransform {
       // Not reproduced tile by tile: refuse rather than silently differ.
       throw std::runtime_error("plane size differs from the size the low-pass plan was generated for");
     }
+    for (int c = 0; c < t360::kStripMaxHy; ++c) {
+      if (!plan.numStripJobs[c]) continue;
+      t360::StripParams sp{dIn, dOut, w, h, inPitch, outPitch, plan.stripJobs[c].ptr, plan.numStripJobs[c], plan.taps.ptr};
+      CU(t360::launchBlurStrips(sp, c + 1, s));
+    }
     t360::BlurParams bp{dIn, dOut, w, h, inPitch, outPitch, plan.tileJobs.ptr, plan.numTileJobs, plan.taps.ptr, plan.tileSmem};
-    CU(t360::launchBlur(bp, s));
+    if (plan.numTileJobs) CU(t360::launchBlur(bp, s));
     if (plan.numDirectJobs) {
       bp.jobs = plan.directJobs.ptr;
       bp.numJobs = plan.numDirectJobs;
@@ -474,12 +561,32 @@ class VideoFrameTransform {
     for (int c = 0; c < t360::kNumBoxClasses && stage; ++c)
       if (plan.numStaged[c]) stage = encodePlaneMap(&maps[c], src, inW, inH, srcPitch, plan.kernelSize, c);
     if (stage) {
-      for (int c = 0; c < t360::kNumBoxClasses; ++c) {
+      // The tile lists are disjoint, so their kernels are independent.  The minority lists (general-path tiles
+      // near the poles and borders, wide-box tiles) are latency-bound and small: they are forked onto side
+      // streams so that they share the SMs with the main staged kernel instead of running after it.
+      int side = 0;
+      auto forked = [&](auto&& launch) {
+        if (side == 0) CU(cudaEventRecord(forkJoin_[0], s));
+        cudaStream_t ss = side_[side];
+        CU(cudaStreamWaitEvent(ss, forkJoin_[0], 0));
+        launch(ss);
+        CU(cudaEventRecord(forkJoin_[1 + side], ss));
+        ++side;
+      };
+      if (plan.numFallback)
+        forked([&](cudaStream_t ss) { CU(t360::launchGather(gp, plan.fallbackTiles.ptr, plan.numFallback, numSMs_, ss)); });
+      for (int c = t360::kNumBoxClasses - 1; c >= 1; --c) {
         if (!plan.numStaged[c]) continue;
-        t360::StagedParams sp{plan.stagedTiles[c].ptr, plan.numStaged[c]};
-        CU(t360::launchGatherStaged(gp, sp, &maps[c], c, numSMs_, s));
+        forked([&](cudaStream_t ss) {
+          t360::StagedParams sp{plan.stagedTiles[c].ptr, plan.numStaged[c]};
+          CU(t360::launchGatherStaged(gp, sp, &maps[c], c, numSMs_, ss));
+        });
       }
-      if (plan.numFallback) CU(t360::launchGather(gp, plan.fallbackTiles.ptr, plan.numFallback, numSMs_, s));
+      if (plan.numStaged[0]) {
+        t360::StagedParams sp{plan.stagedTiles[0].ptr, plan.numStaged[0]};
+        CU(t360::launchGatherStaged(gp, sp, &maps[0], 0, numSMs_, s));
+      }
+      for (int i = 0; i < side; ++i) CU(cudaStreamWaitEvent(s, forkJoin_[1 + i], 0));
     } else {
       CU(t360::launchGather(gp, nullptr, 0, numSMs_, s));
     }
@@ -492,6 +599,8 @@ class VideoFrameTransform {
   DeviceBuffer<int16_t> weights_[9];
   DeviceBuffer<uint8_t> stagingIn_, stagingOut_, blurred_;
   cudaStream_t stream_ = nullptr;
+  cudaStream_t side_[t360::kNumBoxClasses] = {};        // for the minority tile lists of a plane
+  cudaEvent_t forkJoin_[1 + t360::kNumBoxClasses] = {};  // [0] fork, [1..] joins
   int device_ = 0, numSMs_ = 0;
   bool deviceReady_ = false;
 };
