@@ -43,6 +43,14 @@ int T360B200_transformFramePlaneAsync(VideoFrameTransform* transform, const uint
                                       uint8_t* deviceOutput, int inputWidth, int inputHeight, int inputPitch,
                                       int outputWidth, int outputHeight, int outputPitch,
                                       int transformMatPlaneIndex, void* cudaStream);
+/* All planes of one frame in one call, device to device, asynchronous on `cudaStream`: plane 0 uses plan index 0,
+ * planes 1 and 2 plan index 1 (the reference filter's convention, vf_transform360.c:372) and run concurrently with
+ * plane 0 on internal streams; `cudaStream` observes the completion of all of them.  Arrays have numPlanes (1..3)
+ * entries: device pointers, per-plane widths / heights / pitches in bytes. */
+int T360B200_transformFrameAsync(VideoFrameTransform* transform, int numPlanes, const uint8_t* const* deviceInputs,
+                                 uint8_t* const* deviceOutputs, const int* inputWidths, const int* inputHeights,
+                                 const int* inputPitches, const int* outputWidths, const int* outputHeights,
+                                 const int* outputPitches, void* cudaStream);
 /* Runs only the segmented low-pass stage (reference filterPlane, cpp:621-704) device to device. */
 int T360B200_lowPassPlaneAsync(VideoFrameTransform* transform, const uint8_t* deviceInput, uint8_t* deviceOutput,
                                int width, int height, int inputPitch, int outputPitch,

@@ -127,6 +127,16 @@ bool encodePlaneMap(CUtensorMap* map, const uint8_t* base, int w, int h, int pit
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// Everything one image plane needs to be in flight independently of the others: the frame entry point runs the
+// luma plane on the caller's stream and the two chroma planes on their own lanes.
+constexpr int kPlaneLanes = 3;
+struct PlaneLane {
+  cudaStream_t main = nullptr;                       // chroma lanes only (lane 0 runs on the caller's stream)
+  cudaStream_t side[t360::kNumBoxClasses] = {};      // the minority gather tile lists of this plane
+  cudaEvent_t fork = nullptr, join[t360::kNumBoxClasses] = {}, done = nullptr;
+  DeviceBuffer<uint8_t> blurred;                     // low-pass output of this plane
+};
+
 constexpr int kPitchAlign = 256;
 inline int alignedPitch(int w) { return (w + kPitchAlign - 1) / kPitchAlign * kPitchAlign; }
 
@@ -141,9 +151,16 @@ class VideoFrameTransform {
       cudaSetDevice(device_);
       plans_.clear();
       for (auto& w : weights_) w.release();
-      stagingIn_.release(); stagingOut_.release(); blurred_.release();
-      for (auto& st : side_) if (st) cudaStreamDestroy(st);
-      for (auto& e : forkJoin_) if (e) cudaEventDestroy(e);
+      stagingIn_.release(); stagingOut_.release();
+      for (PlaneLane& l : lanes_) {
+        l.blurred.release();
+        if (l.main) cudaStreamDestroy(l.main);
+        for (auto& st : l.side) if (st) cudaStreamDestroy(st);
+        for (auto& e : l.join) if (e) cudaEventDestroy(e);
+        if (l.fork) cudaEventDestroy(l.fork);
+        if (l.done) cudaEventDestroy(l.done);
+      }
+      if (frameFork_) cudaEventDestroy(frameFork_);
       if (stream_) cudaStreamDestroy(stream_);
     }
   }
@@ -200,7 +217,7 @@ class VideoFrameTransform {
       } else if (plan->transparent && planIndex) {
         CU(cudaMemset2DAsync(dOut, dOutPitch, 128, outW, outH, stream_));
       }
-      if (!enqueue(*plan, dIn, dOut, inW, inH, dInPitch, outW, outH, dOutPitch, stream_, imagePlaneIndex)) return false;
+      if (!enqueue(*plan, dIn, dOut, inW, inH, dInPitch, outW, outH, dOutPitch, stream_, imagePlaneIndex, lanes_[0])) return false;
       if (!outOnDevice)
         CU(cudaMemcpy2DAsync(out, outPitch, dOut, dOutPitch, outW, outH, cudaMemcpyDeviceToHost, stream_));
       CU(cudaStreamSynchronize(stream_));
@@ -224,13 +241,48 @@ class VideoFrameTransform {
       if (!plan) return false;
       cudaStream_t s = stream ? stream : stream_;
       if (plan->transparent && planIndex) CU(cudaMemset2DAsync(dOut, outPitch, 128, outW, outH, s));
-      return enqueue(*plan, dIn, dOut, inW, inH, inPitch, outW, outH, outPitch, s, planIndex);
+      return enqueue(*plan, dIn, dOut, inW, inH, inPitch, outW, outH, outPitch, s, planIndex, lanes_[0]);
     } catch (const CudaFail& f) {
       std::printf("Could not transform the plane %d. Error: CUDA %s (%s) in %s\n", planIndex, cudaGetErrorName(f.err),
                   cudaGetErrorString(f.err), f.what);
       cudaGetLastError();
     } catch (const std::exception& ex) {
       std::printf("Could not transform the plane %d. Error: %s\n", planIndex, ex.what());
+    }
+    return false;
+  }
+
+  // Whole frame, device to device, asynchronous: plane 0 with plan 0 on the caller's stream, planes 1.. with plan 1
+  // on their own lanes (the planes are independent: reference vf_transform360.c:368-397 loops over them).
+  bool transformFrameDevice(int numPlanes, const uint8_t* const* dIn, uint8_t* const* dOut, const int* inW, const int* inH,
+                            const int* inPitch, const int* outW, const int* outH, const int* outPitch, cudaStream_t stream) {
+    try {
+      if (numPlanes < 1 || numPlanes > kPlaneLanes) {
+        std::printf("Could not transform the frame. Error: %d planes (1..%d supported)\n", numPlanes, kPlaneLanes);
+        return false;
+      }
+      ensureDevice();
+      cudaStream_t s = stream ? stream : stream_;
+      if (numPlanes > 1) CU(cudaEventRecord(frameFork_, s));
+      bool ok = true;
+      for (int p = numPlanes - 1; p >= 0 && ok; --p) {  // small planes first: they fill in around the luma kernels
+        const int planIndex = p ? 1 : 0;
+        const DevicePlan* plan = findPlan(planIndex, p);
+        if (!plan) return false;
+        PlaneLane& lane = lanes_[p];
+        cudaStream_t ps = p ? lane.main : s;
+        if (p) CU(cudaStreamWaitEvent(ps, frameFork_, 0));
+        if (plan->transparent && planIndex) CU(cudaMemset2DAsync(dOut[p], outPitch[p], 128, outW[p], outH[p], ps));
+        ok = enqueue(*plan, dIn[p], dOut[p], inW[p], inH[p], inPitch[p], outW[p], outH[p], outPitch[p], ps, p, lane);
+        if (p) CU(cudaEventRecord(lane.done, ps));
+      }
+      for (int p = 1; p < numPlanes; ++p) CU(cudaStreamWaitEvent(s, lanes_[p].done, 0));
+      return ok;
+    } catch (const CudaFail& f) {
+      std::printf("Could not transform the frame. Error: CUDA %s (%s) in %s\n", cudaGetErrorName(f.err), cudaGetErrorString(f.err), f.what);
+      cudaGetLastError();
+    } catch (const std::exception& ex) {
+      std::printf("Could not transform the frame. Error: %s\n", ex.what());
     }
     return false;
   }
@@ -292,8 +344,15 @@ class VideoFrameTransform {
     CU(cudaGetDeviceProperties(&prop, device_));
     numSMs_ = prop.multiProcessorCount;
     CU(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
-    for (auto& st : side_) CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-    for (auto& e : forkJoin_) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (int i = 0; i < kPlaneLanes; ++i) {
+      PlaneLane& l = lanes_[i];
+      if (i > 0) CU(cudaStreamCreateWithFlags(&l.main, cudaStreamNonBlocking));
+      for (auto& st : l.side) CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+      for (auto& e : l.join) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      CU(cudaEventCreateWithFlags(&l.fork, cudaEventDisableTiming));
+      CU(cudaEventCreateWithFlags(&l.done, cudaEventDisableTiming));
+    }
+    CU(cudaEventCreateWithFlags(&frameFork_, cudaEventDisableTiming));
     deviceReady_ = true;
   }
 
@@ -532,7 +591,7 @@ class VideoFrameTransform {
 
   // reference transformPlane (cpp:707-794): [low-pass] -> gather.  Device pointers, asynchronous.
   bool enqueue(const DevicePlan& plan, const uint8_t* dIn, uint8_t* dOut, int inW, int inH, int inPitch, int outW,
-               int outH, int outPitch, cudaStream_t s, int imagePlaneIndex) {
+               int outH, int outPitch, cudaStream_t s, int imagePlaneIndex, PlaneLane& lane) {
     if (plan.kernelSize == 0) {
       std::printf("Could not find interpolation algorithm for plane %d", imagePlaneIndex);  // reference cpp:780-784
       return true;
@@ -547,9 +606,9 @@ class VideoFrameTransform {
     int srcPitch = inPitch;
     if (plan.lowPass) {
       const int bp = alignedPitch(inW);
-      blurred_.reserve(static_cast<size_t>(bp) * inH + 64);
-      runLowPass(plan, dIn, blurred_.ptr, inW, inH, inPitch, bp, s);
-      src = blurred_.ptr;
+      lane.blurred.reserve(static_cast<size_t>(bp) * inH + 64);
+      runLowPass(plan, dIn, lane.blurred.ptr, inW, inH, inPitch, bp, s);
+      src = lane.blurred.ptr;
       srcPitch = bp;
     }
     t360::GatherParams gp{src, inW, inH, srcPitch, dOut, outW, outH, outPitch, plan.samples.ptr, plan.samplesPitch,
@@ -566,11 +625,11 @@ class VideoFrameTransform {
       // streams so that they share the SMs with the main staged kernel instead of running after it.
       int side = 0;
       auto forked = [&](auto&& launch) {
-        if (side == 0) CU(cudaEventRecord(forkJoin_[0], s));
-        cudaStream_t ss = side_[side];
-        CU(cudaStreamWaitEvent(ss, forkJoin_[0], 0));
+        if (side == 0) CU(cudaEventRecord(lane.fork, s));
+        cudaStream_t ss = lane.side[side];
+        CU(cudaStreamWaitEvent(ss, lane.fork, 0));
         launch(ss);
-        CU(cudaEventRecord(forkJoin_[1 + side], ss));
+        CU(cudaEventRecord(lane.join[side], ss));
         ++side;
       };
       if (plan.numFallback)
@@ -586,7 +645,7 @@ class VideoFrameTransform {
         t360::StagedParams sp{plan.stagedTiles[0].ptr, plan.numStaged[0]};
         CU(t360::launchGatherStaged(gp, sp, &maps[0], 0, numSMs_, s));
       }
-      for (int i = 0; i < side; ++i) CU(cudaStreamWaitEvent(s, forkJoin_[1 + i], 0));
+      for (int i = 0; i < side; ++i) CU(cudaStreamWaitEvent(s, lane.join[i], 0));
     } else {
       CU(t360::launchGather(gp, nullptr, 0, numSMs_, s));
     }
@@ -597,10 +656,10 @@ class VideoFrameTransform {
   std::mutex mu_;
   std::map<int, DevicePlan> plans_;
   DeviceBuffer<int16_t> weights_[9];
-  DeviceBuffer<uint8_t> stagingIn_, stagingOut_, blurred_;
+  DeviceBuffer<uint8_t> stagingIn_, stagingOut_;
+  PlaneLane lanes_[kPlaneLanes];
+  cudaEvent_t frameFork_ = nullptr;
   cudaStream_t stream_ = nullptr;
-  cudaStream_t side_[t360::kNumBoxClasses] = {};        // for the minority tile lists of a plane
-  cudaEvent_t forkJoin_[1 + t360::kNumBoxClasses] = {};  // [0] fork, [1..] joins
   int device_ = 0, numSMs_ = 0;
   bool deviceReady_ = false;
 };
@@ -677,6 +736,12 @@ T360_API int T360B200_transformFramePlaneAsync(VideoFrameTransform* t, const uin
                                                int inPitch, int outW, int outH, int outPitch, int planIndex, void* stream) {
   if (!t || !dIn || !dOut) return 0;
   return t->transformDevice(dIn, dOut, inW, inH, inPitch, outW, outH, outPitch, planIndex, static_cast<cudaStream_t>(stream));
+}
+T360_API int T360B200_transformFrameAsync(VideoFrameTransform* t, int numPlanes, const uint8_t* const* dIn, uint8_t* const* dOut,
+                                          const int* inW, const int* inH, const int* inPitch, const int* outW, const int* outH,
+                                          const int* outPitch, void* stream) {
+  if (!t || !dIn || !dOut || !inW || !inH || !inPitch || !outW || !outH || !outPitch) return 0;
+  return t->transformFrameDevice(numPlanes, dIn, dOut, inW, inH, inPitch, outW, outH, outPitch, static_cast<cudaStream_t>(stream));
 }
 T360_API int T360B200_lowPassPlaneAsync(VideoFrameTransform* t, const uint8_t* dIn, uint8_t* dOut, int w, int h, int inPitch,
                                         int outPitch, int planIndex, void* stream) {

@@ -100,6 +100,8 @@ def load(path: os.PathLike | None = None):
     L.T360B200_remapTable.argtypes = [ci, C.POINTER(vp)]
     L.T360B200_transformFramePlaneAsync.restype = ci
     L.T360B200_transformFramePlaneAsync.argtypes = [vp, vp, vp] + [ci] * 7 + [vp]
+    L.T360B200_transformFrameAsync.restype = ci
+    L.T360B200_transformFrameAsync.argtypes = [vp, ci, vp, vp] + [vp] * 6 + [vp]
     L.T360B200_lowPassPlaneAsync.restype = ci
     L.T360B200_lowPassPlaneAsync.argtypes = [vp, vp, vp] + [ci] * 5 + [vp]
     L.T360B200_synchronize.restype = ci
@@ -122,7 +124,8 @@ EXPORTED_SYMBOLS = [
     "VideoFrameTransform_new", "VideoFrameTransform_delete", "VideoFrameTransform_generateMapForPlane",
     "VideoFrameTransform_transformFramePlane", "T360B200_hostPlanCreate", "T360B200_hostPlanDestroy",
     "T360B200_hostPlanInfo", "T360B200_hostPlanMap", "T360B200_hostPlanSamples", "T360B200_hostPlanSegment",
-    "T360B200_remapTable", "T360B200_transformFramePlaneAsync", "T360B200_lowPassPlaneAsync",
+    "T360B200_remapTable", "T360B200_transformFramePlaneAsync", "T360B200_transformFrameAsync",
+    "T360B200_lowPassPlaneAsync",
     "T360B200_synchronize", "T360B200_stream", "T360B200_kernelLaunchCount", "T360B200_planDeviceBytes",
     "T360B200_planTileCounts", "T360B200_deviceCount", "T360B200_version",
 ]
@@ -182,6 +185,24 @@ class VideoFrameTransform:
                               stream: int = 0) -> bool:
         return bool(self._lib.T360B200_transformFramePlaneAsync(self._h, d_in, d_out, in_w, in_h, in_pitch, out_w,
                                                                 out_h, out_pitch, plan_index, stream))
+
+    def make_frame_call(self, in_planes, out_planes, dims):
+        """Prebuilds the argument arrays of T360B200_transformFrameAsync for one (input frame, output frame) pair.
+        in_planes / out_planes: per plane (device_address, pitch); dims: per plane (in_w, in_h, out_w, out_h).
+        Returns a callable f(stream) -> bool that enqueues the whole frame."""
+        n = len(in_planes)
+        VP, IA = C.c_void_p * n, C.c_int * n
+        d_in = VP(*[p[0] for p in in_planes])
+        d_out = VP(*[p[0] for p in out_planes])
+        arrs = [IA(*[d[0] for d in dims]), IA(*[d[1] for d in dims]), IA(*[p[1] for p in in_planes]),
+                IA(*[d[2] for d in dims]), IA(*[d[3] for d in dims]), IA(*[p[1] for p in out_planes])]
+        fn, h = self._lib.T360B200_transformFrameAsync, self._h
+        ptrs = [C.cast(a, C.c_void_p) for a in arrs]
+        pin, pout = C.cast(d_in, C.c_void_p), C.cast(d_out, C.c_void_p)
+
+        def call(stream: int = 0, _keep=(d_in, d_out, arrs)) -> bool:
+            return bool(fn(h, n, pin, pout, *ptrs, stream))
+        return call
 
     def low_pass_async(self, d_in: int, d_out: int, w, h, in_pitch, out_pitch, plan_index, stream: int = 0) -> bool:
         return bool(self._lib.T360B200_lowPassPlaneAsync(self._h, d_in, d_out, w, h, in_pitch, out_pitch, plan_index,

@@ -90,13 +90,17 @@ class FrameTransformer:
     def close(self):
         self.vft.close()
 
+    def frame_call(self, in_planes, out_planes):
+        """Prebuilt whole-frame call (T360B200_transformFrameAsync) for one (input, output) buffer pair:
+        in_planes / out_planes are per plane (device_address, pitch).  Returns f(stream) -> bool."""
+        dims = [self.spec.plane_dims(p)[:4] for p in range(self.spec.num_planes)]
+        return self.vft.make_frame_call(in_planes, out_planes, dims)
+
     def transform_frame_device(self, in_planes, out_planes, stream: int = 0):
-        """in_planes / out_planes: per plane (device_address, pitch).  Asynchronous on `stream`."""
-        for p in range(self.spec.num_planes):
-            iw, ih, ow, oh, idx = self.spec.plane_dims(p)
-            (src, sp), (dst, dp) = in_planes[p], out_planes[p]
-            if not self.vft.transform_plane_async(src, dst, iw, ih, sp, ow, oh, dp, idx, stream):
-                raise RuntimeError("T360B200_transformFramePlaneAsync failed (message on stdout)")
+        """in_planes / out_planes: per plane (device_address, pitch).  Asynchronous on `stream`; the planes of
+        the frame run concurrently on the transform's internal lanes."""
+        if not self.frame_call(in_planes, out_planes)(stream):
+            raise RuntimeError("T360B200_transformFrameAsync failed (message on stdout)")
 
     def transform_frame_host(self, in_planes, out_planes):
         """in_planes / out_planes: per plane (host_address, pitch).  The reference-facing, synchronous path."""
