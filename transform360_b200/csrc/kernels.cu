@@ -56,6 +56,9 @@ __device__ __forceinline__ int2 loadPlan(const int2* p) {
   return r;
 }
 
+__device__ __forceinline__ int recordColumn(int word0) { return (int)((unsigned)word0 >> kRecordColumnShift); }
+__device__ __forceinline__ int recordCol0(int word0) { return (word0 << (32 - kRecordColumnShift)) >> (32 - kRecordColumnShift); }
+
 __device__ __forceinline__ int wrapIndex(int p, int n) {  // cv::borderInterpolate(BORDER_WRAP)
   if ((unsigned)p < (unsigned)n) return p;
   p %= n;
@@ -70,17 +73,8 @@ __device__ __forceinline__ int reflect101(int p, int n) {  // what remap uses fo
 template <int K>
 __host__ __device__ constexpr int weightBytes() { return 1024 * K * K * 2; }
 
-// Where the weights of phase a = (fracY << 5) | fracX live in the shared table.  A 128-bit shared load is
-// served 8 lanes at a time from 8 bank groups of 16 bytes (a 64-bit one 16 lanes from 16 groups); the group
-// is the low bits of the slot index.  Adjacent output pixels step fracX by a near-constant amount (48/32 px
-// for the 8K -> 1280-face case, i.e. 16 mod 32) while fracY drifts slowly, so indexing by fracX alone would
-// put the 8 different phases of a quarter-warp into the same group.  Rotating the group by fracY spreads
-// them (measured: see DESIGN.md).
 template <int K>
-__device__ __forceinline__ int weightSlot(int phase) {
-  constexpr int kMask = K == 2 ? 15 : 7;
-  return (phase & ~kMask) | ((phase + (phase >> 5)) & kMask);
-}
+__device__ __forceinline__ int weightSlot(int phase) { return weightSlotOf(K, phase); }
 
 // Copies the [1024][K][K] int16 table into shared memory as [K*K/8][1024] 16-byte vectors (K >= 4) or
 // [1024] 8-byte vectors (K == 2), slot-permuted by weightSlot().
@@ -141,6 +135,70 @@ __device__ __forceinline__ int foldWindow(const uint32_t* __restrict__ words, in
       off += pitch;
     }
   }
+  return acc;
+}
+
+// Shared-memory flavour used by the staged kernel.  The staging pitch is a compile-time multiple of 4, so the
+// aligned word address of every window row is (base & ~3) + r * PITCH and the byte shift is the same for all rows:
+// one address computation per pixel, every load uses an immediate offset.
+template <int IMM>
+__device__ __forceinline__ uint32_t ldsWordImm(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(v) : "r"(addr), "n"(IMM));
+  return v;
+}
+template <int IMM>
+__device__ __forceinline__ uint4 ldsVecImm(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4+%5];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr), "n"(IMM));
+  return v;
+}
+template <int IMM>
+__device__ __forceinline__ uint2 ldsVec2Imm(uint32_t addr) {
+  uint2 v;
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2+%3];" : "=r"(v.x), "=r"(v.y) : "r"(addr), "n"(IMM));
+  return v;
+}
+
+template <int K, int PITCH, int R>
+struct WindowRows {
+  static __device__ __forceinline__ void run(uint32_t rowAddr, int sh, uint32_t wAddr, const uint4& wa, const uint4& wb,
+                                             const uint2& w2, int& acc) {
+    if constexpr (K == 2) {
+      const uint32_t b = __funnelshift_r(ldsWordImm<R * PITCH>(rowAddr), ldsWordImm<R * PITCH + 4>(rowAddr), sh);
+      acc = dp2aLo(R == 0 ? w2.x : w2.y, b, acc);
+    } else if constexpr (K == 4) {
+      const uint32_t b = __funnelshift_r(ldsWordImm<R * PITCH>(rowAddr), ldsWordImm<R * PITCH + 4>(rowAddr), sh);
+      const uint32_t w01 = R == 0 ? wa.x : (R == 1 ? wa.z : (R == 2 ? wb.x : wb.z));
+      const uint32_t w23 = R == 0 ? wa.y : (R == 1 ? wa.w : (R == 2 ? wb.y : wb.w));
+      acc = dp2aLo(w01, b, acc);
+      acc = dp2aHi(w23, b, acc);
+    } else {
+      const uint4 wt = ldsVecImm<R * 16384>(wAddr);
+      const uint32_t q0 = ldsWordImm<R * PITCH>(rowAddr), q1 = ldsWordImm<R * PITCH + 4>(rowAddr), q2 = ldsWordImm<R * PITCH + 8>(rowAddr);
+      const uint32_t b0 = __funnelshift_r(q0, q1, sh), b1 = __funnelshift_r(q1, q2, sh);
+      acc = dp2aLo(wt.x, b0, acc);
+      acc = dp2aHi(wt.y, b0, acc);
+      acc = dp2aLo(wt.z, b1, acc);
+      acc = dp2aHi(wt.w, b1, acc);
+    }
+    if constexpr (R + 1 < K) WindowRows<K, PITCH, R + 1>::run(rowAddr, sh, wAddr, wa, wb, w2, acc);
+  }
+};
+
+// stageAddr / wAddr: 32-bit shared-window addresses of the staging buffer and of the weight table
+template <int K, int PITCH>
+__device__ __forceinline__ int foldWindowShared(uint32_t stageAddr, int off, uint32_t wAddr, int phase) {
+  static_assert(PITCH % 4 == 0, "staging pitch must keep rows word-aligned");
+  const uint32_t rowAddr = stageAddr + (uint32_t)(off & ~3);
+  const int sh = (off & 3) * 8;
+  const uint32_t slotAddr = wAddr + (uint32_t)weightSlot<K>(phase) * (K == 2 ? 8u : 16u);
+  uint4 wa = make_uint4(0, 0, 0, 0), wb = wa;
+  uint2 w2 = make_uint2(0, 0);
+  if constexpr (K == 2) w2 = ldsVec2Imm<0>(slotAddr);
+  if constexpr (K == 4) { wa = ldsVecImm<0>(slotAddr); wb = ldsVecImm<16384>(slotAddr); }
+  int acc = 0;
+  WindowRows<K, PITCH, 0>::run(rowAddr, sh, slotAddr, wa, wb, w2, acc);
   return acc;
 }
 
@@ -207,17 +265,17 @@ gatherKernel(GatherParams p, const int* __restrict__ tileList, int tilesX, int n
     const int tile = tileList ? tileList[i] : i;
     const int ty = tile / tilesX, tx = tile - ty * tilesX;
     const int y0 = ty * gatherTileH(K) + warp * kRowsPerThread;
-    const int x = tx * kGatherTileW + lane;
-    if (y0 >= p.dstH || x >= p.dstW) continue;
+    const int segX = tx * kGatherTileW;
+    if (y0 >= p.dstH || segX + lane >= p.dstW) continue;  // records exist for every pixel of the plane, in lane order
     int2 rec[kRowsPerThread];
 #pragma unroll
     for (int j = 0; j < kRowsPerThread; ++j)
-      rec[j] = y0 + j < p.dstH ? loadPlan(p.samples + (size_t)(y0 + j) * p.samplesPitch + x) : make_int2(0, 0);
+      rec[j] = y0 + j < p.dstH ? loadPlan(p.samples + (size_t)(y0 + j) * p.samplesPitch + segX + lane) : make_int2(0, 0);
 #pragma unroll
     for (int j = 0; j < kRowsPerThread; ++j) {
       if (y0 + j >= p.dstH) break;
-      const int v = gatherPixel<K, TRANSPARENT>(s, smem, rec[j].x, rec[j].y);
-      if (!TRANSPARENT || v >= 0) p.dst[(size_t)(y0 + j) * p.dstPitch + x] = (uint8_t)v;
+      const int v = gatherPixel<K, TRANSPARENT>(s, smem, recordCol0(rec[j].x), rec[j].y);
+      if (!TRANSPARENT || v >= 0) p.dst[(size_t)(y0 + j) * p.dstPitch + segX + recordColumn(rec[j].x)] = (uint8_t)v;
     }
   }
 }
@@ -228,13 +286,14 @@ __global__ void __launch_bounds__(256, 4) nearestKernel(GatherParams p, int tile
   for (int tile = blockIdx.x; tile < numTiles; tile += gridDim.x) {
     const int ty = tile / tilesX, tx = tile - ty * tilesX;
     const int y0 = ty * gatherTileH(1) + warp * kRowsPerThread;
-    const int x = tx * kGatherTileW + lane;
-    if (y0 >= p.dstH || x >= p.dstW) continue;
+    const int segX = tx * kGatherTileW;
+    if (y0 >= p.dstH || segX + lane >= p.dstW) continue;
 #pragma unroll
     for (int j = 0; j < kRowsPerThread; ++j) {
       if (y0 + j >= p.dstH) break;
-      const int2 rec = loadPlan(p.samples + (size_t)(y0 + j) * p.samplesPitch + x);
-      int sx = rec.x, sy = rec.y >> 10;
+      const int2 rec = loadPlan(p.samples + (size_t)(y0 + j) * p.samplesPitch + segX + lane);
+      const int x = segX + recordColumn(rec.x);
+      int sx = recordCol0(rec.x), sy = rec.y >> 10;
       const bool inside = (unsigned)sx < (unsigned)p.srcW && (unsigned)sy < (unsigned)p.srcH;
       if (!inside && TRANSPARENT) continue;
       if (!inside) { sx = wrapIndex(sx, p.srcW); sy = wrapIndex(sy, p.srcH); }
@@ -269,7 +328,9 @@ __device__ __forceinline__ void tmaLoadBox(void* dst, const CUtensorMap* map, in
 }
 
 template <int K, int CLS>
-__host__ __device__ constexpr int stageBytes() { return stageBoxW(K, CLS) * stageBoxH(K, CLS) + 128; }  // + slack for the last word over-read
+__host__ __device__ constexpr int stageBytes() {  // + slack for the last word over-read; TMA destinations need 128-byte alignment
+  return (stageBoxW(K, CLS) * stageBoxH(K, CLS) + 64 + 127) & ~127;
+}
 template <int K, int CLS>
 __host__ __device__ constexpr int stagedSmemBytes() { return weightBytes<K>() + 2 * stageBytes<K, CLS>() + 64; }
 
@@ -293,6 +354,7 @@ gatherStagedKernel(GatherParams p, StagedParams sp, const __grid_constant__ CUte
   __syncthreads();
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t wAddr = smemAddr(wsmem);
   const int first = blockIdx.x;
   if (threadIdx.x == 0 && first < sp.numTiles) {
     const StagedTile t = sp.tiles[first];
@@ -302,10 +364,10 @@ gatherStagedKernel(GatherParams p, StagedParams sp, const __grid_constant__ CUte
   // software pipeline: the plan records (and tile header) of tile n+1 are fetched while tile n is computed
   auto fetch = [&](int i, StagedTile& t, int2 (&rec)[kRowsPerThread]) {
     t = sp.tiles[i];
-    const int y0 = t.outY + warp * kRowsPerThread, x = t.outX + lane;
+    const int y0 = t.outY + warp * kRowsPerThread, slot = t.outX + lane;  // records are stored in lane order
 #pragma unroll
     for (int j = 0; j < kRowsPerThread; ++j)
-      rec[j] = (x < p.dstW && y0 + j < p.dstH) ? loadPlan(p.samples + (size_t)(y0 + j) * p.samplesPitch + x) : make_int2(0, 0);
+      rec[j] = (slot < p.dstW && y0 + j < p.dstH) ? loadPlan(p.samples + (size_t)(y0 + j) * p.samplesPitch + slot) : make_int2(0, 0);
   };
   StagedTile tile{};
   int2 rec[kRowsPerThread] = {};
@@ -325,17 +387,16 @@ gatherStagedKernel(GatherParams p, StagedParams sp, const __grid_constant__ CUte
     if (next < sp.numTiles) fetch(next, tileNext, recNext);
 
     const int y0 = tile.outY + warp * kRowsPerThread;
-    const int x = tile.outX + lane;
     mbarWait(&bars[st], (it >> 1) & 1);
-    const uint32_t* words = reinterpret_cast<const uint32_t*>(stage0 + st * kStage);
-    if (x < p.dstW) {
+    const uint32_t stageAddr = smemAddr(stage0) + st * kStage;
+    if (tile.outX + lane < p.dstW) {
 #pragma unroll
       for (int j = 0; j < kRowsPerThread; ++j) {
         if (y0 + j >= p.dstH) break;
         const int row0 = rec[j].y >> 10, phase = rec[j].y & 1023;
-        const int off = (row0 - tile.boxY) * kPitch + (rec[j].x - tile.boxX);
-        const int acc = foldWindow<K, true>(words, off, kPitch, wsmem, phase);
-        p.dst[(size_t)(y0 + j) * p.dstPitch + x] = (uint8_t)roundToByte(acc);
+        const int off = (row0 - tile.boxY) * kPitch + (recordCol0(rec[j].x) - tile.boxX);
+        const int acc = foldWindowShared<K, kPitch>(stageAddr, off, wAddr, phase);
+        p.dst[(size_t)(y0 + j) * p.dstPitch + tile.outX + recordColumn(rec[j].x)] = (uint8_t)roundToByte(acc);
       }
     }
     __syncthreads();  // everyone is done with stage `st` before it is refilled two iterations later

@@ -35,7 +35,27 @@ __host__ __device__ constexpr int gatherTileH(int k) { return gatherThreads(k) /
 // source rows still reads conflict-free; 240 B = 60 words puts them 28 banks apart.
 constexpr int kNumBoxClasses = 2;
 __host__ __device__ constexpr int stageBoxW(int /*k*/, int cls) { return cls == 0 ? 192 : 240; }
+// (three 256-thread CTAs of the common class share an SM: 32 KB of cubic weights + two 12 KB stages each.  A fourth
+// fits with 63-row boxes but measured no faster -- the kernel is bound by shared-memory wavefronts, not by latency
+// -- and it leaves no room for the concurrently running minority-tile kernels.)
 __host__ __device__ constexpr int stageBoxH(int k, int cls) { return k == 8 ? (cls == 0 ? 112 : 144) : (cls == 0 ? 64 : 96); }
+
+// Shared-memory slot of the weights of phase a = (fracY << 5) | fracX.  A 128-bit shared load is served 8 lanes
+// (one quarter-warp) at a time out of 8 bank groups of 16 bytes -- a 64-bit one 16 lanes out of 16 groups -- and
+// the group is the low bits of the slot.  The slot takes fracX's HIGH bits as its low bits: of the hashes tried in
+// the offline bank simulator this one balances the phases of 32 adjacent pixels best.
+__host__ __device__ constexpr int weightSlotOf(int k, int phase) {
+  return k == 2 ? ((phase & ~31) | ((phase & 1) << 4) | ((phase & 31) >> 1))
+                : ((phase & ~31) | ((phase & 3) << 3) | ((phase & 31) >> 2));
+}
+__host__ __device__ constexpr int weightBankGroups(int k) { return k == 2 ? 16 : 8; }
+__host__ __device__ constexpr int weightLanesPerPass(int k) { return k == 2 ? 16 : 8; }
+
+// The sampling records of a plane are stored per 32-pixel row segment in LANE order, not column order: the host
+// deals the pixels of a segment to lanes so that the lanes served together by one shared-memory pass ask for
+// different bank groups (see buildLaneOrder in video_frame_transform.cpp).  Record word 0 therefore carries the
+// pixel's column inside the segment in its top 5 bits: x = segmentX + (word0 >> 27), col0 = (word0 << 5) >> 5.
+constexpr int kRecordColumnShift = 27;
 
 struct StagedParams {
   const StagedTile* tiles;  // device list

@@ -396,9 +396,7 @@ class VideoFrameTransform {
       deviceWeights(ctx_.interpolation_alg);
       d.samplesPitch = (h.mapW + 3) & ~3;
       std::vector<int2> padded(static_cast<size_t>(d.samplesPitch) * h.mapH, int2{0, 0});
-      for (int y = 0; y < h.mapH; ++y)
-        std::memcpy(&padded[static_cast<size_t>(y) * d.samplesPitch], &h.samples[static_cast<size_t>(y) * h.mapW],
-                    static_cast<size_t>(h.mapW) * sizeof(int2));
+      buildLaneOrder(h, padded, d.samplesPitch);
       d.samples.reserve(padded.size());
       CU(cudaMemcpy(d.samples.ptr, padded.data(), padded.size() * sizeof(int2), cudaMemcpyHostToDevice));
       if (d.kernelSize >= 2 && !d.transparent) buildGatherTiles(h, d);
@@ -406,6 +404,42 @@ class VideoFrameTransform {
     d.lowPass = ctx_.enable_low_pass_filter != 0;
     if (d.lowPass) buildBlurJobs(h, d);
     return d;
+  }
+
+  // Device order of the sampling records.  Each row is cut into segments of 32 pixels (= the width of a gather
+  // tile = one warp); inside a segment the pixels are dealt to LANES so that the lanes which one shared-memory pass
+  // serves together (8 for the 128-bit weight loads of cubic / Lanczos, 16 for the 64-bit ones of bilinear) ask for
+  // different bank groups of the weight table: sort the pixels by (bank group, phase), then deal them round-robin
+  // over the passes.  The window reads are unaffected (the warp still touches the same 32 windows) and the stores
+  // still fill one 32-byte sector.  The pixel's column inside the segment travels in the record's top 5 bits.
+  static void buildLaneOrder(const HostPlan& h, std::vector<int2>& out, int pitch) {
+    const int k = h.kernelSize;
+    const int groups = t360::weightBankGroups(k), lanesPerPass = t360::weightLanesPerPass(k), passes = 32 / lanesPerPass;
+    for (int y = 0; y < h.mapH; ++y) {
+      const t360::SamplePoint* row = &h.samples[static_cast<size_t>(y) * h.mapW];
+      int2* dst = &out[static_cast<size_t>(y) * pitch];
+      for (int x0 = 0; x0 < h.mapW; x0 += 32) {
+        const int n = std::min(32, h.mapW - x0);
+        int order[32];
+        for (int i = 0; i < n; ++i) order[i] = i;
+        if (k >= 2 && n == 32) {
+          auto keyOf = [&](int c) {
+            const int phase = row[x0 + c].rowPhase & 1023;
+            return ((t360::weightSlotOf(k, phase) & (groups - 1)) << 10) | phase;
+          };
+          std::stable_sort(order, order + n, [&](int a, int b) { return keyOf(a) < keyOf(b); });
+        }
+        for (int i = 0; i < n; ++i) {
+          // i-th pixel of the sorted sequence -> pass i % passes, position i / passes inside the pass
+          const int lane = (k >= 2 && n == 32) ? (i % passes) * lanesPerPass + i / passes : i;
+          const int c = order[i];
+          const t360::SamplePoint& sp = row[x0 + c];
+          dst[x0 + lane] = int2{static_cast<int>((static_cast<unsigned>(sp.col0) & ((1u << t360::kRecordColumnShift) - 1)) |
+                                                 (static_cast<unsigned>(c) << t360::kRecordColumnShift)),
+                                sp.rowPhase};
+        }
+      }
+    }
   }
 
   // Splits the output plane into CTA tiles and finds, per tile, the bounding box of all source windows.  A tile is
