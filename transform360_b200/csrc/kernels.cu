@@ -1,6 +1,6 @@
 // sm_100a kernels of the projection-remap hot path.
 //
-//   gatherStagedKernel<K>  replaces cv::remap as the reference calls it (VideoFrameTransform.cpp:748-754):
+//   gatherPlaneKernel<K>   replaces cv::remap as the reference calls it (VideoFrameTransform.cpp:748-754):
 //   gatherKernel<K>        per output pixel a K x K window of the 8-bit source is weighted with OpenCV's
 //                          15-bit fixed-point table and rounded with (sum + 16384) >> 15.  Bit-exact by
 //                          construction: same table (host-built, sampling.cpp), same integer arithmetic.
@@ -202,6 +202,86 @@ __device__ __forceinline__ int foldWindowShared(uint32_t stageAddr, int off, uin
   return acc;
 }
 
+// ---- column sharing (staged kernel) ---------------------------------------------------------------------
+// A thread computes 4 vertically adjacent output pixels.  On every face whose longitude does not depend on the
+// output row (4 of the 6 cube faces, and equirect->equirect) they sample the SAME source columns, and consecutive
+// pixels start 1 or 2 source rows apart, so their K-row windows overlap in K-1 or K-2 rows.  The window is kept in
+// registers and slid down: each further pixel fetches only its 1 or 2 new rows (2-4 shared-memory words instead of
+// 8 for cubic, 3-6 instead of 24 for Lanczos4).  Selecting "shift by 1 or by 2" is a SEL per row.
+template <int K>
+struct RowBytes {
+  uint32_t b[K / 4];  // the K source bytes of one window row, already aligned
+};
+
+template <int K>
+__device__ __forceinline__ RowBytes<K> loadWindowRow(const uint32_t* __restrict__ rowWords, int sh) {
+  RowBytes<K> o;
+  const uint32_t q0 = rowWords[0], q1 = rowWords[1];
+  o.b[0] = __funnelshift_r(q0, q1, sh);
+  if constexpr (K == 8) o.b[1] = __funnelshift_r(q1, rowWords[2], sh);
+  return o;
+}
+
+template <int K>
+__device__ __forceinline__ int foldRows(const RowBytes<K> (&W)[K], const unsigned char* wsmem, int phase) {
+  const uint4* tab = reinterpret_cast<const uint4*>(wsmem) + weightSlot<K>(phase);
+  int acc = 0;
+  if constexpr (K == 4) {
+    const uint4 wa = tab[0], wb = tab[1024];
+    acc = dp2aLo(wa.x, W[0].b[0], acc); acc = dp2aHi(wa.y, W[0].b[0], acc);
+    acc = dp2aLo(wa.z, W[1].b[0], acc); acc = dp2aHi(wa.w, W[1].b[0], acc);
+    acc = dp2aLo(wb.x, W[2].b[0], acc); acc = dp2aHi(wb.y, W[2].b[0], acc);
+    acc = dp2aLo(wb.z, W[3].b[0], acc); acc = dp2aHi(wb.w, W[3].b[0], acc);
+  } else {
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const uint4 wt = tab[r * 1024];
+      acc = dp2aLo(wt.x, W[r].b[0], acc); acc = dp2aHi(wt.y, W[r].b[0], acc);
+      acc = dp2aLo(wt.z, W[r].b[1], acc); acc = dp2aHi(wt.w, W[r].b[1], acc);
+    }
+  }
+  return acc;
+}
+
+// true when the 4 records of a thread can share their window columns: same first column, row steps of 1 or 2
+__device__ __forceinline__ bool columnShareable(const int2 (&rec)[4]) {
+  bool ok = true;
+#pragma unroll
+  for (int j = 1; j < 4; ++j) {
+    const int d = (rec[j].y >> 10) - (rec[j - 1].y >> 10);
+    ok = ok && (d == 1 || d == 2) && recordCol0(rec[j].x) == recordCol0(rec[0].x);
+  }
+  return ok;
+}
+
+template <int K, int PITCH>
+__device__ __forceinline__ void gatherColumnShared(const unsigned char* stage, int boxX, int boxY, const int2 (&rec)[4],
+                                                   const unsigned char* wsmem, int (&acc)[4]) {
+  static_assert(PITCH % 4 == 0 && (K == 4 || K == 8), "");
+  const int off = ((rec[0].y >> 10) - boxY) * PITCH + (recordCol0(rec[0].x) - boxX);
+  const uint32_t* rowWords = reinterpret_cast<const uint32_t*>(stage + (off & ~3));
+  const int sh = (off & 3) * 8;
+  RowBytes<K> W[K];
+#pragma unroll
+  for (int r = 0; r < K; ++r) W[r] = loadWindowRow<K>(rowWords + r * (PITCH / 4), sh);
+  acc[0] = foldRows<K>(W, wsmem, rec[0].y & 1023);
+#pragma unroll
+  for (int j = 1; j < 4; ++j) {
+    const int d = (rec[j].y >> 10) - (rec[j - 1].y >> 10);
+    rowWords += d * (PITCH / 4);
+    const RowBytes<K> last = loadWindowRow<K>(rowWords + (K - 1) * (PITCH / 4), sh);
+    RowBytes<K> prev = W[K - 1];
+    if (d == 2) prev = loadWindowRow<K>(rowWords + (K - 2) * (PITCH / 4), sh);
+#pragma unroll
+    for (int r = 0; r + 2 < K; ++r)
+#pragma unroll
+      for (int i = 0; i < K / 4; ++i) W[r].b[i] = d == 1 ? W[r + 1].b[i] : W[r + 2].b[i];
+    W[K - 2] = prev;
+    W[K - 1] = last;
+    acc[j] = foldRows<K>(W, wsmem, rec[j].y & 1023);
+  }
+}
+
 __device__ __forceinline__ int roundToByte(int acc) {  // FixedPtCast<int, uchar, 15>
   return min(max((acc + (1 << 14)) >> 15, 0), 255);
 }
@@ -331,75 +411,128 @@ template <int K, int CLS>
 __host__ __device__ constexpr int stageBytes() {  // + slack for the last word over-read; TMA destinations need 128-byte alignment
   return (stageBoxW(K, CLS) * stageBoxH(K, CLS) + 64 + 127) & ~127;
 }
-template <int K, int CLS>
-__host__ __device__ constexpr int stagedSmemBytes() { return weightBytes<K>() + 2 * stageBytes<K, CLS>() + 64; }
+// One persistent kernel per plane.  The job list is sorted by kind and dealt round-robin over the CTAs, so every CTA
+// first streams its class-0 tiles through the double-buffered TMA pipeline, then handles its few class-1 tiles (their
+// larger box takes both stage buffers, no prefetch), then its few general tiles (taps through L1, any border case).
+template <int K>
+__host__ __device__ constexpr int planeSmemBytes() { return weightBytes<K>() + 2 * stageBytes<K, 0>() + 64; }
 
-template <int K, int CLS>
-__global__ void __launch_bounds__(gatherThreads(K), K == 8 ? 1 : (CLS == 0 ? 3 : 2))
-gatherStagedKernel(GatherParams p, StagedParams sp, const __grid_constant__ CUtensorMap srcMap) {
-  constexpr int kPitch = stageBoxW(K, CLS);
+template <int K, int PITCH>
+__device__ __forceinline__ void computeStagedTile(const GatherParams& p, const unsigned char* stage, int outX, int outY, int boxX,
+                                                  int boxY, const int2 (&rec)[kRowsPerThread], const unsigned char* wsmem, int lane,
+                                                  int warp) {
+  const int y0 = outY + warp * kRowsPerThread;
+  const bool active = outX + lane < p.dstW;
+  bool shared = false;
+  if constexpr (K >= 4) {
+    // warp-uniform choice: every lane's 4 pixels share their columns (inactive lanes do not veto); needs all 4 rows
+    shared = y0 + kRowsPerThread <= p.dstH && __all_sync(0xffffffffu, !active || columnShareable(rec));
+  }
+  if (shared) {
+    if constexpr (K >= 4) {
+      if (active) {
+        int acc[kRowsPerThread];
+        gatherColumnShared<K, PITCH>(stage, boxX, boxY, rec, wsmem, acc);
+#pragma unroll
+        for (int j = 0; j < kRowsPerThread; ++j)
+          p.dst[(size_t)(y0 + j) * p.dstPitch + outX + recordColumn(rec[j].x)] = (uint8_t)roundToByte(acc[j]);
+      }
+    }
+  } else if (active) {
+    const uint32_t stageAddr = smemAddr(stage), wAddr = smemAddr(wsmem);
+#pragma unroll
+    for (int j = 0; j < kRowsPerThread; ++j) {
+      if (y0 + j >= p.dstH) break;
+      const int row0 = rec[j].y >> 10, phase = rec[j].y & 1023;
+      const int off = (row0 - boxY) * PITCH + (recordCol0(rec[j].x) - boxX);
+      const int acc = foldWindowShared<K, PITCH>(stageAddr, off, wAddr, phase);
+      p.dst[(size_t)(y0 + j) * p.dstPitch + outX + recordColumn(rec[j].x)] = (uint8_t)roundToByte(acc);
+    }
+  }
+}
+
+template <int K>
+__global__ void __launch_bounds__(gatherThreads(K), K == 8 ? 1 : 3)
+gatherPlaneKernel(GatherParams p, StagedParams jobs, const __grid_constant__ CUtensorMap map0,
+                  const __grid_constant__ CUtensorMap map1) {
+  static_assert(stageBoxW(K, 1) * stageBoxH(K, 1) + 64 <= 2 * stageBytes<K, 0>(), "a class-1 box must fit both stage buffers");
   extern __shared__ __align__(16) unsigned char smem[];
   unsigned char* wsmem = smem;
   unsigned char* stage0 = smem + weightBytes<K>();
-  constexpr int kStage = stageBytes<K, CLS>();
+  constexpr int kStage = stageBytes<K, 0>();
   uint64_t* bars = reinterpret_cast<uint64_t*>(stage0 + 2 * kStage);
-  constexpr uint32_t kBoxBytes = kPitch * stageBoxH(K, CLS);
+  constexpr uint32_t kBox0 = stageBoxW(K, 0) * stageBoxH(K, 0), kBox1 = stageBoxW(K, 1) * stageBoxH(K, 1);
 
   if (threadIdx.x == 0) {
     mbarInit(&bars[0], 1);
     mbarInit(&bars[1], 1);
+    mbarInit(&bars[2], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   stageWeights<K>(p.weights, wsmem);
   __syncthreads();
 
+  SrcView sv;
+  sv.bytes = p.src;
+  sv.misalign = (int)(reinterpret_cast<uintptr_t>(p.src) & 3);
+  sv.words = reinterpret_cast<const uint32_t*>(p.src - sv.misalign);
+  sv.w = p.srcW; sv.h = p.srcH; sv.pitch = p.srcPitch;
+
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const uint32_t wAddr = smemAddr(wsmem);
-  const int first = blockIdx.x;
-  if (threadIdx.x == 0 && first < sp.numTiles) {
-    const StagedTile t = sp.tiles[first];
-    mbarExpectTx(&bars[0], kBoxBytes);
-    tmaLoadBox(stage0, &srcMap, t.boxX, t.boxY, &bars[0]);
-  }
-  // software pipeline: the plan records (and tile header) of tile n+1 are fetched while tile n is computed
+  // software pipeline: tile header and plan records of job n+1 are fetched while job n is computed
   auto fetch = [&](int i, StagedTile& t, int2 (&rec)[kRowsPerThread]) {
-    t = sp.tiles[i];
-    const int y0 = t.outY + warp * kRowsPerThread, slot = t.outX + lane;  // records are stored in lane order
+    t = jobs.tiles[i];
+    const int y0 = (t.outY & kJobRowMask) + warp * kRowsPerThread, slot = t.outX + lane;  // records are in lane order
 #pragma unroll
     for (int j = 0; j < kRowsPerThread; ++j)
       rec[j] = (slot < p.dstW && y0 + j < p.dstH) ? loadPlan(p.samples + (size_t)(y0 + j) * p.samplesPitch + slot) : make_int2(0, 0);
   };
+  const int first = blockIdx.x;
   StagedTile tile{};
   int2 rec[kRowsPerThread] = {};
-  if (first < sp.numTiles) fetch(first, tile, rec);
-
-  uint32_t it = 0;
-  for (int i = first; i < sp.numTiles; i += gridDim.x, ++it) {
-    const uint32_t st = it & 1;
-    const int next = i + gridDim.x;
-    if (threadIdx.x == 0 && next < sp.numTiles) {  // prefetch the next tile's box into the other stage
-      const StagedTile t = sp.tiles[next];
-      mbarExpectTx(&bars[st ^ 1], kBoxBytes);
-      tmaLoadBox(stage0 + (st ^ 1) * kStage, &srcMap, t.boxX, t.boxY, &bars[st ^ 1]);
+  if (first < jobs.numTiles) {
+    fetch(first, tile, rec);
+    if (threadIdx.x == 0 && (tile.outY >> kJobKindShift) == 0) {
+      mbarExpectTx(&bars[0], kBox0);
+      tmaLoadBox(stage0, &map0, tile.boxX, tile.boxY, &bars[0]);
     }
+  }
+  uint32_t q0 = 0, q1 = 0;  // how many class-0 / class-1 tiles this CTA has consumed
+  for (int i = first; i < jobs.numTiles; i += gridDim.x) {
+    const int next = i + gridDim.x;
     StagedTile tileNext{};
     int2 recNext[kRowsPerThread] = {};
-    if (next < sp.numTiles) fetch(next, tileNext, recNext);
-
-    const int y0 = tile.outY + warp * kRowsPerThread;
-    mbarWait(&bars[st], (it >> 1) & 1);
-    const uint32_t stageAddr = smemAddr(stage0) + st * kStage;
-    if (tile.outX + lane < p.dstW) {
+    if (next < jobs.numTiles) fetch(next, tileNext, recNext);
+    const int kind = tile.outY >> kJobKindShift, outY = tile.outY & kJobRowMask;
+    if (kind == 0) {
+      const uint32_t st = q0 & 1;
+      if (threadIdx.x == 0 && next < jobs.numTiles && (tileNext.outY >> kJobKindShift) == 0) {
+        mbarExpectTx(&bars[st ^ 1], kBox0);  // the other stage was released by the barrier that ended the previous job
+        tmaLoadBox(stage0 + (st ^ 1) * kStage, &map0, tileNext.boxX, tileNext.boxY, &bars[st ^ 1]);
+      }
+      mbarWait(&bars[st], (q0 >> 1) & 1);
+      computeStagedTile<K, stageBoxW(K, 0)>(p, stage0 + st * kStage, tile.outX, outY, tile.boxX, tile.boxY, rec, wsmem, lane, warp);
+      ++q0;
+    } else if (kind == 1) {
+      if (threadIdx.x == 0) {  // nothing is in flight any more (kinds are sorted): the box may span both stage buffers
+        mbarExpectTx(&bars[2], kBox1);
+        tmaLoadBox(stage0, &map1, tile.boxX, tile.boxY, &bars[2]);
+      }
+      mbarWait(&bars[2], q1 & 1);
+      computeStagedTile<K, stageBoxW(K, 1)>(p, stage0, tile.outX, outY, tile.boxX, tile.boxY, rec, wsmem, lane, warp);
+      ++q1;
+    } else {
+      const int y0 = outY + warp * kRowsPerThread;
+      if (tile.outX + lane < p.dstW) {
 #pragma unroll
-      for (int j = 0; j < kRowsPerThread; ++j) {
-        if (y0 + j >= p.dstH) break;
-        const int row0 = rec[j].y >> 10, phase = rec[j].y & 1023;
-        const int off = (row0 - tile.boxY) * kPitch + (recordCol0(rec[j].x) - tile.boxX);
-        const int acc = foldWindowShared<K, kPitch>(stageAddr, off, wAddr, phase);
-        p.dst[(size_t)(y0 + j) * p.dstPitch + tile.outX + recordColumn(rec[j].x)] = (uint8_t)roundToByte(acc);
+        for (int j = 0; j < kRowsPerThread; ++j) {
+          if (y0 + j >= p.dstH) break;
+          const int v = gatherPixel<K, false>(sv, wsmem, recordCol0(rec[j].x), rec[j].y);
+          p.dst[(size_t)(y0 + j) * p.dstPitch + tile.outX + recordColumn(rec[j].x)] = (uint8_t)v;
+        }
       }
     }
-    __syncthreads();  // everyone is done with stage `st` before it is refilled two iterations later
+    __syncthreads();  // everyone is done with this job's stage before it is refilled
     tile = tileNext;
 #pragma unroll
     for (int j = 0; j < kRowsPerThread; ++j) rec[j] = recNext[j];
@@ -690,14 +823,15 @@ cudaError_t launchNearest(const GatherParams& p, int numSMs, cudaStream_t stream
   return cudaGetLastError();
 }
 
-template <int K, int CLS>
-cudaError_t launchStagedK(const GatherParams& p, const StagedParams& sp, const CUtensorMap& map, int numSMs, cudaStream_t stream) {
+template <int K>
+cudaError_t launchPlaneK(const GatherParams& p, const StagedParams& jobs, const CUtensorMap& map0, const CUtensorMap& map1, int numSMs,
+                         cudaStream_t stream) {
   static thread_local LaunchCfg cfg;
-  constexpr int threads = gatherThreads(K), smemBytes = stagedSmemBytes<K, CLS>();
-  cudaError_t err = prepare<gatherStagedKernel<K, CLS>>(cfg, threads, smemBytes);
+  constexpr int threads = gatherThreads(K), smemBytes = planeSmemBytes<K>();
+  cudaError_t err = prepare<gatherPlaneKernel<K>>(cfg, threads, smemBytes);
   if (err != cudaSuccess) return err;
-  const int grid = std::min(numSMs * cfg.perSM, sp.numTiles);
-  gatherStagedKernel<K, CLS><<<grid, threads, smemBytes, stream>>>(p, sp, map);
+  const int grid = std::min(numSMs * cfg.perSM, jobs.numTiles);  // persistent: whole waves of CTAs
+  gatherPlaneKernel<K><<<grid, threads, smemBytes, stream>>>(p, jobs, map0, map1);
   gLaunches.fetch_add(1, std::memory_order_relaxed);
   return cudaGetLastError();
 }
@@ -716,18 +850,15 @@ cudaError_t launchGather(const GatherParams& p, const int* tileList, int numList
   }
 }
 
-cudaError_t launchGatherStaged(const GatherParams& p, const StagedParams& sp, const void* tensorMap, int boxClass,
-                               int numSMs, cudaStream_t stream) {
-  if (sp.numTiles <= 0) return cudaSuccess;
-  if (p.transparent || boxClass < 0 || boxClass >= kNumBoxClasses) return cudaErrorInvalidValue;
-  const CUtensorMap& map = *static_cast<const CUtensorMap*>(tensorMap);
-  switch (p.kernelSize * 2 + boxClass) {
-    case 4: return launchStagedK<2, 0>(p, sp, map, numSMs, stream);
-    case 5: return launchStagedK<2, 1>(p, sp, map, numSMs, stream);
-    case 8: return launchStagedK<4, 0>(p, sp, map, numSMs, stream);
-    case 9: return launchStagedK<4, 1>(p, sp, map, numSMs, stream);
-    case 16: return launchStagedK<8, 0>(p, sp, map, numSMs, stream);
-    case 17: return launchStagedK<8, 1>(p, sp, map, numSMs, stream);
+cudaError_t launchGatherPlane(const GatherParams& p, const StagedParams& jobs, const void* tensorMaps, int numSMs,
+                              cudaStream_t stream) {
+  if (jobs.numTiles <= 0) return cudaSuccess;
+  if (p.transparent) return cudaErrorInvalidValue;
+  const CUtensorMap* maps = static_cast<const CUtensorMap*>(tensorMaps);
+  switch (p.kernelSize) {
+    case 2: return launchPlaneK<2>(p, jobs, maps[0], maps[1], numSMs, stream);
+    case 4: return launchPlaneK<4>(p, jobs, maps[0], maps[1], numSMs, stream);
+    case 8: return launchPlaneK<8>(p, jobs, maps[0], maps[1], numSMs, stream);
     default: return cudaErrorInvalidValue;
   }
 }

@@ -23,8 +23,10 @@ struct GatherParams {
 // One tile of the TMA-staged gather: a gatherTileW x gatherTileH block of output pixels whose whole source
 // window fits the fixed staging box placed at (boxX, boxY) of the source plane (boxX % 16 == 0).
 struct StagedTile {
-  int outX, outY, boxX, boxY;
+  int outX, outY, boxX, boxY;  // outY carries the job kind in its top byte (kJobKindShift)
 };
+// job kinds of the per-plane gather kernel: 0 / 1 = staged through TMA with box class 0 / 1, 2 = general (L1) path
+constexpr int kJobKindShift = 24, kJobRowMask = (1 << kJobKindShift) - 1, kJobGeneral = 2;
 
 constexpr int kGatherTileW = 32;                                   // one warp = 32 adjacent columns
 __host__ __device__ constexpr int gatherThreads(int k) { return k == 8 ? 512 : 256; }
@@ -104,10 +106,11 @@ constexpr int kBlurMaxSmem = 96 * 1024;
 // Launchers: enqueue on `stream`, return the CUDA status of the launch.  Each counts the kernels it launches.
 // tileList == nullptr: every tile of the plane; otherwise only the listed tile indices (row-major, tilesX wide)
 cudaError_t launchGather(const GatherParams& p, const int* tileList, int numListed, int numSMs, cudaStream_t stream);
-// TMA-staged tiles of one box class.  tensorMap: a CUtensorMap (128 bytes, by value) describing the source plane
-// with the staging box of (p.kernelSize, boxClass).  BORDER_WRAP only (tiles touching a border are never staged).
-cudaError_t launchGatherStaged(const GatherParams& p, const StagedParams& sp, const void* tensorMap, int boxClass,
-                               int numSMs, cudaStream_t stream);
+// The whole plane in one persistent kernel: `jobs` is sorted by kind (class 0, class 1, general).  tensorMaps: two
+// CUtensorMap (128 bytes each) describing the source plane with the staging boxes of class 0 and 1 of p.kernelSize.
+// BORDER_WRAP only.
+cudaError_t launchGatherPlane(const GatherParams& p, const StagedParams& jobs, const void* tensorMaps, int numSMs,
+                              cudaStream_t stream);
 cudaError_t launchBlurStrips(const StripParams& p, int hy, cudaStream_t stream);  // register-resident, hy <= kStripMaxHy
 cudaError_t launchBlur(const BlurParams& p, cudaStream_t stream);        // shared-memory tiles
 cudaError_t launchBlurDirect(const BlurParams& p, cudaStream_t stream);  // any kernel size, slow

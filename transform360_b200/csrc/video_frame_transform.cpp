@@ -79,9 +79,8 @@ struct DevicePlan {
   DeviceBuffer<int2> samples;
   int samplesPitch = 0;
   // gather tiles: those whose source window fits the TMA staging box, and the rest (by tile index)
-  DeviceBuffer<StagedTile> stagedTiles[t360::kNumBoxClasses];
-  DeviceBuffer<int> fallbackTiles;
-  int numStaged[t360::kNumBoxClasses] = {}, numFallback = 0;
+  DeviceBuffer<StagedTile> gatherJobs;  // every tile of the plane, sorted by kind (class 0, class 1, general)
+  int numJobs = 0, numStaged[t360::kNumBoxClasses] = {}, numFallback = 0;
   int totalStaged() const { int n = 0; for (int c : numStaged) n += c; return n; }
   // low-pass: register-resident strip jobs grouped by vertical half-size 1..3, and the rest (large vertical kernels)
   DeviceBuffer<StripJob> stripJobs[t360::kStripMaxHy];
@@ -90,7 +89,7 @@ struct DevicePlan {
   int numTileJobs = 0, numDirectJobs = 0, tileSmem = 0;
   DeviceBuffer<float> taps;
   size_t deviceBytes() const {
-    return samples.bytes() + stagedTiles[0].bytes() + stagedTiles[1].bytes() + fallbackTiles.bytes() + stripJobs[0].bytes() + stripJobs[1].bytes() + stripJobs[2].bytes() + tileJobs.bytes() + directJobs.bytes() + taps.bytes();
+    return samples.bytes() + gatherJobs.bytes() + stripJobs[0].bytes() + stripJobs[1].bytes() + stripJobs[2].bytes() + tileJobs.bytes() + directJobs.bytes() + taps.bytes();
   }
 };
 
@@ -415,28 +414,35 @@ class VideoFrameTransform {
   static void buildLaneOrder(const HostPlan& h, std::vector<int2>& out, int pitch) {
     const int k = h.kernelSize;
     const int groups = t360::weightBankGroups(k), lanesPerPass = t360::weightLanesPerPass(k), passes = 32 / lanesPerPass;
-    for (int y = 0; y < h.mapH; ++y) {
-      const t360::SamplePoint* row = &h.samples[static_cast<size_t>(y) * h.mapW];
-      int2* dst = &out[static_cast<size_t>(y) * pitch];
+    constexpr int kRows = 4;  // rows per thread: one lane order per 32 x 4 block, so that a thread keeps ONE column
+    for (int yb = 0; yb < h.mapH; yb += kRows) {
       for (int x0 = 0; x0 < h.mapW; x0 += 32) {
         const int n = std::min(32, h.mapW - x0);
         int order[32];
         for (int i = 0; i < n; ++i) order[i] = i;
-        if (k >= 2 && n == 32) {
+        const bool deal = k >= 2 && n == 32;
+        if (deal) {
+          // the bank group depends on fracX only, and fracX is the same down a column wherever the source column
+          // does not depend on the output row (the four equatorial cube faces): order by the block's first row
+          const t360::SamplePoint* row = &h.samples[static_cast<size_t>(yb) * h.mapW];
           auto keyOf = [&](int c) {
             const int phase = row[x0 + c].rowPhase & 1023;
             return ((t360::weightSlotOf(k, phase) & (groups - 1)) << 10) | phase;
           };
           std::stable_sort(order, order + n, [&](int a, int b) { return keyOf(a) < keyOf(b); });
         }
-        for (int i = 0; i < n; ++i) {
-          // i-th pixel of the sorted sequence -> pass i % passes, position i / passes inside the pass
-          const int lane = (k >= 2 && n == 32) ? (i % passes) * lanesPerPass + i / passes : i;
-          const int c = order[i];
-          const t360::SamplePoint& sp = row[x0 + c];
-          dst[x0 + lane] = int2{static_cast<int>((static_cast<unsigned>(sp.col0) & ((1u << t360::kRecordColumnShift) - 1)) |
-                                                 (static_cast<unsigned>(c) << t360::kRecordColumnShift)),
-                                sp.rowPhase};
+        for (int y = yb; y < std::min(h.mapH, yb + kRows); ++y) {
+          const t360::SamplePoint* row = &h.samples[static_cast<size_t>(y) * h.mapW];
+          int2* dst = &out[static_cast<size_t>(y) * pitch];
+          for (int i = 0; i < n; ++i) {
+            // i-th pixel of the sorted sequence -> pass i % passes, position i / passes inside the pass
+            const int lane = deal ? (i % passes) * lanesPerPass + i / passes : i;
+            const int c = order[i];
+            const t360::SamplePoint& sp = row[x0 + c];
+            dst[x0 + lane] = int2{static_cast<int>((static_cast<unsigned>(sp.col0) & ((1u << t360::kRecordColumnShift) - 1)) |
+                                                   (static_cast<unsigned>(c) << t360::kRecordColumnShift)),
+                                  sp.rowPhase};
+          }
         }
       }
     }
@@ -449,7 +455,7 @@ class VideoFrameTransform {
     const int k = h.kernelSize, tw = t360::kGatherTileW, th = t360::gatherTileH(k);
     const int tilesX = (h.mapW + tw - 1) / tw, tilesY = (h.mapH + th - 1) / th;
     std::vector<StagedTile> staged[t360::kNumBoxClasses];
-    std::vector<int> fallback;
+    std::vector<StagedTile> fallback;
     for (int ty = 0; ty < tilesY; ++ty)
       for (int tx = 0; tx < tilesX; ++tx) {
         int minC = INT32_MAX, maxC = INT32_MIN, minR = INT32_MAX, maxR = INT32_MIN;
@@ -467,19 +473,20 @@ class VideoFrameTransform {
         int cls = -1;
         for (int c = 0; c < t360::kNumBoxClasses && inPlane && cls < 0; ++c)
           if (maxC + k - boxX <= t360::stageBoxW(k, c) && maxR + k - minR <= t360::stageBoxH(k, c)) cls = c;
-        if (cls >= 0) staged[cls].push_back(StagedTile{tx * tw, ty * th, boxX, minR});
-        else fallback.push_back(ty * tilesX + tx);
+        if (cls >= 0) staged[cls].push_back(StagedTile{tx * tw, ty * th | (cls << t360::kJobKindShift), boxX, minR});
+        else fallback.push_back(StagedTile{tx * tw, ty * th | (t360::kJobGeneral << t360::kJobKindShift), 0, 0});
       }
+    std::vector<StagedTile> jobs;
     for (int c = 0; c < t360::kNumBoxClasses; ++c) {
       d.numStaged[c] = static_cast<int>(staged[c].size());
-      if (staged[c].empty()) continue;
-      d.stagedTiles[c].reserve(staged[c].size());
-      CU(cudaMemcpy(d.stagedTiles[c].ptr, staged[c].data(), staged[c].size() * sizeof(StagedTile), cudaMemcpyHostToDevice));
+      jobs.insert(jobs.end(), staged[c].begin(), staged[c].end());
     }
     d.numFallback = static_cast<int>(fallback.size());
-    if (!fallback.empty()) {
-      d.fallbackTiles.reserve(fallback.size());
-      CU(cudaMemcpy(d.fallbackTiles.ptr, fallback.data(), fallback.size() * sizeof(int), cudaMemcpyHostToDevice));
+    jobs.insert(jobs.end(), fallback.begin(), fallback.end());
+    d.numJobs = static_cast<int>(jobs.size());
+    if (!jobs.empty()) {
+      d.gatherJobs.reserve(jobs.size());
+      CU(cudaMemcpy(d.gatherJobs.ptr, jobs.data(), jobs.size() * sizeof(StagedTile), cudaMemcpyHostToDevice));
     }
   }
 
@@ -652,34 +659,10 @@ class VideoFrameTransform {
     bool stage = plan.totalStaged() > 0 && inW == plan.inW && inH == plan.inH;
     CUtensorMap maps[t360::kNumBoxClasses];
     for (int c = 0; c < t360::kNumBoxClasses && stage; ++c)
-      if (plan.numStaged[c]) stage = encodePlaneMap(&maps[c], src, inW, inH, srcPitch, plan.kernelSize, c);
+      stage = encodePlaneMap(&maps[c], src, inW, inH, srcPitch, plan.kernelSize, c);
     if (stage) {
-      // The tile lists are disjoint, so their kernels are independent.  The minority lists (general-path tiles
-      // near the poles and borders, wide-box tiles) are latency-bound and small: they are forked onto side
-      // streams so that they share the SMs with the main staged kernel instead of running after it.
-      int side = 0;
-      auto forked = [&](auto&& launch) {
-        if (side == 0) CU(cudaEventRecord(lane.fork, s));
-        cudaStream_t ss = lane.side[side];
-        CU(cudaStreamWaitEvent(ss, lane.fork, 0));
-        launch(ss);
-        CU(cudaEventRecord(lane.join[side], ss));
-        ++side;
-      };
-      if (plan.numFallback)
-        forked([&](cudaStream_t ss) { CU(t360::launchGather(gp, plan.fallbackTiles.ptr, plan.numFallback, numSMs_, ss)); });
-      for (int c = t360::kNumBoxClasses - 1; c >= 1; --c) {
-        if (!plan.numStaged[c]) continue;
-        forked([&](cudaStream_t ss) {
-          t360::StagedParams sp{plan.stagedTiles[c].ptr, plan.numStaged[c]};
-          CU(t360::launchGatherStaged(gp, sp, &maps[c], c, numSMs_, ss));
-        });
-      }
-      if (plan.numStaged[0]) {
-        t360::StagedParams sp{plan.stagedTiles[0].ptr, plan.numStaged[0]};
-        CU(t360::launchGatherStaged(gp, sp, &maps[0], 0, numSMs_, s));
-      }
-      for (int i = 0; i < side; ++i) CU(cudaStreamWaitEvent(s, lane.join[i], 0));
+      t360::StagedParams jobs{plan.gatherJobs.ptr, plan.numJobs};
+      CU(t360::launchGatherPlane(gp, jobs, maps, numSMs_, s));
     } else {
       CU(t360::launchGather(gp, nullptr, 0, numSMs_, s));
     }
