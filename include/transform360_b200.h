@@ -55,6 +55,10 @@ int T360B200_transformFrameAsync(VideoFrameTransform* transform, int numPlanes, 
 int T360B200_lowPassPlaneAsync(VideoFrameTransform* transform, const uint8_t* deviceInput, uint8_t* deviceOutput,
                                int width, int height, int inputPitch, int outputPitch,
                                int transformMatPlaneIndex, void* cudaStream);
+/* Opt-in (also: environment T360B200_PIN_HOST_PLANES=1): page-lock pageable caller planes in place the second time
+ * the same buffer is seen (cudaHostRegister), so that recycled frame-pool buffers are DMA'd at full PCIe speed.  The
+ * caller must keep such buffers alive until VideoFrameTransform_delete. */
+void T360B200_setPinHostPlanes(VideoFrameTransform* transform, int enable);
 /* Blocks until everything enqueued on the transform's own stream has finished; 1 = ok. */
 int T360B200_synchronize(VideoFrameTransform* transform);
 /* The transform's own stream (cudaStream_t) */

@@ -622,10 +622,23 @@ void t360o_remap_u8(const uint8_t* src, int sw, int sh, size_t spitch, uint8_t* 
         }
       } else {
         if (border == T360O_BORDER_TRANSPARENT) {
-          /* remapBilinear skips every non-inlier; bicubic/lanczos skip when the anchor pixel is outside */
-          if (k == 2) continue;
+          /* every interpolator leaves the pixel alone when its anchor sample lies outside the source */
           int ax = sx + (k / 2 - 1), ay = sy + (k / 2 - 1);
           if ((unsigned)ax >= (unsigned)sw || (unsigned)ay >= (unsigned)sh) continue;
+          if (k == 2) {
+            /* cv2 4.13 remapBilinear: anchor inside but the 2x2 window sticks out (last row / column): blend the
+             * taps that exist and renormalise by their weight, rounding half up (pinned against cv2 on 12 000
+             * edge samples, tests/test_oracle_pin.py) */
+            long num = 0, den = 0;
+            for (int r = 0; r < 2; r++)
+              for (int c = 0; c < 2; c++)
+                if (sx + c < sw && sy + r < sh) {
+                  num += (long)w[r * 2 + c] * src[(size_t)(sy + r) * spitch + sx + c];
+                  den += w[r * 2 + c];
+                }
+            if (den > 0) D[dx] = (uint8_t)((2 * num + den) / (2 * den));
+            continue;
+          }
         }
         if (border == T360O_BORDER_CONSTANT && (sx >= sw || sx + k <= 0 || sy >= sh || sy + k <= 0)) {
           D[dx] = 0;

@@ -35,9 +35,6 @@ def _prefill(ctx):
     return 7 if ctx.output_layout in (t360.LAYOUT_BARREL, t360.LAYOUT_BARREL_SPLIT) else 0
 
 
-XFAIL_TRANSPARENT_LINEAR = {"barrel_split_linear"}
-
-
 @pytest.mark.parametrize("name", sorted(SMALL))
 def test_small_cases_bit_exact_through_c_abi(name, golden, torch_cuda):
     case = SMALL[name]
@@ -158,6 +155,23 @@ def test_huge_kernels_take_the_direct_path(torch_cuda):
     plan = co.OraclePlan(octx, iw, ih, ow, oh)
     want = co.transform_plane(octx, plan, src, ow, oh)
     assert np.array_equal(got, want)
+
+
+def test_recurring_pageable_planes_can_be_pinned_in_place(torch_cuda):
+    """Opt-in cudaHostRegister of recycled caller buffers: same bytes before and after the buffer gets page-locked."""
+    case = SMALL["lp_tiles"]
+    ctx, octx = _ctxs(case)
+    iw, ih, ow, oh, idx = plane_dims(case, 0)
+    src = np.ascontiguousarray(co.noise_plane(iw, ih, frame=1))
+    out = np.zeros((oh, ow), np.uint8)
+    plan = co.OraclePlan(octx, iw, ih, ow, oh)
+    with t360.VideoFrameTransform(ctx) as vft:
+        vft.set_pin_host_planes(True)
+        assert vft.generateMapForPlane(iw, ih, ow, oh, 0)
+        for frame in range(4):  # the same two buffers every frame, like a frame pool
+            src[...] = co.noise_plane(iw, ih, frame=frame)
+            vft.transform_plane(src, ow, oh, 0, out=out)
+            assert np.array_equal(out, co.transform_plane(octx, plan, src, ow, oh))
 
 
 def test_errors_follow_the_reference_contract(torch_cuda):

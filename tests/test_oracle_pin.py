@@ -90,13 +90,7 @@ def test_remap_arithmetic_vs_cv2(interp):
     assert np.array_equal(got, want)
 
 
-@pytest.mark.parametrize("interp", [
-    rh.NEAREST,
-    pytest.param(rh.LINEAR, marks=pytest.mark.xfail(
-        reason="cv2 4.13 remapBilinear blends partially-inside pixels on the last row/column under "
-               "BORDER_TRANSPARENT with a renormalised-weights formula that is not restated yet "
-               "(barrel layouts are SURVEY.md 8f rank 4)", strict=False)),
-    rh.CUBIC, rh.LANCZOS4])
+@pytest.mark.parametrize("interp", [rh.NEAREST, rh.LINEAR, rh.CUBIC, rh.LANCZOS4])
 def test_remap_transparent_vs_cv2(interp):
     rng = np.random.default_rng(99 + interp)
     src = rng.integers(0, 256, (64, 80), dtype=np.uint8)
@@ -107,6 +101,21 @@ def test_remap_transparent_vs_cv2(interp):
     want = np.full((120, 150), 128, np.uint8)
     cv2.remap(src, m, None, interp, dst=want, borderMode=cv2.BORDER_TRANSPARENT)
     got = co.remap_u8(src, m, interp, 5, dst=np.full((120, 150), 128, np.uint8))
+    assert np.array_equal(got, want)
+
+
+def test_bilinear_transparent_edge_rule_vs_cv2():
+    """Pixels whose anchor is on the last row / column under BORDER_TRANSPARENT (renormalised blend, round half up)."""
+    rng = np.random.default_rng(5)
+    H, W = 40, 50
+    src = rng.integers(0, 256, (H, W), dtype=np.uint8)
+    m = np.zeros((3, 4000, 2), np.float32)
+    m[0, :, 0] = W - 1 + rng.uniform(0, 0.99, 4000); m[0, :, 1] = rng.uniform(-0.4, H - 0.01, 4000)
+    m[1, :, 0] = rng.uniform(-0.4, W - 0.01, 4000); m[1, :, 1] = H - 1 + rng.uniform(0, 0.99, 4000)
+    m[2, :, 0] = W - 1 + rng.uniform(0, 0.99, 4000); m[2, :, 1] = H - 1 + rng.uniform(0, 0.99, 4000)
+    want = np.full((3, 4000), 77, np.uint8)
+    cv2.remap(src, m, None, cv2.INTER_LINEAR, dst=want, borderMode=cv2.BORDER_TRANSPARENT)
+    got = co.remap_u8(src, m, rh.LINEAR, 5, dst=np.full((3, 4000), 77, np.uint8))
     assert np.array_equal(got, want)
 
 

@@ -304,13 +304,26 @@ __device__ __forceinline__ int gatherPixel(const SrcView& s, const unsigned char
     return roundToByte(foldWindow<K, false>(s.words, row0 * s.pitch + col0 + s.misalign, s.pitch, wsmem, phase));
 
   // window touches an edge: per-tap addressing.  BORDER_WRAP wraps columns AND rows (reference cpp:719).
+  const int16_t* wt = reinterpret_cast<const int16_t*>(wsmem) + weightSlot<K>(phase) * (K == 2 ? 4 : 8);
   if (TRANSPARENT) {
-    const bool inlier = col0 >= 0 && row0 >= 0 && col0 + K <= s.w && row0 + K <= s.h;
-    if (K == 2 && !inlier) return -1;  // remapBilinear leaves every non-inlier alone
+    // every interpolator leaves the pixel alone when its anchor sample lies outside the source
     const int ax = col0 + (K / 2 - 1), ay = row0 + (K / 2 - 1);
     if ((unsigned)ax >= (unsigned)s.w || (unsigned)ay >= (unsigned)s.h) return -1;
+    if (K == 2) {
+      // bilinear, anchor inside but the 2x2 window sticks out on the last row / column: OpenCV blends the taps
+      // that exist and renormalises by their weight, rounding half up (oracle/t360_oracle.c)
+      int num = 0, den = 0;
+#pragma unroll
+      for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+          if (col0 + c < s.w && row0 + r < s.h) {
+            num += wt[r * 2 + c] * (int)__ldg(s.bytes + (size_t)(row0 + r) * s.pitch + col0 + c);
+            den += wt[r * 2 + c];
+          }
+      return den > 0 ? (2 * num + den) / (2 * den) : -1;
+    }
   }
-  const int16_t* wt = reinterpret_cast<const int16_t*>(wsmem) + weightSlot<K>(phase) * (K == 2 ? 4 : 8);
   int acc = 0;
 #pragma unroll 1
   for (int r = 0; r < K; ++r) {

@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <climits>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -143,7 +144,12 @@ inline int alignedPitch(int w) { return (w + kPitchAlign - 1) / kPitchAlign * kP
 
 class VideoFrameTransform {
  public:
-  explicit VideoFrameTransform(FrameTransformContext* ctx) { std::memcpy(&ctx_, ctx, sizeof(ctx_)); }
+  explicit VideoFrameTransform(FrameTransformContext* ctx) {
+    std::memcpy(&ctx_, ctx, sizeof(ctx_));
+    const char* e = std::getenv("T360B200_PIN_HOST_PLANES");
+    pinHostPlanes_ = e && *e && *e != '0';
+  }
+  void setPinHostPlanes(bool on) { pinHostPlanes_ = on; }
 
   ~VideoFrameTransform() {
     if (deviceReady_) {
@@ -151,6 +157,8 @@ class VideoFrameTransform {
       plans_.clear();
       for (auto& w : weights_) w.release();
       stagingIn_.release(); stagingOut_.release();
+      for (HostRange& r : hostRanges_)
+        if (r.pinned) cudaHostUnregister(reinterpret_cast<void*>(r.base));
       for (PlaneLane& l : lanes_) {
         l.blurred.release();
         if (l.main) cudaStreamDestroy(l.main);
@@ -198,12 +206,14 @@ class VideoFrameTransform {
       uint8_t* dOut = out;
       int dInPitch = inPitch, dOutPitch = outPitch;
       if (!inOnDevice) {
+        pinIfRecurring(in, static_cast<size_t>(inPitch) * (inH - 1) + inW);
         dInPitch = alignedPitch(inW);
         stagingIn_.reserve(static_cast<size_t>(dInPitch) * inH + 64);
         CU(cudaMemcpy2DAsync(stagingIn_.ptr, dInPitch, in, inPitch, inW, inH, cudaMemcpyHostToDevice, stream_));
         dIn = stagingIn_.ptr;
       }
       if (!outOnDevice) {
+        pinIfRecurring(out, static_cast<size_t>(outPitch) * (outH - 1) + outW);
         dOutPitch = alignedPitch(outW);
         stagingOut_.reserve(static_cast<size_t>(dOutPitch) * outH + 64);
         dOut = stagingOut_.ptr;
@@ -353,6 +363,28 @@ class VideoFrameTransform {
     }
     CU(cudaEventCreateWithFlags(&frameFork_, cudaEventDisableTiming));
     deviceReady_ = true;
+  }
+
+  // Pageable host planes are copied through the driver's bounce buffers at a fraction of PCIe speed.  When enabled
+  // (T360B200_setPinHostPlanes or T360B200_PIN_HOST_PLANES=1), a plane address seen for the second time is page-locked
+  // in place with cudaHostRegister so that later frames in the same buffer are DMA'd directly.  Opt-in because the
+  // caller must not free such a buffer while the transform is alive (it is unregistered in the destructor).
+  void pinIfRecurring(const void* ptr, size_t bytes) {
+    if (!pinHostPlanes_ || !ptr || !bytes) return;
+    cudaPointerAttributes a{};
+    if (cudaPointerGetAttributes(&a, ptr) != cudaSuccess) { cudaGetLastError(); return; }
+    if (a.type != cudaMemoryTypeUnregistered) return;
+    const uintptr_t page = 4096, lo = reinterpret_cast<uintptr_t>(ptr) & ~(page - 1);
+    const size_t len = ((reinterpret_cast<uintptr_t>(ptr) + bytes + page - 1) & ~(page - 1)) - lo;
+    for (HostRange& r : hostRanges_) {
+      if (r.base != lo || r.bytes != len) continue;
+      if (!r.pinned && ++r.seen >= 2) {
+        if (cudaHostRegister(reinterpret_cast<void*>(lo), len, cudaHostRegisterDefault) == cudaSuccess) r.pinned = true;
+        else { cudaGetLastError(); r.seen = -1000000; }  // do not retry this range
+      }
+      return;
+    }
+    if (hostRanges_.size() < 64) hostRanges_.push_back(HostRange{lo, len, 1, false});
   }
 
   static bool isDevicePointer(const void* p) {
@@ -674,6 +706,10 @@ class VideoFrameTransform {
   std::map<int, DevicePlan> plans_;
   DeviceBuffer<int16_t> weights_[9];
   DeviceBuffer<uint8_t> stagingIn_, stagingOut_;
+  // opt-in page-locking of recurring pageable caller planes (ffmpeg recycles its frame pool): see pinIfRecurring()
+  struct HostRange { uintptr_t base; size_t bytes; int seen; bool pinned; };
+  std::vector<HostRange> hostRanges_;
+  bool pinHostPlanes_ = false;
   PlaneLane lanes_[kPlaneLanes];
   cudaEvent_t frameFork_ = nullptr;
   cudaStream_t stream_ = nullptr;
@@ -770,6 +806,7 @@ T360_API int T360B200_lowPassPlaneAsync(VideoFrameTransform* t, const uint8_t* d
     return 0;
   }
 }
+T360_API void T360B200_setPinHostPlanes(VideoFrameTransform* t, int enable) { if (t) t->setPinHostPlanes(enable != 0); }
 T360_API int T360B200_synchronize(VideoFrameTransform* t) { return t ? t->synchronize() : 0; }
 T360_API void* T360B200_stream(VideoFrameTransform* t) { return t ? t->stream() : nullptr; }
 T360_API unsigned long long T360B200_kernelLaunchCount(void) { return t360::kernelLaunchCount(); }

@@ -104,6 +104,8 @@ def load(path: os.PathLike | None = None):
     L.T360B200_transformFrameAsync.argtypes = [vp, ci, vp, vp] + [vp] * 6 + [vp]
     L.T360B200_lowPassPlaneAsync.restype = ci
     L.T360B200_lowPassPlaneAsync.argtypes = [vp, vp, vp] + [ci] * 5 + [vp]
+    L.T360B200_setPinHostPlanes.restype = None
+    L.T360B200_setPinHostPlanes.argtypes = [vp, ci]
     L.T360B200_synchronize.restype = ci
     L.T360B200_synchronize.argtypes = [vp]
     L.T360B200_stream.restype = vp
@@ -126,7 +128,7 @@ EXPORTED_SYMBOLS = [
     "T360B200_hostPlanInfo", "T360B200_hostPlanMap", "T360B200_hostPlanSamples", "T360B200_hostPlanSegment",
     "T360B200_remapTable", "T360B200_transformFramePlaneAsync", "T360B200_transformFrameAsync",
     "T360B200_lowPassPlaneAsync",
-    "T360B200_synchronize", "T360B200_stream", "T360B200_kernelLaunchCount", "T360B200_planDeviceBytes",
+    "T360B200_setPinHostPlanes", "T360B200_synchronize", "T360B200_stream", "T360B200_kernelLaunchCount", "T360B200_planDeviceBytes",
     "T360B200_planTileCounts", "T360B200_deviceCount", "T360B200_version",
 ]
 
@@ -207,6 +209,9 @@ class VideoFrameTransform:
     def low_pass_async(self, d_in: int, d_out: int, w, h, in_pitch, out_pitch, plan_index, stream: int = 0) -> bool:
         return bool(self._lib.T360B200_lowPassPlaneAsync(self._h, d_in, d_out, w, h, in_pitch, out_pitch, plan_index,
                                                          stream))
+
+    def set_pin_host_planes(self, enable: bool) -> None:
+        self._lib.T360B200_setPinHostPlanes(self._h, 1 if enable else 0)
 
     def synchronize(self) -> bool:
         return bool(self._lib.T360B200_synchronize(self._h))
