@@ -49,6 +49,7 @@ def lib():
         L.t360o_filter_plane.argtypes = [vp, vp, ci, ci, sz, vp, sz, vp, ci, vp]
         L.t360o_filter_plane.restype = None
         L.t360o_transform_plane.argtypes = [vp, vp, ci, ci, sz, vp, ci, ci, sz, vp, ci, ci, ci, vp, ci, vp]
+        L.t360o_resize_area_u8.argtypes = [vp, ci, ci, sz, vp, ci, ci, sz]
         L.t360o_noise_plane.argtypes = [vp, ci, ci, sz, C.c_uint32, C.c_uint32]
         L.t360o_noise_plane.restype = None
         L.t360o_fnv1a64.argtypes = [vp, sz]
@@ -147,7 +148,15 @@ def transform_plane(ctx, plan: OraclePlan, src: np.ndarray, out_w, out_h, map_in
                                      dst.ctypes.data, out_w, out_h, dst.strides[0], plan.map.ctypes.data, mw, mh,
                                      map_index, plan.segs, plan.nsegs, plan.taps.ctypes.data)
     if not ok:
-        raise RuntimeError("oracle: resize branch not restated (map size != output size)")
+        raise RuntimeError("oracle: the area resize would enlarge (scale factor < 1): not restated")
+    return dst
+
+
+def resize_area(src: np.ndarray, dw: int, dh: int) -> np.ndarray:
+    dst = np.zeros((dh, dw), np.uint8)
+    if not lib().t360o_resize_area_u8(src.ctypes.data, src.shape[1], src.shape[0], src.strides[0], dst.ctypes.data, dw, dh,
+                                      dst.strides[0]):
+        raise ValueError("oracle: INTER_AREA enlarging is not restated")
     return dst
 
 

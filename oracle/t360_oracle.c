@@ -720,13 +720,90 @@ void t360o_filter_plane(const T360OContext* c, const uint8_t* src, int w, int h,
     }
 }
 
-/* ref:707-794 transformPlane, non-resize branch */
+/* ------------------------------------------------------------------------------------------
+ * cv::resize(INTER_AREA), 8-bit, one channel, shrinking (OpenCV 4.x imgproc/resize.cpp)
+ * ---------------------------------------------------------------------------------------- */
+typedef struct { int di, si; float alpha; } AreaTap;
+
+/* computeResizeAreaTab */
+static int area_tab(int ssize, int dsize, double scale, AreaTap* tab) {
+  int k = 0;
+  for (int dx = 0; dx < dsize; dx++) {
+    double fsx1 = dx * scale, fsx2 = fsx1 + scale;
+    double cell = scale < ssize - fsx1 ? scale : ssize - fsx1;
+    int sx1 = (int)ceil(fsx1), sx2 = (int)floor(fsx2);
+    if (sx2 > ssize - 1) sx2 = ssize - 1;
+    if (sx1 > sx2) sx1 = sx2;
+    if (sx1 - fsx1 > 1e-3) { tab[k].di = dx; tab[k].si = sx1 - 1; tab[k++].alpha = (float)((sx1 - fsx1) / cell); }
+    for (int sx = sx1; sx < sx2; sx++) { tab[k].di = dx; tab[k].si = sx; tab[k++].alpha = (float)(1.0 / cell); }
+    if (fsx2 - sx2 > 1e-3) {
+      double a = fsx2 - sx2;
+      if (a > 1.0) a = 1.0;
+      if (a > cell) a = cell;
+      tab[k].di = dx; tab[k].si = sx2; tab[k++].alpha = (float)(a / cell);
+    }
+  }
+  return k;
+}
+
+int t360o_resize_area_u8(const uint8_t* src, int sw, int sh, size_t spitch, uint8_t* dst, int dw, int dh, size_t dpitch) {
+  const double scale_x = 1.0 / ((double)dw / sw), scale_y = 1.0 / ((double)dh / sh); /* cv::resize: 1./inv_scale */
+  if (scale_x < 1.0 || scale_y < 1.0) return 0;
+  const int isx = (int)lrint(scale_x), isy = (int)lrint(scale_y);
+  if (fabs(scale_x - isx) < DBL_EPSILON && fabs(scale_y - isy) < DBL_EPSILON) { /* resizeAreaFast_ */
+    const int area = isx * isy;
+    const float scale = 1.f / area;
+    for (int dy = 0; dy < dh; dy++)
+      for (int dx = 0; dx < dw; dx++) {
+        int sum = 0;
+        for (int y = 0; y < isy; y++)
+          for (int x = 0; x < isx; x++) sum += src[(size_t)(dy * isy + y) * spitch + dx * isx + x];
+        int v;
+        if (isx == 2 && isy == 2) v = (sum + 2) >> 2;
+        else v = (int)lrintf((float)sum * scale);
+        dst[(size_t)dy * dpitch + dx] = (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v));
+      }
+    return 1;
+  }
+  AreaTap* xt = (AreaTap*)malloc(sizeof(AreaTap) * ((size_t)sw * 2 + dw * 2));
+  AreaTap* yt = (AreaTap*)malloc(sizeof(AreaTap) * ((size_t)sh * 2 + dh * 2));
+  const int nx = area_tab(sw, dw, scale_x, xt), ny = area_tab(sh, dh, scale_y, yt);
+  float* buf = (float*)malloc(sizeof(float) * dw * 2);
+  float* sum = buf + dw;
+  int prev = yt[0].di;
+  for (int dx = 0; dx < dw; dx++) sum[dx] = 0;
+  for (int j = 0; j < ny; j++) { /* ResizeArea_Invoker */
+    const uint8_t* S = src + (size_t)yt[j].si * spitch;
+    const float beta = yt[j].alpha;
+    for (int dx = 0; dx < dw; dx++) buf[dx] = 0;
+    for (int k = 0; k < nx; k++) buf[xt[k].di] += (float)S[xt[k].si] * xt[k].alpha;
+    if (yt[j].di != prev) {
+      for (int dx = 0; dx < dw; dx++) {
+        long v = lrintf(sum[dx]);
+        dst[(size_t)prev * dpitch + dx] = (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v));
+        sum[dx] = beta * buf[dx];
+      }
+      prev = yt[j].di;
+    } else {
+      for (int dx = 0; dx < dw; dx++) sum[dx] += beta * buf[dx];
+    }
+  }
+  for (int dx = 0; dx < dw; dx++) {
+    long v = lrintf(sum[dx]);
+    dst[(size_t)prev * dpitch + dx] = (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v));
+  }
+  free(buf); free(xt); free(yt);
+  return 1;
+}
+
+/* ref:707-794 transformPlane, both branches */
 int t360o_transform_plane(const T360OContext* c, const uint8_t* src, int inW, int inH, size_t spitch, uint8_t* dst,
                           int outW, int outH, size_t dpitch, const float* map, int mapW, int mapH, int mapIndex,
                           const T360OSegment* segs, int nsegs, const float* taps) {
-  if (outW != mapW || outH != mapH) return 0;
   int interp = c->interpolation_alg;
   if (t360o_remap_ksize(interp) == 0) return 1; /* ref:780-784: prints, still returns true */
+  const int needResize = outW != mapW || outH != mapH; /* ref:735-737 */
+  if (needResize && (mapW < outW || mapH < outH)) return 0;
   const int barrel = c->output_layout == T360O_BARREL || c->output_layout == T360O_BARREL_SPLIT;
   int border = barrel ? T360O_BORDER_TRANSPARENT : T360O_BORDER_WRAP;
   const uint8_t* in = src;
@@ -738,9 +815,17 @@ int t360o_transform_plane(const T360OContext* c, const uint8_t* src, int inW, in
     in = blurred;
     inPitch = (size_t)inW;
   }
-  if (mapIndex && barrel)
-    for (int y = 0; y < outH; y++) memset(dst + (size_t)y * dpitch, 128, (size_t)outW);
-  t360o_remap_u8(in, inW, inH, inPitch, dst, outW, outH, dpitch, map, interp, border);
+  if (!needResize) {
+    if (mapIndex && barrel)
+      for (int y = 0; y < outH; y++) memset(dst + (size_t)y * dpitch, 128, (size_t)outW);
+    t360o_remap_u8(in, inW, inH, inPitch, dst, outW, outH, dpitch, map, interp, border);
+  } else { /* ref:755-777: render at the map's size into a 0 / 128 plane, then INTER_AREA down */
+    uint8_t* big = (uint8_t*)malloc((size_t)mapW * mapH);
+    memset(big, mapIndex ? 128 : 0, (size_t)mapW * mapH);
+    t360o_remap_u8(in, inW, inH, inPitch, big, mapW, mapH, (size_t)mapW, map, interp, border);
+    t360o_resize_area_u8(big, mapW, mapH, (size_t)mapW, dst, outW, outH, dpitch);
+    free(big);
+  }
   free(blurred);
   return 1;
 }

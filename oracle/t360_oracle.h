@@ -73,8 +73,12 @@ void t360o_sepfilter_roi_u8(const uint8_t* parent, int pw, int ph, size_t ppitch
 /* reference filterPlane (cpp:621-704): applies the plan once (MONO) or twice (LR/TB) */
 void t360o_filter_plane(const T360OContext* c, const uint8_t* src, int w, int h, size_t spitch,
                         uint8_t* dst, size_t dpitch, const T360OSegment* segs, int nsegs, const float* taps);
-/* reference transformPlane (cpp:707-794) without the resize branch: [low-pass] -> remap.
- * map/segs/taps as produced above; returns 1 on success, 0 if the resize branch would be needed. */
+/* cv::resize(INTER_AREA) for 8-bit single-channel SHRINKING (OpenCV 4.x resize.cpp: resizeAreaFast_ for integer
+ * ratios -- (sum+2)>>2 for 2x2, cvRound(sum * (1.f/area)) otherwise -- and resizeArea_ with computeResizeAreaTab
+ * for the rest).  Returns 0 (nothing written) when either axis would be enlarged. */
+int t360o_resize_area_u8(const uint8_t* src, int sw, int sh, size_t spitch, uint8_t* dst, int dw, int dh, size_t dpitch);
+/* reference transformPlane (cpp:707-794): [low-pass] -> remap [-> area resize when the map was planned at a scaled
+ * size, cpp:755-777].  map/segs/taps as produced above; returns 1 on success, 0 if the resize would enlarge. */
 int t360o_transform_plane(const T360OContext* c, const uint8_t* src, int inW, int inH, size_t spitch,
                           uint8_t* dst, int outW, int outH, size_t dpitch, const float* map, int mapW,
                           int mapH, int mapIndex, const T360OSegment* segs, int nsegs, const float* taps);

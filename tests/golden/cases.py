@@ -59,6 +59,12 @@ SMALL = {
                                      enable_low_pass_filter=0), inp=(512, 256), out=(128, 192)),
     "flat_fixed": dict(ov=dict(output_layout=L_FLAT, fixed_yaw=100.0, fixed_pitch=50.0, interpolation_alg=I_CUBIC,
                                enable_low_pass_filter=0), inp=(512, 256), out=(160, 120)),
+    "scaled_2x2": dict(ov=dict(width_scale_factor=2.0, height_scale_factor=2.0, interpolation_alg=I_CUBIC,
+                               enable_low_pass_filter=0), inp=(512, 256), out=(96, 64)),
+    "scaled_fractional_lp": dict(ov=dict(width_scale_factor=1.5, height_scale_factor=1.25, interpolation_alg=I_LINEAR,
+                                         num_vertical_segments=7, num_horizontal_segments=2), inp=(640, 320), out=(96, 64)),
+    "scaled_3x1": dict(ov=dict(width_scale_factor=3.0, height_scale_factor=1.0, interpolation_alg=I_LANCZOS4,
+                               enable_low_pass_filter=0), inp=(512, 256), out=(96, 64)),
     "barrel": dict(ov=dict(output_layout=L_BARREL, interpolation_alg=I_CUBIC, enable_low_pass_filter=0),
                    inp=(512, 256), out=(250, 100)),
     "barrel_split_linear": dict(ov=dict(output_layout=L_BARREL_SPLIT, interpolation_alg=I_LINEAR,

@@ -119,6 +119,17 @@ def test_bilinear_transparent_edge_rule_vs_cv2():
     assert np.array_equal(got, want)
 
 
+@pytest.mark.parametrize("dims", [(64, 48, 32, 24), (96, 60, 32, 20), (96, 60, 48, 20), (64, 48, 32, 48), (128, 64, 32, 16),
+                                  (65, 49, 32, 24), (96, 72, 64, 48), (100, 60, 40, 24), (75, 50, 50, 20), (64, 48, 48, 48),
+                                  (97, 31, 13, 7), (1152, 1024, 768, 512)])
+def test_area_resize_vs_cv2(dims):
+    """cv::resize(INTER_AREA) shrinking, the call at reference cpp:770-776: integer ratios (2x2 and general) and
+    fractional ratios, bit-exact."""
+    sw, sh, dw, dh = dims
+    src = np.random.default_rng(sw * 7 + dh).integers(0, 256, (sh, sw), dtype=np.uint8)
+    assert np.array_equal(co.resize_area(src, dw, dh), cv2.resize(src, (dw, dh), interpolation=cv2.INTER_AREA))
+
+
 def test_itab_sums():
     for interp in (rh.LINEAR, rh.CUBIC, rh.LANCZOS4):
         t = co.build_itab(interp)

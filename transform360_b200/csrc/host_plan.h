@@ -29,6 +29,24 @@ struct SamplePoint {
   int32_t rowPhase;
 };
 
+// cv::resize(INTER_AREA) from the render size (mapW x mapH) down to the requested output size, used when
+// width/height_scale_factor != 1 (reference cpp:755-777).  Integer ratios average whole cells; other ratios weight
+// partially covered source pixels with the tables OpenCV's computeResizeAreaTab produces.
+struct AreaTap {
+  int src;      // source column / row
+  float alpha;  // its share of the destination cell
+};
+struct AreaAxis {
+  std::vector<AreaTap> taps;   // grouped by destination index, in OpenCV's order
+  std::vector<int> first;      // [dst + 1]: taps of destination i are taps[first[i] .. first[i+1])
+};
+struct AreaResizePlan {
+  bool needed = false, supported = true;
+  int srcW = 0, srcH = 0, dstW = 0, dstH = 0;
+  int cellW = 0, cellH = 0;  // > 0: both ratios are integers (fast path), else use the axes below
+  AreaAxis x, y;
+};
+
 struct HostPlan {
   FrameTransformContext ctx{};
   int inW = 0, inH = 0;
@@ -40,6 +58,7 @@ struct HostPlan {
   std::vector<SamplePoint> samples;  // [mapH][mapW]
   std::vector<LowPassSegment> segments;
   std::vector<float> taps;
+  AreaResizePlan resize;
 };
 
 // Geometry: fills plan.map (reference cpp:534-556).  Multi-threaded over rows.  false if the layout is invalid.
@@ -64,6 +83,9 @@ inline int kernelSizeOf(int interpolationAlg) {
     default: return 0;
   }
 }
+
+// Fills plan.resize for (mapW x mapH) -> (outW x outH).
+void buildAreaResizePlan(HostPlan& plan);
 
 // Whole plan for one plane; returns false (message on stdout) on invalid parameters.
 bool buildHostPlan(const FrameTransformContext& ctx, int inW, int inH, int outW, int outH, HostPlan& plan);

@@ -787,6 +787,43 @@ __global__ void __launch_bounds__(256) blurDirectKernel(BlurParams p) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// cv::resize(INTER_AREA) shrink (reference cpp:770-776, only when *_scale_factor != 1).  Not on the hot
+// configurations: a straightforward one-thread-per-output-pixel kernel that follows OpenCV's order of
+// operations (separate multiply and add, float32) so that the result is bit-exact.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) areaResizeKernel(AreaParams p) {
+  const int dx = blockIdx.x * 32 + (threadIdx.x & 31), dy = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (dx >= p.dstW || dy >= p.dstH) return;
+  int v;
+  if (p.cellW > 0) {
+    int sum = 0;
+    for (int y = 0; y < p.cellH; ++y) {
+      const uint8_t* row = p.src + (size_t)(dy * p.cellH + y) * p.srcPitch + dx * p.cellW;
+      for (int x = 0; x < p.cellW; ++x) sum += __ldg(row + x);
+    }
+    if (p.cellW == 2 && p.cellH == 2) v = (sum + 2) >> 2;
+    else v = __float2int_rn(__fmul_rn((float)sum, 1.f / (float)(p.cellW * p.cellH)));
+  } else {
+    const int x0 = __ldg(p.xFirst + dx), x1 = __ldg(p.xFirst + dx + 1);
+    const int y0 = __ldg(p.yFirst + dy), y1 = __ldg(p.yFirst + dy + 1);
+    float sum = 0.f;
+    for (int j = y0; j < y1; ++j) {
+      const int2 ty = __ldg(p.yTaps + j);
+      const uint8_t* row = p.src + (size_t)ty.x * p.srcPitch;
+      float buf = 0.f;
+      for (int k = x0; k < x1; ++k) {
+        const int2 tx = __ldg(p.xTaps + k);
+        buf = __fadd_rn(buf, __fmul_rn((float)__ldg(row + tx.x), __int_as_float(tx.y)));
+      }
+      const float term = __fmul_rn(__int_as_float(ty.y), buf);
+      sum = j == y0 ? term : __fadd_rn(sum, term);
+    }
+    v = __float2int_rn(sum);
+  }
+  p.dst[(size_t)dy * p.dstPitch + dx] = (uint8_t)min(max(v, 0), 255);
+}
+
 struct LaunchCfg {
   bool ready = false;
   int perSM = 0;
@@ -874,6 +911,14 @@ cudaError_t launchGatherPlane(const GatherParams& p, const StagedParams& jobs, c
     case 8: return launchPlaneK<8>(p, jobs, maps[0], maps[1], numSMs, stream);
     default: return cudaErrorInvalidValue;
   }
+}
+
+cudaError_t launchAreaResize(const AreaParams& p, cudaStream_t stream) {
+  if (p.dstW <= 0 || p.dstH <= 0) return cudaSuccess;
+  const dim3 grid((p.dstW + 31) / 32, (p.dstH + 7) / 8);
+  areaResizeKernel<<<grid, 256, 0, stream>>>(p);
+  gLaunches.fetch_add(1, std::memory_order_relaxed);
+  return cudaGetLastError();
 }
 
 cudaError_t launchBlurStrips(const StripParams& p, int hy, cudaStream_t stream) {

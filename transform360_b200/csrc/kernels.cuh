@@ -98,6 +98,21 @@ struct StripParams {
   const float* taps;
 };
 
+// cv::resize(INTER_AREA) shrink, one thread per destination pixel.  cellW > 0: integer ratios (sum of a cellW x cellH
+// block, (sum+2)>>2 for 2x2, else rint(sum * (1.f/area))); otherwise the per-axis tap tables ({src, alpha} pairs,
+// first[] offsets) with OpenCV's accumulation order: row sums over x taps, then weighted by the y taps.
+struct AreaParams {
+  const uint8_t* src;
+  uint8_t* dst;
+  int srcW, srcH, srcPitch, dstW, dstH, dstPitch;
+  int cellW, cellH;
+  const int2* xTaps;  // {src index, alpha bits}
+  const int* xFirst;
+  const int2* yTaps;
+  const int* yFirst;
+};
+cudaError_t launchAreaResize(const AreaParams& p, cudaStream_t stream);
+
 constexpr int kStripLanePx = 8, kStripW = 32 * kStripLanePx, kStripMaxHy = 3;
 
 constexpr int kBlurTileW = 64, kBlurTileH = 32;

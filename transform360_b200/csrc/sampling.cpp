@@ -7,6 +7,7 @@
 //   * a k x k window (k = 2, 4, 8) is weighted with 15-bit fixed-point products of two 1-D kernels,
 //     each 2-D entry rounded separately and the window patched so that it sums to exactly 32768;
 //   * the result is (sum + 16384) >> 15, saturated to 8 bits.
+#include <algorithm>
 #include <cfloat>
 #include <cmath>
 #include <cstdio>
@@ -129,6 +130,48 @@ void quantizeWarpMap(HostPlan& plan) {
   }
 }
 
+namespace {
+// OpenCV 4.x imgproc/resize.cpp computeResizeAreaTab, one axis
+AreaAxis areaAxis(int ssize, int dsize, double scale) {
+  AreaAxis a;
+  a.first.reserve(static_cast<size_t>(dsize) + 1);
+  for (int d = 0; d < dsize; ++d) {
+    a.first.push_back(static_cast<int>(a.taps.size()));
+    const double f1 = d * scale, f2 = f1 + scale;
+    const double cell = std::min(scale, ssize - f1);
+    int s1 = static_cast<int>(std::ceil(f1)), s2 = static_cast<int>(std::floor(f2));
+    s2 = std::min(s2, ssize - 1);
+    s1 = std::min(s1, s2);
+    if (s1 - f1 > 1e-3) a.taps.push_back(AreaTap{s1 - 1, static_cast<float>((s1 - f1) / cell)});
+    for (int sx = s1; sx < s2; ++sx) a.taps.push_back(AreaTap{sx, static_cast<float>(1.0 / cell)});
+    if (f2 - s2 > 1e-3) a.taps.push_back(AreaTap{s2, static_cast<float>(std::min(std::min(f2 - s2, 1.), cell) / cell)});
+  }
+  a.first.push_back(static_cast<int>(a.taps.size()));
+  return a;
+}
+}  // namespace
+
+void buildAreaResizePlan(HostPlan& plan) {
+  AreaResizePlan& r = plan.resize;
+  r = AreaResizePlan{};
+  r.srcW = plan.mapW; r.srcH = plan.mapH; r.dstW = plan.outW; r.dstH = plan.outH;
+  r.needed = r.srcW != r.dstW || r.srcH != r.dstH;  // reference cpp:735-737
+  if (!r.needed) return;
+  // cv::resize: scale = 1. / ((double)dsize / ssize); INTER_AREA takes the area paths only when shrinking both ways
+  const double sx = 1.0 / (static_cast<double>(r.dstW) / r.srcW), sy = 1.0 / (static_cast<double>(r.dstH) / r.srcH);
+  if (sx < 1.0 || sy < 1.0) {
+    r.supported = false;  // enlarging INTER_AREA is a bilinear variant: not implemented (scale factors < 1)
+    return;
+  }
+  const int ix = static_cast<int>(std::lrint(sx)), iy = static_cast<int>(std::lrint(sy));
+  if (std::abs(sx - ix) < DBL_EPSILON && std::abs(sy - iy) < DBL_EPSILON) {
+    r.cellW = ix; r.cellH = iy;
+    return;
+  }
+  r.x = areaAxis(r.srcW, r.dstW, sx);
+  r.y = areaAxis(r.srcH, r.dstH, sy);
+}
+
 bool buildHostPlan(const FrameTransformContext& ctx, int inW, int inH, int outW, int outH, HostPlan& plan) {
   plan = HostPlan{};
   plan.ctx = ctx;
@@ -148,6 +191,7 @@ bool buildHostPlan(const FrameTransformContext& ctx, int inW, int inH, int outW,
   plan.transparentBorder = ctx.output_layout == LAYOUT_BARREL || ctx.output_layout == LAYOUT_BARREL_SPLIT;
   if (!buildWarpMap(plan)) return false;
   if (plan.kernelSize > 0) quantizeWarpMap(plan);
+  buildAreaResizePlan(plan);
   if (ctx.enable_low_pass_filter) {
     if (ctx.num_vertical_segments < 1 || ctx.num_horizontal_segments < 1) {
       std::printf("Could not generate map: segment counts must be positive.\n");

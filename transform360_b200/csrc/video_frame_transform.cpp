@@ -89,6 +89,11 @@ struct DevicePlan {
   DeviceBuffer<BlurJob> tileJobs, directJobs;
   int numTileJobs = 0, numDirectJobs = 0, tileSmem = 0;
   DeviceBuffer<float> taps;
+  // area down-scale after the gather (only when the scale factors are not 1)
+  bool resizeNeeded = false, resizeSupported = true;
+  int cellW = 0, cellH = 0;
+  DeviceBuffer<int2> areaXTaps, areaYTaps;
+  DeviceBuffer<int> areaXFirst, areaYFirst;
   size_t deviceBytes() const {
     return samples.bytes() + gatherJobs.bytes() + stripJobs[0].bytes() + stripJobs[1].bytes() + stripJobs[2].bytes() + tileJobs.bytes() + directJobs.bytes() + taps.bytes();
   }
@@ -135,6 +140,7 @@ struct PlaneLane {
   cudaStream_t side[t360::kNumBoxClasses] = {};      // the minority gather tile lists of this plane
   cudaEvent_t fork = nullptr, join[t360::kNumBoxClasses] = {}, done = nullptr;
   DeviceBuffer<uint8_t> blurred;                     // low-pass output of this plane
+  DeviceBuffer<uint8_t> scaled;                      // render target at map size when an area resize follows
 };
 
 constexpr int kPitchAlign = 256;
@@ -161,6 +167,7 @@ class VideoFrameTransform {
         if (r.pinned) cudaHostUnregister(reinterpret_cast<void*>(r.base));
       for (PlaneLane& l : lanes_) {
         l.blurred.release();
+        l.scaled.release();
         if (l.main) cudaStreamDestroy(l.main);
         for (auto& st : l.side) if (st) cudaStreamDestroy(st);
         for (auto& e : l.join) if (e) cudaEventDestroy(e);
@@ -434,6 +441,25 @@ class VideoFrameTransform {
     }
     d.lowPass = ctx_.enable_low_pass_filter != 0;
     if (d.lowPass) buildBlurJobs(h, d);
+    d.resizeNeeded = h.resize.needed;
+    d.resizeSupported = h.resize.supported;
+    d.cellW = h.resize.cellW; d.cellH = h.resize.cellH;
+    if (d.resizeNeeded && d.resizeSupported && d.cellW == 0) {
+      auto uploadAxis = [&](const t360::AreaAxis& a, DeviceBuffer<int2>& taps, DeviceBuffer<int>& first) {
+        std::vector<int2> packed(a.taps.size());
+        for (size_t i = 0; i < a.taps.size(); ++i) {
+          int bits;
+          std::memcpy(&bits, &a.taps[i].alpha, sizeof(bits));
+          packed[i] = int2{a.taps[i].src, bits};
+        }
+        taps.reserve(packed.size());
+        CU(cudaMemcpy(taps.ptr, packed.data(), packed.size() * sizeof(int2), cudaMemcpyHostToDevice));
+        first.reserve(a.first.size());
+        CU(cudaMemcpy(first.ptr, a.first.data(), a.first.size() * sizeof(int), cudaMemcpyHostToDevice));
+      };
+      uploadAxis(h.resize.x, d.areaXTaps, d.areaXFirst);
+      uploadAxis(h.resize.y, d.areaYTaps, d.areaYFirst);
+    }
     return d;
   }
 
@@ -669,11 +695,28 @@ class VideoFrameTransform {
       std::printf("Could not find interpolation algorithm for plane %d", imagePlaneIndex);  // reference cpp:780-784
       return true;
     }
-    if (outW != plan.mapW || outH != plan.mapH) {
-      // reference cpp:735-737, 755-777: render at map size, then cv::resize(INTER_AREA).  SURVEY.md 8(f) rank 4.
-      std::printf("Could not transform the plane %d. Error: output %dx%d differs from the planned %dx%d "
-                  "(area-resize path is not implemented yet)\n", imagePlaneIndex, outW, outH, plan.mapW, plan.mapH);
+    if (outW != plan.outW || outH != plan.outH) {
+      std::printf("Could not transform the plane %d. Error: output %dx%d differs from the %dx%d the map was generated for\n",
+                  imagePlaneIndex, outW, outH, plan.outW, plan.outH);
       return false;
+    }
+    // reference cpp:735-737, 755-777: when the map was planned at a scaled size, render at that size into a plane
+    // pre-filled with 0 (luma) / 128 (chroma), then cv::resize(INTER_AREA) down to the requested size
+    uint8_t* finalOut = dOut;
+    const int finalPitch = outPitch;
+    if (plan.resizeNeeded) {
+      if (!plan.resizeSupported) {
+        std::printf("Could not transform the plane %d. Error: scale factors below 1 (INTER_AREA enlarging) are not supported\n",
+                    imagePlaneIndex);
+        return false;
+      }
+      const int sp = alignedPitch(plan.mapW);
+      lane.scaled.reserve(static_cast<size_t>(sp) * plan.mapH + 64);
+      if (plan.transparent) CU(cudaMemset2DAsync(lane.scaled.ptr, sp, imagePlaneIndex ? 128 : 0, plan.mapW, plan.mapH, s));
+      dOut = lane.scaled.ptr;
+      outPitch = sp;
+      outW = plan.mapW;
+      outH = plan.mapH;
     }
     const uint8_t* src = dIn;
     int srcPitch = inPitch;
@@ -697,6 +740,11 @@ class VideoFrameTransform {
       CU(t360::launchGatherPlane(gp, jobs, maps, numSMs_, s));
     } else {
       CU(t360::launchGather(gp, nullptr, 0, numSMs_, s));
+    }
+    if (plan.resizeNeeded) {
+      t360::AreaParams ap{dOut, finalOut, plan.mapW, plan.mapH, outPitch, plan.outW, plan.outH, finalPitch, plan.cellW, plan.cellH,
+                          plan.areaXTaps.ptr, plan.areaXFirst.ptr, plan.areaYTaps.ptr, plan.areaYFirst.ptr};
+      CU(t360::launchAreaResize(ap, s));
     }
     return true;
   }
