@@ -424,9 +424,11 @@ template <int K, int CLS>
 __host__ __device__ constexpr int stageBytes() {  // + slack for the last word over-read; TMA destinations need 128-byte alignment
   return (stageBoxW(K, CLS) * stageBoxH(K, CLS) + 64 + 127) & ~127;
 }
-// One persistent kernel per plane.  The job list is sorted by kind and dealt round-robin over the CTAs, so every CTA
-// first streams its class-0 tiles through the double-buffered TMA pipeline, then handles its few class-1 tiles (their
-// larger box takes both stage buffers, no prefetch), then its few general tiles (taps through L1, any border case).
+// One persistent kernel per plane.  The job list is sorted by kind and dealt round-robin over the CTAs: every CTA starts
+// with its few general tiles (taps through L1, any border case: latency-bound, so they run while all CTAs of the SM
+// are busy and the first TMA box is already on its way), then its few class-1 tiles (their larger box takes both
+// stage buffers, no prefetch), then streams its class-0 tiles through the double-buffered TMA pipeline, which leaves a
+// short, uniform tail.
 template <int K>
 __host__ __device__ constexpr int planeSmemBytes() { return weightBytes<K>() + 2 * stageBytes<K, 0>() + 64; }
 
@@ -503,31 +505,37 @@ gatherPlaneKernel(GatherParams p, StagedParams jobs, const __grid_constant__ CUt
   const int first = blockIdx.x;
   StagedTile tile{};
   int2 rec[kRowsPerThread] = {};
-  if (first < jobs.numTiles) {
-    fetch(first, tile, rec);
-    if (threadIdx.x == 0 && (tile.outY >> kJobKindShift) == 0) {
-      mbarExpectTx(&bars[0], kBox0);
-      tmaLoadBox(stage0, &map0, tile.boxX, tile.boxY, &bars[0]);
-    }
-  }
-  uint32_t q0 = 0, q1 = 0;  // how many class-0 / class-1 tiles this CTA has consumed
+  if (first < jobs.numTiles) fetch(first, tile, rec);
+  // q0 / q1: class-0 / class-1 tiles this CTA has consumed; issued0: class-0 boxes it has requested.  A class-0 tile
+  // with sequence number q lives in stage q & 1 and completes phase (q >> 1) & 1 of that stage's barrier.
+  uint32_t q0 = 0, q1 = 0, issued0 = 0;
+  auto requestClass0 = [&](const StagedTile& t) {  // thread 0 only
+    const uint32_t st = issued0 & 1;
+    mbarExpectTx(&bars[st], kBox0);
+    tmaLoadBox(stage0 + st * kStage, &map0, t.boxX, t.boxY, &bars[st]);
+  };
   for (int i = first; i < jobs.numTiles; i += gridDim.x) {
     const int next = i + gridDim.x;
     StagedTile tileNext{};
     int2 recNext[kRowsPerThread] = {};
     if (next < jobs.numTiles) fetch(next, tileNext, recNext);
     const int kind = tile.outY >> kJobKindShift, outY = tile.outY & kJobRowMask;
+    const bool nextIsClass0 = next < jobs.numTiles && (tileNext.outY >> kJobKindShift) == 0;
     if (kind == 0) {
-      const uint32_t st = q0 & 1;
-      if (threadIdx.x == 0 && next < jobs.numTiles && (tileNext.outY >> kJobKindShift) == 0) {
-        mbarExpectTx(&bars[st ^ 1], kBox0);  // the other stage was released by the barrier that ended the previous job
-        tmaLoadBox(stage0 + (st ^ 1) * kStage, &map0, tileNext.boxX, tileNext.boxY, &bars[st ^ 1]);
+      if (issued0 == q0) {  // not prefetched (first job, or it follows a class-1 tile that needed both stages)
+        if (threadIdx.x == 0) requestClass0(tile);
+        ++issued0;
       }
+      if (nextIsClass0) {  // the other stage was released by the barrier that ended the previous job
+        if (threadIdx.x == 0) requestClass0(tileNext);
+        ++issued0;
+      }
+      const uint32_t st = q0 & 1;
       mbarWait(&bars[st], (q0 >> 1) & 1);
       computeStagedTile<K, stageBoxW(K, 0)>(p, stage0 + st * kStage, tile.outX, outY, tile.boxX, tile.boxY, rec, wsmem, lane, warp);
       ++q0;
     } else if (kind == 1) {
-      if (threadIdx.x == 0) {  // nothing is in flight any more (kinds are sorted): the box may span both stage buffers
+      if (threadIdx.x == 0) {  // no class-0 box is in flight here: the larger box may span both stage buffers
         mbarExpectTx(&bars[2], kBox1);
         tmaLoadBox(stage0, &map1, tile.boxX, tile.boxY, &bars[2]);
       }
@@ -535,6 +543,10 @@ gatherPlaneKernel(GatherParams p, StagedParams jobs, const __grid_constant__ CUt
       computeStagedTile<K, stageBoxW(K, 1)>(p, stage0, tile.outX, outY, tile.boxX, tile.boxY, rec, wsmem, lane, warp);
       ++q1;
     } else {
+      if (nextIsClass0 && issued0 == q0) {  // both stages are idle during a general tile: start the next box now
+        if (threadIdx.x == 0) requestClass0(tileNext);
+        ++issued0;
+      }
       const int y0 = outY + warp * kRowsPerThread;
       if (tile.outX + lane < p.dstW) {
 #pragma unroll

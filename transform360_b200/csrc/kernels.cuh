@@ -121,7 +121,7 @@ constexpr int kBlurMaxSmem = 96 * 1024;
 // Launchers: enqueue on `stream`, return the CUDA status of the launch.  Each counts the kernels it launches.
 // tileList == nullptr: every tile of the plane; otherwise only the listed tile indices (row-major, tilesX wide)
 cudaError_t launchGather(const GatherParams& p, const int* tileList, int numListed, int numSMs, cudaStream_t stream);
-// The whole plane in one persistent kernel: `jobs` is sorted by kind (class 0, class 1, general).  tensorMaps: two
+// The whole plane in one persistent kernel: `jobs` is sorted by kind (general, class 1, class 0).  tensorMaps: two
 // CUtensorMap (128 bytes each) describing the source plane with the staging boxes of class 0 and 1 of p.kernelSize.
 // BORDER_WRAP only.
 cudaError_t launchGatherPlane(const GatherParams& p, const StagedParams& jobs, const void* tensorMaps, int numSMs,

@@ -80,7 +80,7 @@ struct DevicePlan {
   DeviceBuffer<int2> samples;
   int samplesPitch = 0;
   // gather tiles: those whose source window fits the TMA staging box, and the rest (by tile index)
-  DeviceBuffer<StagedTile> gatherJobs;  // every tile of the plane, sorted by kind (class 0, class 1, general)
+  DeviceBuffer<StagedTile> gatherJobs;  // every tile of the plane, sorted by kind (general, class 1, class 0)
   int numJobs = 0, numStaged[t360::kNumBoxClasses] = {}, numFallback = 0;
   int totalStaged() const { int n = 0; for (int c : numStaged) n += c; return n; }
   // low-pass: register-resident strip jobs grouped by vertical half-size 1..3, and the rest (large vertical kernels)
@@ -534,13 +534,14 @@ class VideoFrameTransform {
         if (cls >= 0) staged[cls].push_back(StagedTile{tx * tw, ty * th | (cls << t360::kJobKindShift), boxX, minR});
         else fallback.push_back(StagedTile{tx * tw, ty * th | (t360::kJobGeneral << t360::kJobKindShift), 0, 0});
       }
+    // order: general tiles, then the wide-box class, then the common class (see gatherPlaneKernel)
     std::vector<StagedTile> jobs;
-    for (int c = 0; c < t360::kNumBoxClasses; ++c) {
+    d.numFallback = static_cast<int>(fallback.size());
+    jobs.insert(jobs.end(), fallback.begin(), fallback.end());
+    for (int c = t360::kNumBoxClasses - 1; c >= 0; --c) {
       d.numStaged[c] = static_cast<int>(staged[c].size());
       jobs.insert(jobs.end(), staged[c].begin(), staged[c].end());
     }
-    d.numFallback = static_cast<int>(fallback.size());
-    jobs.insert(jobs.end(), fallback.begin(), fallback.end());
     d.numJobs = static_cast<int>(jobs.size());
     if (!jobs.empty()) {
       d.gatherJobs.reserve(jobs.size());
