@@ -147,6 +147,11 @@ def _remap_hook(src, srows, scols, sstep, dst, drows, dcols, dstep, mp, mstep, i
         out = cv2.remap(s, m, None, interp, dst=d, borderMode=border)
         if not np.shares_memory(out, d):
             d[...] = out
+        # the reference remaps a plane right after it has filtered all of its tiles (cpp:727-754): the whole-plane
+        # low-pass results cached for that plane (keyed by its address) are dead now, and must not be found again
+        # when a later plane or frame is allocated at the same address
+        with _sep_lock:
+            _SEP_CACHE.clear()
         return 0
     except Exception as e:  # pragma: no cover
         print("remap hook error:", e)
