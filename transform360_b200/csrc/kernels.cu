@@ -672,6 +672,24 @@ struct StripRowReader {
   }
 };
 
+// One chunk of 4 taps: 32 FMAs on the ring, then ring slots 4u..4u+3 take the next group of source bytes.
+template <bool EDGE, int U, bool LAST>
+__device__ __forceinline__ void stripChunk(const StripRowReader<EDGE>& rd, const float4* __restrict__ taps, int c, uint32_t& prev,
+                                           float (&ring)[12], float (&s)[8]) {
+  const float4 k4 = __ldg(taps + c);
+  uint32_t grp = 0;
+  if (!LAST) grp = rd.next(c + 3, prev);  // the group that replaces the 4 oldest window positions
+  const float k[4] = {k4.x, k4.y, k4.z, k4.w};
+#pragma unroll
+  for (int t = 0; t < 4; ++t)
+#pragma unroll
+    for (int m = 0; m < 8; ++m) s[m] = __fmaf_rn(k[t], ring[(4 * U + m + t) % 12], s[m]);
+  if (!LAST) {
+#pragma unroll
+    for (int b = 0; b < 4; ++b) ring[4 * U + b] = byteToFloat(grp, b);
+  }
+}
+
 template <bool EDGE>
 __device__ __forceinline__ void stripRow(const StripParams& p, const StripJob& job, const StripRowReader<EDGE>& rd,
                                          const uint32_t (&raw)[4], float (&s)[8]) {
@@ -686,22 +704,27 @@ __device__ __forceinline__ void stripRow(const StripParams& p, const StripJob& j
 #pragma unroll
   for (int m = 0; m < 8; ++m) s[m] = 0.0f;
   const float4* taps = reinterpret_cast<const float4*>(p.taps + job.kxOffset);
-  for (int c = 0; c < job.kxChunks; c += 3) {
-#pragma unroll
-    for (int u = 0; u < 3; ++u) {
-      if (c + u < job.kxChunks) {
-        const float4 k4 = __ldg(taps + c + u);
-        // the group that replaces ring slots 4u..4u+3 is only needed if another chunk follows
-        const uint32_t grp = c + u + 1 < job.kxChunks ? rd.next(c + u + 3, prev) : 0u;
-        const float k[4] = {k4.x, k4.y, k4.z, k4.w};
-#pragma unroll
-        for (int t = 0; t < 4; ++t)
-#pragma unroll
-          for (int m = 0; m < 8; ++m) s[m] = __fmaf_rn(k[t], ring[(4 * u + m + t) % 12], s[m]);
-#pragma unroll
-        for (int b = 0; b < 4; ++b) ring[4 * u + b] = byteToFloat(grp, b);
-      }
-    }
+  // 3-, 5-, 7-, 9-tap kernels (1-3 chunks) cover most of a plane: straight-line code for them (warp-uniform switch)
+  switch (job.kxChunks) {
+    case 1:
+      stripChunk<EDGE, 0, true>(rd, taps, 0, prev, ring, s);
+      return;
+    case 2:
+      stripChunk<EDGE, 0, false>(rd, taps, 0, prev, ring, s);
+      stripChunk<EDGE, 1, true>(rd, taps, 1, prev, ring, s);
+      return;
+    case 3:
+      stripChunk<EDGE, 0, false>(rd, taps, 0, prev, ring, s);
+      stripChunk<EDGE, 1, false>(rd, taps, 1, prev, ring, s);
+      stripChunk<EDGE, 2, true>(rd, taps, 2, prev, ring, s);
+      return;
+    default:
+      break;
+  }
+  for (int c = 0; c < job.kxChunks; c += 3) {  // the ring is back in phase every 3 chunks
+    stripChunk<EDGE, 0, false>(rd, taps, c, prev, ring, s);
+    if (c + 1 < job.kxChunks) stripChunk<EDGE, 1, false>(rd, taps, c + 1, prev, ring, s);
+    if (c + 2 < job.kxChunks) stripChunk<EDGE, 2, false>(rd, taps, c + 2, prev, ring, s);
   }
 }
 
