@@ -92,14 +92,14 @@ __device__ __forceinline__ void stageWeights(const int16_t* __restrict__ g, unsi
   }
 }
 
-// K x K window whose rows are `pitch` bytes apart starting at byte offset `off` of a 4-byte aligned base
-// (global through the read-only path, or shared).  No bounds handling: the caller guarantees the window
-// (plus the tail of its last aligned word) is readable.
-template <int K, bool SHARED>
+// K x K window in GLOBAL memory (read-only path) whose rows are `pitch` bytes apart, starting at byte offset `off`
+// of a 4-byte aligned base.  No bounds handling: the caller guarantees the window (plus the tail of its last
+// aligned word) is readable.
+template <int K>
 __device__ __forceinline__ int foldWindow(const uint32_t* __restrict__ words, int off, int pitch,
                                           const unsigned char* wsmem, int phase) {
   phase = weightSlot<K>(phase);
-  auto ld = [&](int wordIndex) -> uint32_t { return SHARED ? words[wordIndex] : __ldg(words + wordIndex); };
+  auto ld = [&](int wordIndex) -> uint32_t { return __ldg(words + wordIndex); };
   int acc = 0;
   if constexpr (K == 2) {
     const uint2 wt = reinterpret_cast<const uint2*>(wsmem)[phase];
@@ -301,7 +301,7 @@ __device__ __forceinline__ int gatherPixel(const SrcView& s, const unsigned char
   // interior: no wrapping, and the aligned word reads stay inside the row (col0 + K + 3 <= w)
   const bool interior = col0 >= 0 && row0 >= 0 && col0 + K + 3 <= s.w && row0 + K <= s.h;
   if (interior)
-    return roundToByte(foldWindow<K, false>(s.words, row0 * s.pitch + col0 + s.misalign, s.pitch, wsmem, phase));
+    return roundToByte(foldWindow<K>(s.words, row0 * s.pitch + col0 + s.misalign, s.pitch, wsmem, phase));
 
   // window touches an edge: per-tap addressing.  BORDER_WRAP wraps columns AND rows (reference cpp:719).
   const int16_t* wt = reinterpret_cast<const int16_t*>(wsmem) + weightSlot<K>(phase) * (K == 2 ? 4 : 8);
@@ -342,7 +342,7 @@ __device__ __forceinline__ int gatherPixel(const SrcView& s, const unsigned char
 
 template <int K, bool TRANSPARENT>
 __global__ void __launch_bounds__(gatherThreads(K), K == 8 ? 1 : 4)
-gatherKernel(GatherParams p, const int* __restrict__ tileList, int tilesX, int numTiles) {
+gatherKernel(GatherParams p, int tilesX, int numTiles) {
   extern __shared__ __align__(16) unsigned char smem[];
   stageWeights<K>(p.weights, smem);
   __syncthreads();
@@ -354,8 +354,7 @@ gatherKernel(GatherParams p, const int* __restrict__ tileList, int tilesX, int n
   s.w = p.srcW; s.h = p.srcH; s.pitch = p.srcPitch;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
-  for (int i = blockIdx.x; i < numTiles; i += gridDim.x) {
-    const int tile = tileList ? tileList[i] : i;
+  for (int tile = blockIdx.x; tile < numTiles; tile += gridDim.x) {
     const int ty = tile / tilesX, tx = tile - ty * tilesX;
     const int y0 = ty * gatherTileH(K) + warp * kRowsPerThread;
     const int segX = tx * kGatherTileW;
@@ -880,17 +879,17 @@ cudaError_t prepare(LaunchCfg& cfg, int threads, int smemBytes) {
 }
 
 template <int K, bool T>
-cudaError_t launchGatherK(const GatherParams& p, const int* tileList, int numListed, int numSMs, cudaStream_t stream) {
+cudaError_t launchGatherK(const GatherParams& p, int numSMs, cudaStream_t stream) {
   static thread_local LaunchCfg cfg;  // per kernel instantiation (and per host thread / device binding)
   constexpr int threads = gatherThreads(K), smemBytes = weightBytes<K>();
   cudaError_t err = prepare<gatherKernel<K, T>>(cfg, threads, smemBytes);
   if (err != cudaSuccess) return err;
   const int tilesX = (p.dstW + kGatherTileW - 1) / kGatherTileW;
   const int tilesY = (p.dstH + gatherTileH(K) - 1) / gatherTileH(K);
-  const int numTiles = tileList ? numListed : tilesX * tilesY;
+  const int numTiles = tilesX * tilesY;
   if (numTiles <= 0) return cudaSuccess;
   const int grid = std::min(numSMs * cfg.perSM, numTiles);  // whole waves: a multiple of the SM count
-  gatherKernel<K, T><<<grid, threads, smemBytes, stream>>>(p, tileList, tilesX, numTiles);
+  gatherKernel<K, T><<<grid, threads, smemBytes, stream>>>(p, tilesX, numTiles);
   gLaunches.fetch_add(1, std::memory_order_relaxed);
   return cudaGetLastError();
 }
@@ -923,14 +922,14 @@ cudaError_t launchPlaneK(const GatherParams& p, const StagedParams& jobs, const 
 
 }  // namespace
 
-cudaError_t launchGather(const GatherParams& p, const int* tileList, int numListed, int numSMs, cudaStream_t stream) {
+cudaError_t launchGather(const GatherParams& p, int numSMs, cudaStream_t stream) {
   if (p.dstW <= 0 || p.dstH <= 0) return cudaSuccess;
   const bool t = p.transparent != 0;
   switch (p.kernelSize) {
     case 1: return t ? launchNearest<true>(p, numSMs, stream) : launchNearest<false>(p, numSMs, stream);
-    case 2: return t ? launchGatherK<2, true>(p, tileList, numListed, numSMs, stream) : launchGatherK<2, false>(p, tileList, numListed, numSMs, stream);
-    case 4: return t ? launchGatherK<4, true>(p, tileList, numListed, numSMs, stream) : launchGatherK<4, false>(p, tileList, numListed, numSMs, stream);
-    case 8: return t ? launchGatherK<8, true>(p, tileList, numListed, numSMs, stream) : launchGatherK<8, false>(p, tileList, numListed, numSMs, stream);
+    case 2: return t ? launchGatherK<2, true>(p, numSMs, stream) : launchGatherK<2, false>(p, numSMs, stream);
+    case 4: return t ? launchGatherK<4, true>(p, numSMs, stream) : launchGatherK<4, false>(p, numSMs, stream);
+    case 8: return t ? launchGatherK<8, true>(p, numSMs, stream) : launchGatherK<8, false>(p, numSMs, stream);
     default: return cudaErrorInvalidValue;
   }
 }

@@ -119,8 +119,8 @@ constexpr int kBlurTileW = 64, kBlurTileH = 32;
 constexpr int kBlurMaxSmem = 96 * 1024;
 
 // Launchers: enqueue on `stream`, return the CUDA status of the launch.  Each counts the kernels it launches.
-// tileList == nullptr: every tile of the plane; otherwise only the listed tile indices (row-major, tilesX wide)
-cudaError_t launchGather(const GatherParams& p, const int* tileList, int numListed, int numSMs, cudaStream_t stream);
+// General path for a whole plane: taps through L1, every border mode (BORDER_WRAP, BORDER_TRANSPARENT), nearest.
+cudaError_t launchGather(const GatherParams& p, int numSMs, cudaStream_t stream);
 // The whole plane in one persistent kernel: `jobs` is sorted by kind (general, class 1, class 0).  tensorMaps: two
 // CUtensorMap (128 bytes each) describing the source plane with the staging boxes of class 0 and 1 of p.kernelSize.
 // BORDER_WRAP only.

@@ -137,8 +137,7 @@ bool encodePlaneMap(CUtensorMap* map, const uint8_t* base, int w, int h, int pit
 constexpr int kPlaneLanes = 3;
 struct PlaneLane {
   cudaStream_t main = nullptr;                       // chroma lanes only (lane 0 runs on the caller's stream)
-  cudaStream_t side[t360::kNumBoxClasses] = {};      // the minority gather tile lists of this plane
-  cudaEvent_t fork = nullptr, join[t360::kNumBoxClasses] = {}, done = nullptr;
+  cudaEvent_t done = nullptr;                        // recorded when this lane's plane has been enqueued completely
   DeviceBuffer<uint8_t> blurred;                     // low-pass output of this plane
   DeviceBuffer<uint8_t> scaled;                      // render target at map size when an area resize follows
 };
@@ -169,9 +168,6 @@ class VideoFrameTransform {
         l.blurred.release();
         l.scaled.release();
         if (l.main) cudaStreamDestroy(l.main);
-        for (auto& st : l.side) if (st) cudaStreamDestroy(st);
-        for (auto& e : l.join) if (e) cudaEventDestroy(e);
-        if (l.fork) cudaEventDestroy(l.fork);
         if (l.done) cudaEventDestroy(l.done);
       }
       if (frameFork_) cudaEventDestroy(frameFork_);
@@ -363,9 +359,6 @@ class VideoFrameTransform {
     for (int i = 0; i < kPlaneLanes; ++i) {
       PlaneLane& l = lanes_[i];
       if (i > 0) CU(cudaStreamCreateWithFlags(&l.main, cudaStreamNonBlocking));
-      for (auto& st : l.side) CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-      for (auto& e : l.join) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-      CU(cudaEventCreateWithFlags(&l.fork, cudaEventDisableTiming));
       CU(cudaEventCreateWithFlags(&l.done, cudaEventDisableTiming));
     }
     CU(cudaEventCreateWithFlags(&frameFork_, cudaEventDisableTiming));
@@ -740,7 +733,7 @@ class VideoFrameTransform {
       t360::StagedParams jobs{plan.gatherJobs.ptr, plan.numJobs};
       CU(t360::launchGatherPlane(gp, jobs, maps, numSMs_, s));
     } else {
-      CU(t360::launchGather(gp, nullptr, 0, numSMs_, s));
+      CU(t360::launchGather(gp, numSMs_, s));
     }
     if (plan.resizeNeeded) {
       t360::AreaParams ap{dOut, finalOut, plan.mapW, plan.mapH, outPitch, plan.outW, plan.outH, finalPitch, plan.cellW, plan.cellH,
