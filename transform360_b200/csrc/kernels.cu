@@ -29,6 +29,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <cstring>
 
 namespace t360 {
 
@@ -423,16 +424,20 @@ template <int K, int CLS>
 __host__ __device__ constexpr int stageBytes() {  // + slack for the last word over-read; TMA destinations need 128-byte alignment
   return (stageBoxW(K, CLS) * stageBoxH(K, CLS) + 64 + 127) & ~127;
 }
-// One persistent kernel per plane.  The job list is sorted by kind and dealt round-robin over the CTAs: every CTA starts
-// with its few general tiles (taps through L1, any border case: latency-bound, so they run while all CTAs of the SM
-// are busy and the first TMA box is already on its way), then its few class-1 tiles (their larger box takes both
-// stage buffers, no prefetch), then streams its class-0 tiles through the double-buffered TMA pipeline, which leaves a
-// short, uniform tail.
+// One persistent kernel per plane or per frame.  The job list is sorted by kind: every CTA starts with general tiles
+// (taps through L1, any border case: latency-bound, so they run while all CTAs of the SM are busy and the first TMA box
+// is already on its way), then class-1 tiles (their larger box takes both stage buffers, no prefetch), then streams
+// class-0 tiles through the double-buffered TMA pipeline, which leaves a short, uniform tail.  (The staging logic
+// itself accepts any order.)
 template <int K>
 __host__ __device__ constexpr int planeSmemBytes() { return weightBytes<K>() + 2 * stageBytes<K, 0>() + 64; }
 
+struct FrameTensorMaps {
+  CUtensorMap map[kMaxFramePlanes][kNumBoxClasses];
+};
+
 template <int K, int PITCH>
-__device__ __forceinline__ void computeStagedTile(const GatherParams& p, const unsigned char* stage, int outX, int outY, int boxX,
+__device__ __forceinline__ void computeStagedTile(const PlaneView& p, const unsigned char* stage, int outX, int outY, int boxX,
                                                   int boxY, const int2 (&rec)[kRowsPerThread], const unsigned char* wsmem, int lane,
                                                   int warp) {
   const int y0 = outY + warp * kRowsPerThread;
@@ -442,6 +447,8 @@ __device__ __forceinline__ void computeStagedTile(const GatherParams& p, const u
     // warp-uniform choice: every lane's 4 pixels share their columns (inactive lanes do not veto); needs all 4 rows
     shared = y0 + kRowsPerThread <= p.dstH && __all_sync(0xffffffffu, !active || columnShareable(rec));
   }
+  uint8_t* const dst = p.dst;
+  const int dstPitch = p.dstPitch;
   if (shared) {
     if constexpr (K >= 4) {
       if (active) {
@@ -449,26 +456,26 @@ __device__ __forceinline__ void computeStagedTile(const GatherParams& p, const u
         gatherColumnShared<K, PITCH>(stage, boxX, boxY, rec, wsmem, acc);
 #pragma unroll
         for (int j = 0; j < kRowsPerThread; ++j)
-          p.dst[(size_t)(y0 + j) * p.dstPitch + outX + recordColumn(rec[j].x)] = (uint8_t)roundToByte(acc[j]);
+          dst[(size_t)(y0 + j) * dstPitch + outX + recordColumn(rec[j].x)] = (uint8_t)roundToByte(acc[j]);
       }
     }
   } else if (active) {
     const uint32_t stageAddr = smemAddr(stage), wAddr = smemAddr(wsmem);
+    const int dstH = p.dstH;
 #pragma unroll
     for (int j = 0; j < kRowsPerThread; ++j) {
-      if (y0 + j >= p.dstH) break;
+      if (y0 + j >= dstH) break;
       const int row0 = rec[j].y >> 10, phase = rec[j].y & 1023;
       const int off = (row0 - boxY) * PITCH + (recordCol0(rec[j].x) - boxX);
       const int acc = foldWindowShared<K, PITCH>(stageAddr, off, wAddr, phase);
-      p.dst[(size_t)(y0 + j) * p.dstPitch + outX + recordColumn(rec[j].x)] = (uint8_t)roundToByte(acc);
+      dst[(size_t)(y0 + j) * dstPitch + outX + recordColumn(rec[j].x)] = (uint8_t)roundToByte(acc);
     }
   }
 }
 
 template <int K>
 __global__ void __launch_bounds__(gatherThreads(K), K == 8 ? 1 : 3)
-gatherPlaneKernel(GatherParams p, StagedParams jobs, const __grid_constant__ CUtensorMap map0,
-                  const __grid_constant__ CUtensorMap map1) {
+gatherFrameKernel(const __grid_constant__ FrameGatherParams p, StagedParams jobs, const __grid_constant__ FrameTensorMaps maps) {
   static_assert(stageBoxW(K, 1) * stageBoxH(K, 1) + 64 <= 2 * stageBytes<K, 0>(), "a class-1 box must fit both stage buffers");
   extern __shared__ __align__(16) unsigned char smem[];
   unsigned char* wsmem = smem;
@@ -486,40 +493,55 @@ gatherPlaneKernel(GatherParams p, StagedParams jobs, const __grid_constant__ CUt
   stageWeights<K>(p.weights, wsmem);
   __syncthreads();
 
-  SrcView sv;
-  sv.bytes = p.src;
-  sv.misalign = (int)(reinterpret_cast<uintptr_t>(p.src) & 3);
-  sv.words = reinterpret_cast<const uint32_t*>(p.src - sv.misalign);
-  sv.w = p.srcW; sv.h = p.srcH; sv.pitch = p.srcPitch;
-
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  // software pipeline: tile header and plan records of job n+1 are fetched while job n is computed
-  auto fetch = [&](int i, StagedTile& t, int2 (&rec)[kRowsPerThread]) {
-    t = jobs.tiles[i];
+  // Software pipeline, two deep, so that no load is waited for in the iteration that issues it (a warp executes in
+  // order: a header load followed by the record loads that need its fields would stall the whole tile on the header):
+  //   iteration n:  issue header(n+2) | issue records(n+1) from header(n+1), already in registers | compute tile n
+  auto loadHeader = [&](int i) { return i < jobs.numTiles ? jobs.tiles[i] : StagedTile{0, 0, 0, 0}; };
+  // The plane of a tile, field by field through selects on kernel-parameter operands: an indexed load from the
+  // parameter bank instead would put its latency in front of every tile's record loads (measured: +5 % on a plane).
+  static_assert(kMaxFramePlanes == 3, "planeOf selects among three planes");
+  auto planeOf = [&](const StagedTile& t) {
+    const int pl = t.outY >> kJobPlaneShift;
+    const PlaneView &a = p.plane[0], &b = p.plane[1], &c = p.plane[2];
+#define T360_PICK(f) (pl == 0 ? a.f : (pl == 1 ? b.f : c.f))
+    return PlaneView{T360_PICK(src), T360_PICK(dst), T360_PICK(samples), T360_PICK(srcW), T360_PICK(srcH), T360_PICK(srcPitch),
+                     T360_PICK(dstW), T360_PICK(dstH), T360_PICK(dstPitch), T360_PICK(samplesPitch), 0};
+#undef T360_PICK
+  };
+  auto loadRecords = [&](int i, const StagedTile& t, int2 (&rec)[kRowsPerThread]) {
+    const PlaneView pv = planeOf(t);
     const int y0 = (t.outY & kJobRowMask) + warp * kRowsPerThread, slot = t.outX + lane;  // records are in lane order
 #pragma unroll
     for (int j = 0; j < kRowsPerThread; ++j)
-      rec[j] = (slot < p.dstW && y0 + j < p.dstH) ? loadPlan(p.samples + (size_t)(y0 + j) * p.samplesPitch + slot) : make_int2(0, 0);
+      rec[j] = (i < jobs.numTiles && slot < pv.dstW && y0 + j < pv.dstH) ? loadPlan(pv.samples + (size_t)(y0 + j) * pv.samplesPitch + slot)
+                                                                          : make_int2(0, 0);
   };
-  const int first = blockIdx.x;
-  StagedTile tile{};
-  int2 rec[kRowsPerThread] = {};
-  if (first < jobs.numTiles) fetch(first, tile, rec);
+  // Dynamic tile scheduling: the first three jobs of a CTA are static (blockIdx.x + k * gridDim.x), every further one
+  // is claimed from a global counter by thread 0 one iteration before its header is needed and handed to the other
+  // threads through a double-buffered shared slot across the end-of-job barrier.
+  int* claimSlot = reinterpret_cast<int*>(bars + 3);
+  int i0 = blockIdx.x, i1 = i0 + gridDim.x, i2 = i1 + gridDim.x;
+  StagedTile tile = loadHeader(i0), tileNext = loadHeader(i1);
+  int2 rec[kRowsPerThread];
+  loadRecords(i0, tile, rec);
   // q0 / q1: class-0 / class-1 tiles this CTA has consumed; issued0: class-0 boxes it has requested.  A class-0 tile
   // with sequence number q lives in stage q & 1 and completes phase (q >> 1) & 1 of that stage's barrier.
   uint32_t q0 = 0, q1 = 0, issued0 = 0;
   auto requestClass0 = [&](const StagedTile& t) {  // thread 0 only
     const uint32_t st = issued0 & 1;
     mbarExpectTx(&bars[st], kBox0);
-    tmaLoadBox(stage0 + st * kStage, &map0, t.boxX, t.boxY, &bars[st]);
+    tmaLoadBox(stage0 + st * kStage, &maps.map[t.outY >> kJobPlaneShift][0], t.boxX, t.boxY, &bars[st]);
   };
-  for (int i = first; i < jobs.numTiles; i += gridDim.x) {
-    const int next = i + gridDim.x;
-    StagedTile tileNext{};
-    int2 recNext[kRowsPerThread] = {};
-    if (next < jobs.numTiles) fetch(next, tileNext, recNext);
-    const int kind = tile.outY >> kJobKindShift, outY = tile.outY & kJobRowMask;
-    const bool nextIsClass0 = next < jobs.numTiles && (tileNext.outY >> kJobKindShift) == 0;
+  for (uint32_t it = 0; i0 < jobs.numTiles; ++it) {
+    const int next = i1;
+    if (threadIdx.x == 0) claimSlot[it & 1] = 3 * (int)gridDim.x + atomicAdd(jobs.claimCounter, 1);
+    const StagedTile tileAfterNext = loadHeader(i2);
+    int2 recNext[kRowsPerThread];
+    loadRecords(next, tileNext, recNext);
+    const int kind = (tile.outY >> kJobKindShift) & kJobKindMask, outY = tile.outY & kJobRowMask;
+    const PlaneView pv = planeOf(tile);
+    const bool nextIsClass0 = next < jobs.numTiles && ((tileNext.outY >> kJobKindShift) & kJobKindMask) == 0;
     if (kind == 0) {
       if (issued0 == q0) {  // not prefetched (first job, or it follows a class-1 tile that needed both stages)
         if (threadIdx.x == 0) requestClass0(tile);
@@ -531,35 +553,48 @@ gatherPlaneKernel(GatherParams p, StagedParams jobs, const __grid_constant__ CUt
       }
       const uint32_t st = q0 & 1;
       mbarWait(&bars[st], (q0 >> 1) & 1);
-      computeStagedTile<K, stageBoxW(K, 0)>(p, stage0 + st * kStage, tile.outX, outY, tile.boxX, tile.boxY, rec, wsmem, lane, warp);
+      computeStagedTile<K, stageBoxW(K, 0)>(pv, stage0 + st * kStage, tile.outX, outY, tile.boxX, tile.boxY, rec, wsmem, lane, warp);
       ++q0;
     } else if (kind == 1) {
       if (threadIdx.x == 0) {  // no class-0 box is in flight here: the larger box may span both stage buffers
         mbarExpectTx(&bars[2], kBox1);
-        tmaLoadBox(stage0, &map1, tile.boxX, tile.boxY, &bars[2]);
+        tmaLoadBox(stage0, &maps.map[tile.outY >> kJobPlaneShift][1], tile.boxX, tile.boxY, &bars[2]);
       }
       mbarWait(&bars[2], q1 & 1);
-      computeStagedTile<K, stageBoxW(K, 1)>(p, stage0, tile.outX, outY, tile.boxX, tile.boxY, rec, wsmem, lane, warp);
+      computeStagedTile<K, stageBoxW(K, 1)>(pv, stage0, tile.outX, outY, tile.boxX, tile.boxY, rec, wsmem, lane, warp);
       ++q1;
     } else {
       if (nextIsClass0 && issued0 == q0) {  // both stages are idle during a general tile: start the next box now
         if (threadIdx.x == 0) requestClass0(tileNext);
         ++issued0;
       }
+      SrcView sv;
+      sv.bytes = pv.src;
+      sv.misalign = (int)(reinterpret_cast<uintptr_t>(pv.src) & 3);
+      sv.words = reinterpret_cast<const uint32_t*>(pv.src - sv.misalign);
+      sv.w = pv.srcW; sv.h = pv.srcH; sv.pitch = pv.srcPitch;
       const int y0 = outY + warp * kRowsPerThread;
-      if (tile.outX + lane < p.dstW) {
+      if (tile.outX + lane < pv.dstW) {
 #pragma unroll
         for (int j = 0; j < kRowsPerThread; ++j) {
-          if (y0 + j >= p.dstH) break;
+          if (y0 + j >= pv.dstH) break;
           const int v = gatherPixel<K, false>(sv, wsmem, recordCol0(rec[j].x), rec[j].y);
-          p.dst[(size_t)(y0 + j) * p.dstPitch + tile.outX + recordColumn(rec[j].x)] = (uint8_t)v;
+          pv.dst[(size_t)(y0 + j) * pv.dstPitch + tile.outX + recordColumn(rec[j].x)] = (uint8_t)v;
         }
       }
     }
-    __syncthreads();  // everyone is done with this job's stage before it is refilled
+    __syncthreads();  // everyone is done with this job's stage before it is refilled (and sees the claimed index)
+    i0 = i1; i1 = i2; i2 = claimSlot[it & 1];
     tile = tileNext;
+    tileNext = tileAfterNext;
 #pragma unroll
     for (int j = 0; j < kRowsPerThread; ++j) rec[j] = recNext[j];
+  }
+  // the CTA that finishes last re-arms the scheduler for the next launch (claimCounter[0] = claims, [1] = finished CTAs)
+  if (threadIdx.x == 0 && atomicAdd(jobs.claimCounter + 1, 1) == (int)gridDim.x - 1) {
+    jobs.claimCounter[0] = 0;
+    jobs.claimCounter[1] = 0;
+    __threadfence();
   }
 }
 
@@ -908,14 +943,14 @@ cudaError_t launchNearest(const GatherParams& p, int numSMs, cudaStream_t stream
 }
 
 template <int K>
-cudaError_t launchPlaneK(const GatherParams& p, const StagedParams& jobs, const CUtensorMap& map0, const CUtensorMap& map1, int numSMs,
+cudaError_t launchFrameK(const FrameGatherParams& p, const StagedParams& jobs, const FrameTensorMaps& maps, int numSMs,
                          cudaStream_t stream) {
   static thread_local LaunchCfg cfg;
   constexpr int threads = gatherThreads(K), smemBytes = planeSmemBytes<K>();
-  cudaError_t err = prepare<gatherPlaneKernel<K>>(cfg, threads, smemBytes);
+  cudaError_t err = prepare<gatherFrameKernel<K>>(cfg, threads, smemBytes);
   if (err != cudaSuccess) return err;
   const int grid = std::min(numSMs * cfg.perSM, jobs.numTiles);  // persistent: whole waves of CTAs
-  gatherPlaneKernel<K><<<grid, threads, smemBytes, stream>>>(p, jobs, map0, map1);
+  gatherFrameKernel<K><<<grid, threads, smemBytes, stream>>>(p, jobs, maps);
   gLaunches.fetch_add(1, std::memory_order_relaxed);
   return cudaGetLastError();
 }
@@ -934,15 +969,18 @@ cudaError_t launchGather(const GatherParams& p, int numSMs, cudaStream_t stream)
   }
 }
 
-cudaError_t launchGatherPlane(const GatherParams& p, const StagedParams& jobs, const void* tensorMaps, int numSMs,
+cudaError_t launchGatherFrame(const FrameGatherParams& p, const StagedParams& jobs, const void* tensorMaps, int numSMs,
                               cudaStream_t stream) {
   if (jobs.numTiles <= 0) return cudaSuccess;
-  if (p.transparent) return cudaErrorInvalidValue;
-  const CUtensorMap* maps = static_cast<const CUtensorMap*>(tensorMaps);
+  if (p.numPlanes < 1 || p.numPlanes > kMaxFramePlanes) return cudaErrorInvalidValue;
+  FrameTensorMaps maps;
+  std::memcpy(&maps, tensorMaps, sizeof(CUtensorMap) * kNumBoxClasses * p.numPlanes);
+  for (int i = p.numPlanes; i < kMaxFramePlanes; ++i)  // unused entries: valid descriptors that no tile refers to
+    for (int c = 0; c < kNumBoxClasses; ++c) maps.map[i][c] = maps.map[0][c];
   switch (p.kernelSize) {
-    case 2: return launchPlaneK<2>(p, jobs, maps[0], maps[1], numSMs, stream);
-    case 4: return launchPlaneK<4>(p, jobs, maps[0], maps[1], numSMs, stream);
-    case 8: return launchPlaneK<8>(p, jobs, maps[0], maps[1], numSMs, stream);
+    case 2: return launchFrameK<2>(p, jobs, maps, numSMs, stream);
+    case 4: return launchFrameK<4>(p, jobs, maps, numSMs, stream);
+    case 8: return launchFrameK<8>(p, jobs, maps, numSMs, stream);
     default: return cudaErrorInvalidValue;
   }
 }

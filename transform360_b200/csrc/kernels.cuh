@@ -23,10 +23,30 @@ struct GatherParams {
 // One tile of the TMA-staged gather: a gatherTileW x gatherTileH block of output pixels whose whole source
 // window fits the fixed staging box placed at (boxX, boxY) of the source plane (boxX % 16 == 0).
 struct StagedTile {
-  int outX, outY, boxX, boxY;  // outY carries the job kind in its top byte (kJobKindShift)
+  int outX, outY, boxX, boxY;  // outY carries the job kind (kJobKindShift) and the image plane (kJobPlaneShift)
 };
-// job kinds of the per-plane gather kernel: 0 / 1 = staged through TMA with box class 0 / 1, 2 = general (L1) path
+// job kinds of the persistent gather kernel: 0 / 1 = staged through TMA with box class 0 / 1, 2 = general (L1) path
 constexpr int kJobKindShift = 24, kJobRowMask = (1 << kJobKindShift) - 1, kJobGeneral = 2;
+constexpr int kJobPlaneShift = 28, kJobKindMask = (1 << (kJobPlaneShift - kJobKindShift)) - 1;
+
+// The persistent gather kernel takes the tiles of up to three image planes (Y, U, V of one frame) in ONE launch:
+// one weight-table prologue and one tail per frame instead of per plane, and the dynamic scheduler balances the
+// planes against each other.  Everything that differs between the planes sits in a PlaneView (+ two tensor maps).
+constexpr int kMaxFramePlanes = 3;
+struct PlaneView {
+  const uint8_t* src;   // (blurred) input plane
+  uint8_t* dst;
+  const int2* samples;  // lane-ordered records, [dstH][samplesPitch]
+  int srcW, srcH, srcPitch;
+  int dstW, dstH, dstPitch;
+  int samplesPitch;
+  int reserved;
+};
+struct FrameGatherParams {
+  PlaneView plane[kMaxFramePlanes];
+  const int16_t* weights;
+  int kernelSize, numPlanes;
+};
 
 constexpr int kGatherTileW = 32;                                   // one warp = 32 adjacent columns
 __host__ __device__ constexpr int gatherThreads(int k) { return k == 8 ? 512 : 256; }
@@ -62,6 +82,7 @@ constexpr int kRecordColumnShift = 27;
 struct StagedParams {
   const StagedTile* tiles;  // device list
   int numTiles;
+  int* claimCounter;        // two device ints, zero before the first launch (the kernel re-arms them): tile scheduler
 };
 
 // One tile of the segmented low-pass: output rectangle and the taps to use.
@@ -121,10 +142,10 @@ constexpr int kBlurMaxSmem = 96 * 1024;
 // Launchers: enqueue on `stream`, return the CUDA status of the launch.  Each counts the kernels it launches.
 // General path for a whole plane: taps through L1, every border mode (BORDER_WRAP, BORDER_TRANSPARENT), nearest.
 cudaError_t launchGather(const GatherParams& p, int numSMs, cudaStream_t stream);
-// The whole plane in one persistent kernel: `jobs` is sorted by kind (general, class 1, class 0).  tensorMaps: two
-// CUtensorMap (128 bytes each) describing the source plane with the staging boxes of class 0 and 1 of p.kernelSize.
-// BORDER_WRAP only.
-cudaError_t launchGatherPlane(const GatherParams& p, const StagedParams& jobs, const void* tensorMaps, int numSMs,
+// Whole planes in one persistent kernel: `jobs` lists the tiles of every plane, sorted by kind (general, class 1,
+// class 0).  tensorMaps: per plane two CUtensorMap (128 bytes each) describing its source with the staging boxes of
+// class 0 and 1 of p.kernelSize, i.e. [numPlanes][kNumBoxClasses].  BORDER_WRAP only.
+cudaError_t launchGatherFrame(const FrameGatherParams& p, const StagedParams& jobs, const void* tensorMaps, int numSMs,
                               cudaStream_t stream);
 cudaError_t launchBlurStrips(const StripParams& p, int hy, cudaStream_t stream);  // register-resident, hy <= kStripMaxHy
 cudaError_t launchBlur(const BlurParams& p, cudaStream_t stream);        // shared-memory tiles

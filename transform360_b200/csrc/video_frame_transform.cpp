@@ -81,6 +81,7 @@ struct DevicePlan {
   int samplesPitch = 0;
   // gather tiles: those whose source window fits the TMA staging box, and the rest (by tile index)
   DeviceBuffer<StagedTile> gatherJobs;  // every tile of the plane, sorted by kind (general, class 1, class 0)
+  std::vector<StagedTile> hostJobs;     // the same list on the host: merged per frame by frameJobList()
   int numJobs = 0, numStaged[t360::kNumBoxClasses] = {}, numFallback = 0;
   int totalStaged() const { int n = 0; for (int c : numStaged) n += c; return n; }
   // low-pass: register-resident strip jobs grouped by vertical half-size 1..3, and the rest (large vertical kernels)
@@ -140,6 +141,26 @@ struct PlaneLane {
   cudaEvent_t done = nullptr;                        // recorded when this lane's plane has been enqueued completely
   DeviceBuffer<uint8_t> blurred;                     // low-pass output of this plane
   DeviceBuffer<uint8_t> scaled;                      // render target at map size when an area resize follows
+  DeviceBuffer<int> claimCounter;                    // dynamic tile scheduler of this lane's gather launch
+};
+
+// What the gather stage of one image plane needs once its source is ready (see VideoFrameTransform::prepareGather).
+struct GatherWork {
+  const DevicePlan* plan = nullptr;
+  t360::PlaneView view{};
+  bool staged = false;                       // TMA-describable: may run in the persistent (per-plane / per-frame) kernel
+  CUtensorMap maps[t360::kNumBoxClasses];
+  uint8_t* finalOut = nullptr;               // where the area resize (if any) delivers
+  int finalPitch = 0, imagePlane = 0;
+};
+
+// The tiles of all planes of a frame in one list (general, class 1, class 0; luma first inside each kind), rebuilt
+// when a map is regenerated.
+struct FrameJobList {
+  DeviceBuffer<StagedTile> tiles;
+  int numTiles = 0, numPlanes = 0;
+  unsigned long long generation = ~0ull;
+  DeviceBuffer<int> claimCounter;
 };
 
 constexpr int kPitchAlign = 256;
@@ -167,9 +188,12 @@ class VideoFrameTransform {
       for (PlaneLane& l : lanes_) {
         l.blurred.release();
         l.scaled.release();
+        l.claimCounter.release();
         if (l.main) cudaStreamDestroy(l.main);
         if (l.done) cudaEventDestroy(l.done);
       }
+      frameJobs_.tiles.release();
+      frameJobs_.claimCounter.release();
       if (frameFork_) cudaEventDestroy(frameFork_);
       if (stream_) cudaStreamDestroy(stream_);
     }
@@ -183,6 +207,7 @@ class VideoFrameTransform {
       ensureDevice();
       std::lock_guard<std::mutex> lock(mu_);
       plans_[planIndex] = upload(host);
+      ++planGeneration_;
       return true;
     } catch (const CudaFail& f) {
       std::printf("Could not generate map for plane %d. Error: CUDA %s (%s) in %s\n", planIndex,
@@ -275,21 +300,49 @@ class VideoFrameTransform {
       }
       ensureDevice();
       cudaStream_t s = stream ? stream : stream_;
-      if (numPlanes > 1) CU(cudaEventRecord(frameFork_, s));
-      bool ok = true;
-      for (int p = numPlanes - 1; p >= 0 && ok; --p) {  // small planes first: they fill in around the luma kernels
-        const int planIndex = p ? 1 : 0;
-        const DevicePlan* plan = findPlan(planIndex, p);
-        if (!plan) return false;
-        PlaneLane& lane = lanes_[p];
-        cudaStream_t ps = p ? lane.main : s;
-        if (p) CU(cudaStreamWaitEvent(ps, frameFork_, 0));
-        if (plan->transparent && planIndex) CU(cudaMemset2DAsync(dOut[p], outPitch[p], 128, outW[p], outH[p], ps));
-        ok = enqueue(*plan, dIn[p], dOut[p], inW[p], inH[p], inPitch[p], outW[p], outH[p], outPitch[p], ps, p, lane);
-        if (p) CU(cudaEventRecord(lane.done, ps));
+      const DevicePlan* plans[kPlaneLanes];
+      bool sideWork = false;  // does any chroma plane have work before its gather (low-pass, pre-fill)?
+      for (int p = 0; p < numPlanes; ++p) {
+        if (!(plans[p] = findPlan(p ? 1 : 0, p))) return false;
+        if (p) sideWork = sideWork || plans[p]->lowPass || plans[p]->transparent;
+      }
+      // Stage 1, planes side by side (chroma on its own lanes): everything before the gather.
+      const bool fork = numPlanes > 1 && sideWork;
+      if (fork) CU(cudaEventRecord(frameFork_, s));
+      GatherWork work[kPlaneLanes];
+      bool allStaged = true;
+      for (int p = numPlanes - 1; p >= 0; --p) {
+        cudaStream_t ps = (p && fork) ? lanes_[p].main : s;
+        if (p && fork) CU(cudaStreamWaitEvent(ps, frameFork_, 0));
+        if (plans[p]->transparent && p) CU(cudaMemset2DAsync(dOut[p], outPitch[p], 128, outW[p], outH[p], ps));
+        if (!prepareGather(*plans[p], dIn[p], dOut[p], inW[p], inH[p], inPitch[p], outW[p], outH[p], outPitch[p], ps, p, lanes_[p], work[p]))
+          return false;
+        allStaged = allStaged && work[p].staged;
+      }
+      if (allStaged && numPlanes > 1) {
+        // Stage 2: ONE persistent launch gathers every plane (reference vf_transform360.c:368-397 loops over them).
+        if (fork)
+          for (int p = 1; p < numPlanes; ++p) {
+            CU(cudaEventRecord(lanes_[p].done, lanes_[p].main));
+            CU(cudaStreamWaitEvent(s, lanes_[p].done, 0));
+          }
+        gatherFrame(work, numPlanes, s);
+        for (int p = 0; p < numPlanes; ++p) finishGather(work[p], s);
+        return true;
+      }
+      // some plane needs the general kernel (barrel layouts, nearest, unaligned planes): per-plane launches
+      if (numPlanes > 1 && !fork) CU(cudaEventRecord(frameFork_, s));
+      for (int p = numPlanes - 1; p >= 0; --p) {
+        cudaStream_t ps = p ? lanes_[p].main : s;
+        if (p && !fork) CU(cudaStreamWaitEvent(ps, frameFork_, 0));
+        if (work[p].plan->kernelSize) {
+          gatherPlane(work[p], lanes_[p], ps);
+          finishGather(work[p], ps);
+        }
+        if (p) CU(cudaEventRecord(lanes_[p].done, ps));
       }
       for (int p = 1; p < numPlanes; ++p) CU(cudaStreamWaitEvent(s, lanes_[p].done, 0));
-      return ok;
+      return true;
     } catch (const CudaFail& f) {
       std::printf("Could not transform the frame. Error: CUDA %s (%s) in %s\n", cudaGetErrorName(f.err), cudaGetErrorString(f.err), f.what);
       cudaGetLastError();
@@ -540,6 +593,7 @@ class VideoFrameTransform {
       d.gatherJobs.reserve(jobs.size());
       CU(cudaMemcpy(d.gatherJobs.ptr, jobs.data(), jobs.size() * sizeof(StagedTile), cudaMemcpyHostToDevice));
     }
+    d.hostJobs = std::move(jobs);
   }
 
   // Tiles of the plan, applied once (mono) or to both halves of a stereo frame (reference cpp:630-691), cut
@@ -682,9 +736,22 @@ class VideoFrameTransform {
     }
   }
 
-  // reference transformPlane (cpp:707-794): [low-pass] -> gather.  Device pointers, asynchronous.
+  // reference transformPlane (cpp:707-794): [low-pass] -> gather [-> area resize].  Device pointers, asynchronous.
   bool enqueue(const DevicePlan& plan, const uint8_t* dIn, uint8_t* dOut, int inW, int inH, int inPitch, int outW,
                int outH, int outPitch, cudaStream_t s, int imagePlaneIndex, PlaneLane& lane) {
+    GatherWork w;
+    if (!prepareGather(plan, dIn, dOut, inW, inH, inPitch, outW, outH, outPitch, s, imagePlaneIndex, lane, w)) return false;
+    if (plan.kernelSize == 0) return true;
+    gatherPlane(w, lane, s);
+    finishGather(w, s);
+    return true;
+  }
+
+  // Everything before the gather of one plane: argument checks, the render target, the low-pass stage.
+  bool prepareGather(const DevicePlan& plan, const uint8_t* dIn, uint8_t* dOut, int inW, int inH, int inPitch, int outW,
+                     int outH, int outPitch, cudaStream_t s, int imagePlaneIndex, PlaneLane& lane, GatherWork& w) {
+    w.plan = &plan;
+    w.imagePlane = imagePlaneIndex;
     if (plan.kernelSize == 0) {
       std::printf("Could not find interpolation algorithm for plane %d", imagePlaneIndex);  // reference cpp:780-784
       return true;
@@ -696,8 +763,8 @@ class VideoFrameTransform {
     }
     // reference cpp:735-737, 755-777: when the map was planned at a scaled size, render at that size into a plane
     // pre-filled with 0 (luma) / 128 (chroma), then cv::resize(INTER_AREA) down to the requested size
-    uint8_t* finalOut = dOut;
-    const int finalPitch = outPitch;
+    w.finalOut = dOut;
+    w.finalPitch = outPitch;
     if (plan.resizeNeeded) {
       if (!plan.resizeSupported) {
         std::printf("Could not transform the plane %d. Error: scale factors below 1 (INTER_AREA enlarging) are not supported\n",
@@ -721,26 +788,81 @@ class VideoFrameTransform {
       src = lane.blurred.ptr;
       srcPitch = bp;
     }
-    t360::GatherParams gp{src, inW, inH, srcPitch, dOut, outW, outH, outPitch, plan.samples.ptr, plan.samplesPitch,
-                          weights_[plan.kernelSize].ptr, plan.kernelSize, plan.transparent ? 1 : 0};
+    w.view = t360::PlaneView{src, dOut, plan.samples.ptr, inW, inH, srcPitch, outW, outH, outPitch, plan.samplesPitch, 0};
     // staged tiles need the plane the plan was made for (their windows were proven in-bounds for it) and a
     // TMA-describable layout (16-byte aligned base and pitch); otherwise every tile takes the general kernel
-    bool stage = plan.totalStaged() > 0 && inW == plan.inW && inH == plan.inH;
-    CUtensorMap maps[t360::kNumBoxClasses];
-    for (int c = 0; c < t360::kNumBoxClasses && stage; ++c)
-      stage = encodePlaneMap(&maps[c], src, inW, inH, srcPitch, plan.kernelSize, c);
-    if (stage) {
-      t360::StagedParams jobs{plan.gatherJobs.ptr, plan.numJobs};
-      CU(t360::launchGatherPlane(gp, jobs, maps, numSMs_, s));
+    w.staged = plan.totalStaged() > 0 && !plan.transparent && inW == plan.inW && inH == plan.inH;
+    for (int c = 0; c < t360::kNumBoxClasses && w.staged; ++c)
+      w.staged = encodePlaneMap(&w.maps[c], src, inW, inH, srcPitch, plan.kernelSize, c);
+    return true;
+  }
+
+  static void armScheduler(DeviceBuffer<int>& counter, cudaStream_t s) {
+    if (counter.ptr) return;  // zeroed once; every launch leaves it zeroed again
+    counter.reserve(2);
+    CU(cudaMemsetAsync(counter.ptr, 0, 2 * sizeof(int), s));
+  }
+
+  // The gather of one plane as its own launch.
+  void gatherPlane(const GatherWork& w, PlaneLane& lane, cudaStream_t s) {
+    const DevicePlan& plan = *w.plan;
+    if (w.staged) {
+      armScheduler(lane.claimCounter, s);
+      t360::FrameGatherParams fp{};
+      fp.plane[0] = w.view;
+      fp.weights = weights_[plan.kernelSize].ptr;
+      fp.kernelSize = plan.kernelSize;
+      fp.numPlanes = 1;
+      t360::StagedParams jobs{plan.gatherJobs.ptr, plan.numJobs, lane.claimCounter.ptr};
+      CU(t360::launchGatherFrame(fp, jobs, w.maps, numSMs_, s));
     } else {
+      const t360::PlaneView& v = w.view;
+      t360::GatherParams gp{v.src, v.srcW, v.srcH, v.srcPitch, v.dst, v.dstW, v.dstH, v.dstPitch, v.samples, v.samplesPitch,
+                            weights_[plan.kernelSize].ptr, plan.kernelSize, plan.transparent ? 1 : 0};
       CU(t360::launchGather(gp, numSMs_, s));
     }
-    if (plan.resizeNeeded) {
-      t360::AreaParams ap{dOut, finalOut, plan.mapW, plan.mapH, outPitch, plan.outW, plan.outH, finalPitch, plan.cellW, plan.cellH,
-                          plan.areaXTaps.ptr, plan.areaXFirst.ptr, plan.areaYTaps.ptr, plan.areaYFirst.ptr};
-      CU(t360::launchAreaResize(ap, s));
+  }
+
+  // The gathers of all planes of a frame as ONE launch (every plane staged).
+  void gatherFrame(const GatherWork* work, int numPlanes, cudaStream_t s) {
+    FrameJobList& f = frameJobs_;
+    if (f.generation != planGeneration_ || f.numPlanes != numPlanes) {
+      std::vector<StagedTile> merged;
+      for (int kind : {t360::kJobGeneral, 1, 0})
+        for (int p = 0; p < numPlanes; ++p)
+          for (StagedTile t : work[p].plan->hostJobs) {
+            if (((t.outY >> t360::kJobKindShift) & t360::kJobKindMask) != kind) continue;
+            t.outY |= p << t360::kJobPlaneShift;
+            merged.push_back(t);
+          }
+      CU(cudaStreamSynchronize(s));  // a previous frame may still be reading the old list
+      f.tiles.reserve(merged.size());
+      CU(cudaMemcpy(f.tiles.ptr, merged.data(), merged.size() * sizeof(StagedTile), cudaMemcpyHostToDevice));
+      f.numTiles = static_cast<int>(merged.size());
+      f.numPlanes = numPlanes;
+      f.generation = planGeneration_;
     }
-    return true;
+    armScheduler(f.claimCounter, s);
+    t360::FrameGatherParams fp{};
+    CUtensorMap maps[kPlaneLanes][t360::kNumBoxClasses];
+    for (int p = 0; p < numPlanes; ++p) {
+      fp.plane[p] = work[p].view;
+      for (int c = 0; c < t360::kNumBoxClasses; ++c) maps[p][c] = work[p].maps[c];
+    }
+    fp.weights = weights_[work[0].plan->kernelSize].ptr;
+    fp.kernelSize = work[0].plan->kernelSize;
+    fp.numPlanes = numPlanes;
+    t360::StagedParams jobs{f.tiles.ptr, f.numTiles, f.claimCounter.ptr};
+    CU(t360::launchGatherFrame(fp, jobs, maps, numSMs_, s));
+  }
+
+  // What follows the gather: the INTER_AREA down-scale when the map was rendered at a scaled size.
+  void finishGather(const GatherWork& w, cudaStream_t s) {
+    const DevicePlan& plan = *w.plan;
+    if (!plan.resizeNeeded) return;
+    t360::AreaParams ap{w.view.dst, w.finalOut, plan.mapW, plan.mapH, w.view.dstPitch, plan.outW, plan.outH, w.finalPitch,
+                        plan.cellW, plan.cellH, plan.areaXTaps.ptr, plan.areaXFirst.ptr, plan.areaYTaps.ptr, plan.areaYFirst.ptr};
+    CU(t360::launchAreaResize(ap, s));
   }
 
   FrameTransformContext ctx_;
@@ -753,6 +875,8 @@ class VideoFrameTransform {
   std::vector<HostRange> hostRanges_;
   bool pinHostPlanes_ = false;
   PlaneLane lanes_[kPlaneLanes];
+  FrameJobList frameJobs_;
+  unsigned long long planGeneration_ = 0;
   cudaEvent_t frameFork_ = nullptr;
   cudaStream_t stream_ = nullptr;
   int device_ = 0, numSMs_ = 0;
