@@ -9,13 +9,13 @@ workload = BASELINE.json configs[1] ("cfg2": MONO 7680x3840 equirect -> CUBEMAP_
 bicubic, low-pass off).  Mpx/s counts INPUT-plane pixels consumed.
 
 Legs (one JSON line on rank 0):
-  value         frames resident in HBM, T360B200_transformFramePlaneAsync per plane, CUDA events on the launch
+  value         frames resident in HBM, one T360B200_transformFrameAsync per frame, CUDA events on the launch
                 stream, barrier + synchronize on both sides, max over ranks.  Inputs rotate through a ring larger
                 than L2 so every step reads its frame from HBM.
   e2e           same metric through the reference's own C-ABI (VideoFrameTransform_transformFramePlane) with
                 pinned HOST planes: H2D of the inputs and D2H of the outputs are inside the timed region.
-  roofline      luma gather kernel: algorithmic bytes (inW*inH + outW*outH) / its CUDA-event
-                duration inside the timed region / measured HBM peak (MEASURED_PEAKS.json).
+  roofline      the frame gather kernel (all three planes in one launch): algorithmic bytes (input + output
+                plane bytes) / its CUDA-event duration / measured HBM peak (MEASURED_PEAKS.json).
   cpu_baseline  the reference's own CPU path (oracle/_ref: unmodified reference sources driving cv2) on this
                 box's host cores, bounded sample (N=1, rank 0 only).
   --impl reference   only that CPU path, as its own JSON line.
@@ -263,8 +263,8 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
-    # one prebuilt whole-frame call per (input ring slot, output slot): T360B200_transformFrameAsync runs the luma
-    # plane on `stream` and the two chroma planes concurrently on the transform's internal lanes
+    # one prebuilt whole-frame call per (input ring slot, output slot): T360B200_transformFrameAsync runs the low-pass
+    # of the three planes side by side (chroma on the transform's internal lanes) and gathers them in one launch
     frame_calls = [[ft.frame_call(in_args[i], out_args[o]) for o in range(2)] for i in range(ring)]
 
     def step_device(i):
@@ -292,17 +292,29 @@ def main():
     ms_total_max = float(t_max.item())
     value = in_px * K * world / (ms_total_max * 1e-3) / 1e6
 
-    # ---- kernel leg for the roofline: the luma plane alone, each launch bracketed by CUDA events on its stream -----
-    Kl = min(K, 200)
-    luma_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(Kl)]
-    for i in range(Kl):
-        fin, fout = in_args[i % ring], out_args[i % 2]
-        luma_ev[i][0].record(tstream)
-        if not ft.vft.transform_plane_async(fin[0][0], fout[0][0], liw, lih, fin[0][1], low, loh, fout[0][1], 0, stream):
-            raise RuntimeError("luma plane failed")
-        luma_ev[i][1].record(tstream)
+    # ---- kernel leg for the roofline: the dominant kernel of the step is the persistent gather that takes the tiles
+    # of all three planes of a frame in ONE launch.  Each launch is bracketed by CUDA events on its stream.  With the
+    # low-pass enabled a frame call also launches the blur kernels, so the gather is timed through a second transform
+    # with the same geometry and the low-pass switched off (same tiles, same records, same kernel).
+    ft_gather = ft
+    if cfg["ov"].get("enable_low_pass_filter"):
+        ctx_g = t360.make_context(**dict(cfg["ov"], enable_low_pass_filter=0))
+        ft_gather = FrameTransformer(ctx_g, spec)
+    gather_calls = [[ft_gather.frame_call(in_args[i], out_args[o]) for o in range(2)] for i in range(ring)]
+    for i in range(3):
+        gather_calls[i % ring][i % 2](stream)
     barrier()
-    luma_ms = [a.elapsed_time(b) for a, b in luma_ev]
+    Kl = min(K, 200)
+    gl0 = t360.kernel_launch_count()
+    gather_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(Kl)]
+    for i in range(Kl):
+        gather_ev[i][0].record(tstream)
+        if not gather_calls[i % ring][i % 2](stream):
+            raise RuntimeError("frame gather failed")
+        gather_ev[i][1].record(tstream)
+    barrier()
+    gather_launches_per_call = (t360.kernel_launch_count() - gl0) / Kl
+    gather_ms = [a.elapsed_time(b) for a, b in gather_ev]
 
     # ---- end to end through the reference-facing C-ABI with pinned host planes ------------------------------------
     e2e = None
@@ -353,24 +365,27 @@ def main():
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel (luma gather) --------------------------------------------------------------
+    # ---- roofline of the dominant kernel (frame gather) -------------------------------------------------------------
     peak, peak_src = measured_hbm_peak()
-    luma_bytes = liw * lih + low * loh
-    luma_avg_ms = statistics.mean(luma_ms)
-    achieved = luma_bytes / (luma_avg_ms * 1e-3) / 1e9
+    gather_bytes = in_px + out_px  # every input byte read once, every output byte written once
+    gather_avg_ms = statistics.mean(gather_ms)
+    achieved = gather_bytes / (gather_avg_ms * 1e-3) / 1e9
     traffic = None
     tp = ROOT / "profiles" / "traffic.json"
     if tp.exists():
         try:
-            traffic = json.loads(tp.read_text()).get(args.config, {}).get("luma_gather_dram_bytes_per_launch")
+            traffic = json.loads(tp.read_text()).get(args.config, {}).get("frame_gather_dram_bytes_per_launch")
         except Exception:
             traffic = None
-    roofline = {"bound": "hbm", "kernel": "gatherKernel (luma plane)" if not cfg["ov"].get("enable_low_pass_filter") else "blurTileKernel + gatherKernel (luma plane)",
+    ksize = {1: 2, 2: 4, 4: 8}.get(cfg["ov"]["interpolation_alg"], 0)
+    roofline = {"bound": "hbm", "kernel": f"gatherFrameKernel<{ksize}> (Y+U+V tiles of one frame, one persistent launch)",
                 "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                "traffic": traffic, "algorithmic_bytes_per_launch": luma_bytes, "avg_launch_ms": round(luma_avg_ms, 5),
-                "median_launch_ms": round(statistics.median(luma_ms), 5),
-                "read_only_frac": round(liw * lih / (luma_avg_ms * 1e-3) / 1e9 / peak, 4), "peak_source": peak_src,
-                "timing": f"{len(luma_ms)} luma-plane launches, each bracketed by CUDA events on the launch stream, inputs from the >L2 ring"}
+                "traffic": traffic, "algorithmic_bytes_per_launch": gather_bytes, "avg_launch_ms": round(gather_avg_ms, 5),
+                "median_launch_ms": round(statistics.median(gather_ms), 5),
+                "share_of_step": round(gather_avg_ms / (ms_total_max / K), 3),
+                "launches_per_timed_call": gather_launches_per_call,
+                "read_only_frac": round(in_px / (gather_avg_ms * 1e-3) / 1e9 / peak, 4), "peak_source": peak_src,
+                "timing": f"{len(gather_ms)} launches, each bracketed by CUDA events on the launch stream, inputs from the >L2 ring"}
 
     cpu_baseline = None
     if world == 1 and not args.skip_cpu_baseline:

@@ -484,6 +484,11 @@ gatherFrameKernel(const __grid_constant__ FrameGatherParams p, StagedParams jobs
   uint64_t* bars = reinterpret_cast<uint64_t*>(stage0 + 2 * kStage);
   constexpr uint32_t kBox0 = stageBoxW(K, 0) * stageBoxH(K, 0), kBox1 = stageBoxW(K, 1) * stageBoxH(K, 1);
 
+  // Programmatic dependent launch: the next launch on the stream (the next frame's gather) may place its CTAs as soon
+  // as ours retire, and run its prologue -- which touches only constant data: weights, job list, sampling records --
+  // under our tail.  Everything an earlier kernel may have written (the source planes, the scheduler counters) is
+  // only touched after griddepcontrol.wait below.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (threadIdx.x == 0) {
     mbarInit(&bars[0], 1);
     mbarInit(&bars[1], 1);
@@ -528,6 +533,7 @@ gatherFrameKernel(const __grid_constant__ FrameGatherParams p, StagedParams jobs
   // q0 / q1: class-0 / class-1 tiles this CTA has consumed; issued0: class-0 boxes it has requested.  A class-0 tile
   // with sequence number q lives in stage q & 1 and completes phase (q >> 1) & 1 of that stage's barrier.
   uint32_t q0 = 0, q1 = 0, issued0 = 0;
+  asm volatile("griddepcontrol.wait;" ::: "memory");  // earlier kernels on the stream are complete and visible from here on
   auto requestClass0 = [&](const StagedTile& t) {  // thread 0 only
     const uint32_t st = issued0 & 1;
     mbarExpectTx(&bars[st], kBox0);
@@ -950,9 +956,19 @@ cudaError_t launchFrameK(const FrameGatherParams& p, const StagedParams& jobs, c
   cudaError_t err = prepare<gatherFrameKernel<K>>(cfg, threads, smemBytes);
   if (err != cudaSuccess) return err;
   const int grid = std::min(numSMs * cfg.perSM, jobs.numTiles);  // persistent: whole waves of CTAs
-  gatherFrameKernel<K><<<grid, threads, smemBytes, stream>>>(p, jobs, maps);
+  cudaLaunchConfig_t lc{};
+  lc.gridDim = dim3(grid);
+  lc.blockDim = dim3(threads);
+  lc.dynamicSmemBytes = smemBytes;
+  lc.stream = stream;
+  cudaLaunchAttribute attr{};
+  attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;  // see griddepcontrol.* in the kernel
+  attr.val.programmaticStreamSerializationAllowed = 1;
+  lc.attrs = &attr;
+  lc.numAttrs = 1;
+  err = cudaLaunchKernelEx(&lc, gatherFrameKernel<K>, p, jobs, maps);
   gLaunches.fetch_add(1, std::memory_order_relaxed);
-  return cudaGetLastError();
+  return err;
 }
 
 }  // namespace
