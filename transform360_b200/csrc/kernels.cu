@@ -325,17 +325,23 @@ __device__ __forceinline__ int gatherPixel(const SrcView& s, const unsigned char
       return den > 0 ? (2 * num + den) / (2 * den) : -1;
     }
   }
+  // border columns once, then every load of a row (of the whole window for K <= 4) before the first use: a warp that
+  // straddles the +-180 degree seam waits for its few border lanes, so their latency is the tile's latency
   int acc = 0;
-#pragma unroll 1
+  int xs[K];
+#pragma unroll
+  for (int c = 0; c < K; ++c) xs[c] = TRANSPARENT ? reflect101(col0 + c, s.w) : wrapIndex(col0 + c, s.w);
+#pragma unroll(K <= 4 ? K : 1)
   for (int r = 0; r < K; ++r) {
     const int yy = TRANSPARENT ? reflect101(row0 + r, s.h) : wrapIndex(row0 + r, s.h);
     const uint8_t* rowp = s.bytes + (size_t)yy * s.pitch;
-#pragma unroll 1
+    int px[K];
+#pragma unroll
+    for (int c = 0; c < K; ++c) px[c] = __ldg(rowp + xs[c]);
+#pragma unroll
     for (int c = 0; c < K; ++c) {
-      const int xx = TRANSPARENT ? reflect101(col0 + c, s.w) : wrapIndex(col0 + c, s.w);
       const int e = r * K + c;  // element (r, c) lives in vector e / 8, lane e % 8 of the transposed table
-      const int w = K == 2 ? wt[e] : wt[(e >> 3) * 1024 * 8 + (e & 7)];
-      acc += w * (int)__ldg(rowp + xx);
+      acc += (K == 2 ? wt[e] : wt[(e >> 3) * 1024 * 8 + (e & 7)]) * px[c];
     }
   }
   return roundToByte(acc);
