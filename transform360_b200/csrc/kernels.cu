@@ -528,10 +528,14 @@ gatherFrameKernel(const __grid_constant__ FrameGatherParams p, StagedParams jobs
       rec[j] = (i < jobs.numTiles && slot < pv.dstW && y0 + j < pv.dstH) ? loadPlan(pv.samples + (size_t)(y0 + j) * pv.samplesPitch + slot)
                                                                           : make_int2(0, 0);
   };
-  // Dynamic tile scheduling: the first three jobs of a CTA are static (blockIdx.x + k * gridDim.x), every further one
-  // is claimed from a global counter by thread 0 one iteration before its header is needed and handed to the other
-  // threads through a double-buffered shared slot across the end-of-job barrier.
+  // Dynamic tile scheduling: the first four jobs of a CTA are static (blockIdx.x + k * gridDim.x), every further one is
+  // claimed from a global counter by thread 0 and handed to the other threads through a double-buffered shared slot
+  // across the end-of-job barrier.  The value the atomic returns is not touched in the iteration that issues it -- a
+  // warp executes in order and would sit out the round trip while the rest of the CTA waits for it at the barrier --
+  // but one iteration later (in an asm statement, so that the compiler cannot hoist the use).
   int* claimSlot = reinterpret_cast<int*>(bars + 3);
+  const int claimBase = 4 * gridDim.x;
+  int claimedRaw = (int)blockIdx.x - (int)gridDim.x;  // thread 0; claimBase + claimedRaw = the CTA's fourth static job
   int i0 = blockIdx.x, i1 = i0 + gridDim.x, i2 = i1 + gridDim.x;
   StagedTile tile = loadHeader(i0), tileNext = loadHeader(i1);
   int2 rec[kRowsPerThread];
@@ -547,7 +551,12 @@ gatherFrameKernel(const __grid_constant__ FrameGatherParams p, StagedParams jobs
   };
   for (uint32_t it = 0; i0 < jobs.numTiles; ++it) {
     const int next = i1;
-    if (threadIdx.x == 0) claimSlot[it & 1] = 3 * (int)gridDim.x + atomicAdd(jobs.claimCounter, 1);
+    if (threadIdx.x == 0) {
+      int claimed;
+      asm volatile("add.s32 %0, %1, %2;" : "=r"(claimed) : "r"(claimedRaw), "r"(claimBase));
+      claimSlot[it & 1] = claimed;
+      claimedRaw = atomicAdd(jobs.claimCounter, 1);
+    }
     const StagedTile tileAfterNext = loadHeader(i2);
     int2 recNext[kRowsPerThread];
     loadRecords(next, tileNext, recNext);
