@@ -509,6 +509,20 @@ gatherFrameKernel(const __grid_constant__ FrameGatherParams p, StagedParams jobs
   // order: a header load followed by the record loads that need its fields would stall the whole tile on the header):
   //   iteration n:  issue header(n+2) | issue records(n+1) from header(n+1), already in registers | compute tile n
   auto loadHeader = [&](int i) { return i < jobs.numTiles ? jobs.tiles[i] : StagedTile{0, 0, 0, 0}; };
+  // The header fetched two jobs ahead must not be waited for where it is issued.  The compiler keeps warp-uniform
+  // values in uniform registers and converts a loaded header the moment it arrives, which parked every warp on this
+  // load at the top of every job (10 % of all stall samples); so the load is opaque (asm: four ordinary registers), and
+  // the header becomes uniform -- through a warp reduction whose result the compiler knows to be uniform -- only at the
+  // end of the job, when it has long arrived.  An index past the list reads its last entry; validity is tracked by
+  // the index itself.
+  auto issueHeaderLoad = [&](int i, int (&raw)[4]) {
+    const StagedTile* src = jobs.tiles + min(i, jobs.numTiles - 1);
+    asm volatile("ld.global.nc.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(raw[0]), "=r"(raw[1]), "=r"(raw[2]), "=r"(raw[3]) : "l"(src));
+  };
+  auto uniformHeader = [&](const int (&raw)[4]) {
+    return StagedTile{(int)__reduce_or_sync(0xffffffffu, (unsigned)raw[0]), (int)__reduce_or_sync(0xffffffffu, (unsigned)raw[1]),
+                      (int)__reduce_or_sync(0xffffffffu, (unsigned)raw[2]), (int)__reduce_or_sync(0xffffffffu, (unsigned)raw[3])};
+  };
   // The plane of a tile, field by field through selects on kernel-parameter operands: an indexed load from the
   // parameter bank instead would put its latency in front of every tile's record loads (measured: +5 % on a plane).
   static_assert(kMaxFramePlanes == 3, "planeOf selects among three planes");
@@ -557,7 +571,8 @@ gatherFrameKernel(const __grid_constant__ FrameGatherParams p, StagedParams jobs
       claimSlot[it & 1] = claimed;
       claimedRaw = atomicAdd(jobs.claimCounter, 1);
     }
-    const StagedTile tileAfterNext = loadHeader(i2);
+    int headerAfterNext[4];
+    issueHeaderLoad(i2, headerAfterNext);
     int2 recNext[kRowsPerThread];
     loadRecords(next, tileNext, recNext);
     const int kind = (tile.outY >> kJobKindShift) & kJobKindMask, outY = tile.outY & kJobRowMask;
@@ -607,9 +622,13 @@ gatherFrameKernel(const __grid_constant__ FrameGatherParams p, StagedParams jobs
     __syncthreads();  // everyone is done with this job's stage before it is refilled (and sees the claimed index)
     i0 = i1; i1 = i2; i2 = claimSlot[it & 1];
     tile = tileNext;
-    tileNext = tileAfterNext;
+    tileNext = uniformHeader(headerAfterNext);
+    // (asm: the copies stay here, ahead of the next job's loads, whose scoreboards they would otherwise share)
 #pragma unroll
-    for (int j = 0; j < kRowsPerThread; ++j) rec[j] = recNext[j];
+    for (int j = 0; j < kRowsPerThread; ++j) {
+      asm volatile("mov.b32 %0, %1;" : "=r"(rec[j].x) : "r"(recNext[j].x));
+      asm volatile("mov.b32 %0, %1;" : "=r"(rec[j].y) : "r"(recNext[j].y));
+    }
   }
   // the CTA that finishes last re-arms the scheduler for the next launch (claimCounter[0] = claims, [1] = finished CTAs)
   if (threadIdx.x == 0 && atomicAdd(jobs.claimCounter + 1, 1) == (int)gridDim.x - 1) {
