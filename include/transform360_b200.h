@@ -44,9 +44,11 @@ int T360B200_transformFramePlaneAsync(VideoFrameTransform* transform, const uint
                                       int outputWidth, int outputHeight, int outputPitch,
                                       int transformMatPlaneIndex, void* cudaStream);
 /* All planes of one frame in one call, device to device, asynchronous on `cudaStream`: plane 0 uses plan index 0,
- * planes 1 and 2 plan index 1 (the reference filter's convention, vf_transform360.c:372) and run concurrently with
- * plane 0 on internal streams; `cudaStream` observes the completion of all of them.  Arrays have numPlanes (1..3)
- * entries: device pointers, per-plane widths / heights / pitches in bytes. */
+ * planes 1 and 2 plan index 1 (the reference filter's convention, vf_transform360.c:372).  The low-pass stages of the
+ * planes run side by side (chroma on internal streams); one gather launch then takes the tiles of every plane;
+ * `cudaStream` observes the completion of all of it.  Arrays have numPlanes (1..3) entries: device pointers, per-plane
+ * widths / heights / pitches in bytes.  Not re-entrant per transform (scratch planes and the tile scheduler are
+ * per transform): enqueue the frames of one transform from one thread. */
 int T360B200_transformFrameAsync(VideoFrameTransform* transform, int numPlanes, const uint8_t* const* deviceInputs,
                                  uint8_t* const* deviceOutputs, const int* inputWidths, const int* inputHeights,
                                  const int* inputPitches, const int* outputWidths, const int* outputHeights,
