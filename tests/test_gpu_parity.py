@@ -248,6 +248,99 @@ def test_whole_frame_entry_point_matches_per_plane_calls(name, torch_cuda):
     ft.close()
 
 
+def _pitched(torch, arr, pitch):
+    """Device copy of a 2-D uint8 array with the given row pitch (bytes); returns (base tensor, view)."""
+    h, w = arr.shape
+    base = torch.zeros((h, pitch), dtype=torch.uint8, device="cuda")
+    base[:, :w] = torch.from_numpy(np.ascontiguousarray(arr)).cuda()
+    return base
+
+
+@pytest.mark.parametrize("name,planes", [("cube_cubic", 3), ("cube_linear", 3), ("cube_lanczos", 3), ("cube_cubic", 2), ("cube_cubic", 1),
+                                         ("rotated", 3), ("cube_to_equirect", 3), ("scaled_2x2", 3), ("scaled_fractional_lp", 3),
+                                         ("barrel", 3), ("cube_nearest", 3), ("lr_stereo", 3)])
+def test_frame_entry_point_every_path(name, planes, torch_cuda):
+    """The whole-frame entry point against the oracle, plane by plane, with TMA-describable planes (256-byte pitch):
+    staged plans gather all planes in ONE launch; barrel / nearest plans take the per-plane general kernels; scaled
+    plans resize after the shared gather.  Frames are enqueued back to back (programmatic dependent launch, self
+    re-arming tile scheduler) into distinct outputs and every one of them is checked."""
+    torch = torch_cuda
+    from transform360_b200.stream import FrameTransformer, StreamSpec
+    case = SMALL[name]
+    ctx, octx = _ctxs(case)
+    spec = StreamSpec(case["inp"][0], case["inp"][1], case["out"][0], case["out"][1])
+    ft = FrameTransformer(ctx, spec)
+    frames = 6
+    pitch = lambda w: (w + 255) // 256 * 256
+    fill = _prefill(ctx)
+    plans = {}
+    d_in, d_out, want = [], [], []
+    for f in range(frames):
+        ins, outs, exp = [], [], []
+        for p in range(planes):
+            iw, ih, ow, oh, idx = spec.plane_dims(p)
+            if idx not in plans:
+                plans[idx] = co.OraclePlan(octx, iw, ih, ow, oh)
+            src = co.noise_plane(iw, ih, plane=p, frame=f)
+            ins.append(_pitched(torch, src, pitch(iw)))
+            outs.append(torch.full((oh, pitch(ow)), fill, dtype=torch.uint8, device="cuda"))
+            exp.append(co.transform_plane(octx, plans[idx], src, ow, oh, map_index=idx, prefill=fill))
+        d_in.append(ins); d_out.append(outs); want.append(exp)
+    st = torch.cuda.Stream()
+    torch.cuda.synchronize()
+    n0 = t360.kernel_launch_count()
+    dims = [spec.plane_dims(p)[:4] for p in range(planes)]
+    for f in range(frames):
+        call = ft.vft.make_frame_call([(t.data_ptr(), t.stride(0)) for t in d_in[f]], [(t.data_ptr(), t.stride(0)) for t in d_out[f]], dims)
+        assert call(st.cuda_stream), "T360B200_transformFrameAsync failed"
+    st.synchronize()
+    launches = (t360.kernel_launch_count() - n0) / frames
+    staged = ctx.interpolation_alg != t360.NEAREST and not fill and not ctx.enable_low_pass_filter \
+        and ctx.width_scale_factor == 1 and ctx.height_scale_factor == 1
+    staged = staged and all(ft.vft.plan_tile_counts(i)[0] > 0 for i in ((0, 1) if planes > 1 else (0,)))
+    if staged and planes > 1:
+        assert launches == 1, f"{launches} launches per frame: the planes were not gathered in one launch"
+    for f in range(frames):
+        for p in range(planes):
+            ow = spec.plane_dims(p)[2]
+            got = d_out[f][p][:, :ow].cpu().numpy()
+            assert np.array_equal(got, want[f][p]), f"frame {f} plane {p}: {(got != want[f][p]).sum()} px differ"
+            if d_out[f][p].shape[1] > ow:
+                pad = d_out[f][p][:, ow:]
+                assert int(pad.min().item()) == fill and int(pad.max().item()) == fill, "row padding was written"
+    ft.close()
+
+
+def test_frame_entry_point_survives_map_regeneration(torch_cuda):
+    """generateMapForPlane again (other parameters) between frames: the merged job list is rebuilt."""
+    torch = torch_cuda
+    from transform360_b200.stream import FrameTransformer, StreamSpec
+    case = SMALL["cube_cubic"]
+    spec = StreamSpec(case["inp"][0], case["inp"][1], case["out"][0], case["out"][1])
+    ctx, octx = _ctxs(case)
+    ft = FrameTransformer(ctx, spec)
+    pitch = lambda w: (w + 255) // 256 * 256
+    srcs = [co.noise_plane(*spec.plane_dims(p)[:2], plane=p, frame=11) for p in range(3)]
+    d_in = [_pitched(torch, srcs[p], pitch(spec.plane_dims(p)[0])) for p in range(3)]
+    st = torch.cuda.Stream()
+    for out_size in (case["out"], (96, 64), case["out"]):
+        spec2 = StreamSpec(case["inp"][0], case["inp"][1], out_size[0], out_size[1])
+        for idx in (0, 1):
+            iw, ih, ow, oh, _ = spec2.plane_dims(idx)
+            assert ft.vft.generateMapForPlane(iw, ih, ow, oh, idx)
+        d_out = [torch.zeros((spec2.plane_dims(p)[3], pitch(spec2.plane_dims(p)[2])), dtype=torch.uint8, device="cuda") for p in range(3)]
+        dims = [spec2.plane_dims(p)[:4] for p in range(3)]
+        call = ft.vft.make_frame_call([(t.data_ptr(), t.stride(0)) for t in d_in], [(t.data_ptr(), t.stride(0)) for t in d_out], dims)
+        for _ in range(2):
+            assert call(st.cuda_stream)
+        st.synchronize()
+        for p in range(3):
+            iw, ih, ow, oh, idx = spec2.plane_dims(p)
+            exp = co.transform_plane(octx, co.OraclePlan(octx, iw, ih, ow, oh), srcs[p], ow, oh, map_index=idx)
+            assert np.array_equal(d_out[p][:, :ow].cpu().numpy(), exp), f"out {out_size} plane {p}"
+    ft.close()
+
+
 def _rank_worker(rank, world, port, q):
     import os
     import torch
