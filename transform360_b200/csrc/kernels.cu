@@ -244,17 +244,8 @@ __device__ __forceinline__ int foldRows(const RowBytes<K> (&W)[K], const unsigne
   return acc;
 }
 
-// true when the 4 records of a thread can share their window columns: same first column, row steps of 1 or 2
-__device__ __forceinline__ bool columnShareable(const int2 (&rec)[4]) {
-  bool ok = true;
-#pragma unroll
-  for (int j = 1; j < 4; ++j) {
-    const int d = (rec[j].y >> 10) - (rec[j - 1].y >> 10);
-    ok = ok && (d == 1 || d == 2) && recordCol0(rec[j].x) == recordCol0(rec[0].x);
-  }
-  return ok;
-}
-
+// (whether the 4 records of every thread of a warp can share their window columns -- same first column, row steps
+// of 1 or 2 -- is decided by the host per warp and tile: StagedTile::shareMask)
 template <int K, int PITCH>
 __device__ __forceinline__ void gatherColumnShared(const unsigned char* stage, int boxX, int boxY, const int2 (&rec)[4],
                                                    const unsigned char* wsmem, int (&acc)[4]) {
@@ -369,7 +360,7 @@ gatherKernel(GatherParams p, int tilesX, int numTiles) {
     int2 rec[kRowsPerThread];
 #pragma unroll
     for (int j = 0; j < kRowsPerThread; ++j)
-      rec[j] = y0 + j < p.dstH ? loadPlan(p.samples + (size_t)(y0 + j) * p.samplesPitch + segX + lane) : make_int2(0, 0);
+      rec[j] = loadPlan(p.samples + ((size_t)tile * gatherTileH(K) + warp * kRowsPerThread + j) * kGatherTileW + lane);
 #pragma unroll
     for (int j = 0; j < kRowsPerThread; ++j) {
       if (y0 + j >= p.dstH) break;
@@ -390,7 +381,7 @@ __global__ void __launch_bounds__(256, 4) nearestKernel(GatherParams p, int tile
 #pragma unroll
     for (int j = 0; j < kRowsPerThread; ++j) {
       if (y0 + j >= p.dstH) break;
-      const int2 rec = loadPlan(p.samples + (size_t)(y0 + j) * p.samplesPitch + segX + lane);
+      const int2 rec = loadPlan(p.samples + ((size_t)tile * gatherTileH(1) + warp * kRowsPerThread + j) * kGatherTileW + lane);
       const int x = segX + recordColumn(rec.x);
       int sx = recordCol0(rec.x), sy = rec.y >> 10;
       const bool inside = (unsigned)sx < (unsigned)p.srcW && (unsigned)sy < (unsigned)p.srcH;
@@ -444,15 +435,11 @@ struct FrameTensorMaps {
 
 template <int K, int PITCH>
 __device__ __forceinline__ void computeStagedTile(const PlaneView& p, const unsigned char* stage, int outX, int outY, int boxX,
-                                                  int boxY, const int2 (&rec)[kRowsPerThread], const unsigned char* wsmem, int lane,
-                                                  int warp) {
+                                                  int boxY, bool shared, const int2 (&rec)[kRowsPerThread], const unsigned char* wsmem,
+                                                  int lane, int warp) {
   const int y0 = outY + warp * kRowsPerThread;
   const bool active = outX + lane < p.dstW;
-  bool shared = false;
-  if constexpr (K >= 4) {
-    // warp-uniform choice: every lane's 4 pixels share their columns (inactive lanes do not veto); needs all 4 rows
-    shared = y0 + kRowsPerThread <= p.dstH && __all_sync(0xffffffffu, !active || columnShareable(rec));
-  }
+  // `shared` (warp-uniform, from the tile header): every active lane's 4 pixels share their columns, all 4 rows exist
   uint8_t* const dst = p.dst;
   const int dstPitch = p.dstPitch;
   if (shared) {
@@ -531,16 +518,16 @@ gatherFrameKernel(const __grid_constant__ FrameGatherParams p, StagedParams jobs
     const PlaneView &a = p.plane[0], &b = p.plane[1], &c = p.plane[2];
 #define T360_PICK(f) (pl == 0 ? a.f : (pl == 1 ? b.f : c.f))
     return PlaneView{T360_PICK(src), T360_PICK(dst), T360_PICK(samples), T360_PICK(srcW), T360_PICK(srcH), T360_PICK(srcPitch),
-                     T360_PICK(dstW), T360_PICK(dstH), T360_PICK(dstPitch), T360_PICK(samplesPitch), 0};
+                     T360_PICK(dstW), T360_PICK(dstH), T360_PICK(dstPitch), T360_PICK(tilesPerRow), 0};
 #undef T360_PICK
   };
   auto loadRecords = [&](int i, const StagedTile& t, int2 (&rec)[kRowsPerThread]) {
     const PlaneView pv = planeOf(t);
-    const int y0 = (t.outY & kJobRowMask) + warp * kRowsPerThread, slot = t.outX + lane;  // records are in lane order
+    // tile-major records: one base address per warp and tile, the four rows at immediate offsets, no bounds checks
+    const int tileIndex = ((t.outY & kJobRowMask) / gatherTileH(K)) * pv.tilesPerRow + t.outX / kGatherTileW;
+    const int2* base = pv.samples + ((size_t)tileIndex * gatherTileH(K) + warp * kRowsPerThread) * kGatherTileW + lane;
 #pragma unroll
-    for (int j = 0; j < kRowsPerThread; ++j)
-      rec[j] = (i < jobs.numTiles && slot < pv.dstW && y0 + j < pv.dstH) ? loadPlan(pv.samples + (size_t)(y0 + j) * pv.samplesPitch + slot)
-                                                                          : make_int2(0, 0);
+    for (int j = 0; j < kRowsPerThread; ++j) rec[j] = i < jobs.numTiles ? loadPlan(base + j * kGatherTileW) : make_int2(0, 0);
   };
   // Dynamic tile scheduling: the first four jobs of a CTA are static (blockIdx.x + k * gridDim.x), every further one is
   // claimed from a global counter by thread 0 and handed to the other threads through a double-buffered shared slot
@@ -561,7 +548,7 @@ gatherFrameKernel(const __grid_constant__ FrameGatherParams p, StagedParams jobs
   auto requestClass0 = [&](const StagedTile& t) {  // thread 0 only
     const uint32_t st = issued0 & 1;
     mbarExpectTx(&bars[st], kBox0);
-    tmaLoadBox(stage0 + st * kStage, &maps.map[t.outY >> kJobPlaneShift][0], t.boxX, t.boxY, &bars[st]);
+    tmaLoadBox(stage0 + st * kStage, &maps.map[t.outY >> kJobPlaneShift][0], t.boxXY & 0xffff, t.boxXY >> 16, &bars[st]);
   };
   for (uint32_t it = 0; i0 < jobs.numTiles; ++it) {
     const int next = i1;
@@ -589,15 +576,17 @@ gatherFrameKernel(const __grid_constant__ FrameGatherParams p, StagedParams jobs
       }
       const uint32_t st = q0 & 1;
       mbarWait(&bars[st], (q0 >> 1) & 1);
-      computeStagedTile<K, stageBoxW(K, 0)>(pv, stage0 + st * kStage, tile.outX, outY, tile.boxX, tile.boxY, rec, wsmem, lane, warp);
+      computeStagedTile<K, stageBoxW(K, 0)>(pv, stage0 + st * kStage, tile.outX, outY, tile.boxXY & 0xffff, tile.boxXY >> 16,
+                                            K >= 4 && ((tile.shareMask >> warp) & 1), rec, wsmem, lane, warp);
       ++q0;
     } else if (kind == 1) {
       if (threadIdx.x == 0) {  // no class-0 box is in flight here: the larger box may span both stage buffers
         mbarExpectTx(&bars[2], kBox1);
-        tmaLoadBox(stage0, &maps.map[tile.outY >> kJobPlaneShift][1], tile.boxX, tile.boxY, &bars[2]);
+        tmaLoadBox(stage0, &maps.map[tile.outY >> kJobPlaneShift][1], tile.boxXY & 0xffff, tile.boxXY >> 16, &bars[2]);
       }
       mbarWait(&bars[2], q1 & 1);
-      computeStagedTile<K, stageBoxW(K, 1)>(pv, stage0, tile.outX, outY, tile.boxX, tile.boxY, rec, wsmem, lane, warp);
+      computeStagedTile<K, stageBoxW(K, 1)>(pv, stage0, tile.outX, outY, tile.boxXY & 0xffff, tile.boxXY >> 16,
+                                            K >= 4 && ((tile.shareMask >> warp) & 1), rec, wsmem, lane, warp);
       ++q1;
     } else {
       if (nextIsClass0 && issued0 == q0) {  // both stages are idle during a general tile: start the next box now

@@ -13,8 +13,8 @@ struct GatherParams {
   int srcW, srcH, srcPitch;
   uint8_t* dst;
   int dstW, dstH, dstPitch;
-  const int2* samples;  // [dstH][samplesPitch]: {col0, (row0 << 10) | phase}
-  int samplesPitch;     // elements per row, multiple of 4
+  const int2* samples;  // sampling records {col0, (row0 << 10) | phase}, tile-major (see "sampling records" below)
+  int tilesPerRow;      // 32-column tiles per row of tiles
   const int16_t* weights;  // device copy of the [1024][k][k] table (nullptr for nearest)
   int kernelSize;          // 1, 2, 4, 8
   int transparent;         // BORDER_TRANSPARENT (barrel layouts) instead of BORDER_WRAP
@@ -23,7 +23,9 @@ struct GatherParams {
 // One tile of the TMA-staged gather: a gatherTileW x gatherTileH block of output pixels whose whole source
 // window fits the fixed staging box placed at (boxX, boxY) of the source plane (boxX % 16 == 0).
 struct StagedTile {
-  int outX, outY, boxX, boxY;  // outY carries the job kind (kJobKindShift) and the image plane (kJobPlaneShift)
+  int outX, outY;  // outY carries the job kind (kJobKindShift) and the image plane (kJobPlaneShift)
+  int boxXY;       // boxX | boxY << 16
+  int shareMask;   // bit w: warp w of the tile may slide its windows down the column (see gatherColumnShared); found by the host
 };
 // job kinds of the persistent gather kernel: 0 / 1 = staged through TMA with box class 0 / 1, 2 = general (L1) path
 constexpr int kJobKindShift = 24, kJobRowMask = (1 << kJobKindShift) - 1, kJobGeneral = 2;
@@ -36,10 +38,10 @@ constexpr int kMaxFramePlanes = 3;
 struct PlaneView {
   const uint8_t* src;   // (blurred) input plane
   uint8_t* dst;
-  const int2* samples;  // lane-ordered records, [dstH][samplesPitch]
+  const int2* samples;  // lane-ordered, tile-major records
   int srcW, srcH, srcPitch;
   int dstW, dstH, dstPitch;
-  int samplesPitch;
+  int tilesPerRow;
   int reserved;
 };
 struct FrameGatherParams {
@@ -73,10 +75,14 @@ __host__ __device__ constexpr int weightSlotOf(int k, int phase) {
 __host__ __device__ constexpr int weightBankGroups(int k) { return k == 2 ? 16 : 8; }
 __host__ __device__ constexpr int weightLanesPerPass(int k) { return k == 2 ? 16 : 8; }
 
-// The sampling records of a plane are stored per 32-pixel row segment in LANE order, not column order: the host
-// deals the pixels of a segment to lanes so that the lanes served together by one shared-memory pass ask for
-// different bank groups (see buildLaneOrder in video_frame_transform.cpp).  Record word 0 therefore carries the
-// pixel's column inside the segment in its top 5 bits: x = segmentX + (word0 >> 27), col0 = (word0 << 5) >> 5.
+// Sampling records.  Tile-major: the gatherTileH(k) x 32 records of output tile (ty, tx) are contiguous,
+//   records[((ty * tilesPerRow + tx) * gatherTileH(k) + rowInTile) * 32 + lane]
+// (tiles that stick out of the plane are padded with zero records), so a warp fetches the records of its four rows
+// from one base address with immediate offsets and needs no bounds checks.  Inside a 32-pixel row segment the records
+// are in LANE order, not column order: the host deals the pixels of a segment to lanes so that the lanes served
+// together by one shared-memory pass ask for different bank groups (see buildLaneOrder in video_frame_transform.cpp).
+// Record word 0 therefore carries the pixel's column inside the segment in its top 5 bits:
+// x = segmentX + (word0 >> 27), col0 = (word0 << 5) >> 5.
 constexpr int kRecordColumnShift = 27;
 
 struct StagedParams {

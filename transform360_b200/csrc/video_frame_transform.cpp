@@ -77,8 +77,8 @@ struct DevicePlan {
   int inW = 0, inH = 0, outW = 0, outH = 0, mapW = 0, mapH = 0;
   int kernelSize = 0;
   bool transparent = false, lowPass = false, blurNeedsClear = false;
-  DeviceBuffer<int2> samples;
-  int samplesPitch = 0;
+  DeviceBuffer<int2> samples;  // tile-major, lane-ordered records (kernels.cuh)
+  int tilesPerRow = 0;
   // gather tiles: those whose source window fits the TMA staging box, and the rest (by tile index)
   DeviceBuffer<StagedTile> gatherJobs;  // every tile of the plane, sorted by kind (general, class 1, class 0)
   std::vector<StagedTile> hostJobs;     // the same list on the host: merged per frame by frameJobList()
@@ -478,9 +478,11 @@ class VideoFrameTransform {
     d.transparent = h.transparentBorder;
     if (d.kernelSize > 0) {
       deviceWeights(ctx_.interpolation_alg);
-      d.samplesPitch = (h.mapW + 3) & ~3;
-      std::vector<int2> padded(static_cast<size_t>(d.samplesPitch) * h.mapH, int2{0, 0});
-      buildLaneOrder(h, padded, d.samplesPitch);
+      const int tileH = t360::gatherTileH(d.kernelSize);
+      d.tilesPerRow = (h.mapW + t360::kGatherTileW - 1) / t360::kGatherTileW;
+      const size_t tileRows = static_cast<size_t>((h.mapH + tileH - 1) / tileH) * tileH;
+      std::vector<int2> padded(static_cast<size_t>(d.tilesPerRow) * tileRows * t360::kGatherTileW, int2{0, 0});
+      buildLaneOrder(h, padded, d.tilesPerRow, tileH);
       d.samples.reserve(padded.size());
       CU(cudaMemcpy(d.samples.ptr, padded.data(), padded.size() * sizeof(int2), cudaMemcpyHostToDevice));
       if (d.kernelSize >= 2 && !d.transparent) buildGatherTiles(h, d);
@@ -515,7 +517,7 @@ class VideoFrameTransform {
   // different bank groups of the weight table: sort the pixels by (bank group, phase), then deal them round-robin
   // over the passes.  The window reads are unaffected (the warp still touches the same 32 windows) and the stores
   // still fill one 32-byte sector.  The pixel's column inside the segment travels in the record's top 5 bits.
-  static void buildLaneOrder(const HostPlan& h, std::vector<int2>& out, int pitch) {
+  static void buildLaneOrder(const HostPlan& h, std::vector<int2>& out, int tilesPerRow, int tileH) {
     const int k = h.kernelSize;
     const int groups = t360::weightBankGroups(k), lanesPerPass = t360::weightLanesPerPass(k), passes = 32 / lanesPerPass;
     constexpr int kRows = 4;  // rows per thread: one lane order per 32 x 4 block, so that a thread keeps ONE column
@@ -537,13 +539,15 @@ class VideoFrameTransform {
         }
         for (int y = yb; y < std::min(h.mapH, yb + kRows); ++y) {
           const t360::SamplePoint* row = &h.samples[static_cast<size_t>(y) * h.mapW];
-          int2* dst = &out[static_cast<size_t>(y) * pitch];
+          // tile-major: the records of tile (ty, tx) are contiguous, [rowInTile][lane]
+          const size_t tile = static_cast<size_t>(y / tileH) * tilesPerRow + x0 / 32;
+          int2* dst = &out[(tile * tileH + y % tileH) * 32];
           for (int i = 0; i < n; ++i) {
             // i-th pixel of the sorted sequence -> pass i % passes, position i / passes inside the pass
             const int lane = deal ? (i % passes) * lanesPerPass + i / passes : i;
             const int c = order[i];
             const t360::SamplePoint& sp = row[x0 + c];
-            dst[x0 + lane] = int2{static_cast<int>((static_cast<unsigned>(sp.col0) & ((1u << t360::kRecordColumnShift) - 1)) |
+            dst[lane] = int2{static_cast<int>((static_cast<unsigned>(sp.col0) & ((1u << t360::kRecordColumnShift) - 1)) |
                                                    (static_cast<unsigned>(c) << t360::kRecordColumnShift)),
                                   sp.rowPhase};
           }
@@ -577,7 +581,21 @@ class VideoFrameTransform {
         int cls = -1;
         for (int c = 0; c < t360::kNumBoxClasses && inPlane && cls < 0; ++c)
           if (maxC + k - boxX <= t360::stageBoxW(k, c) && maxR + k - minR <= t360::stageBoxH(k, c)) cls = c;
-        if (cls >= 0) staged[cls].push_back(StagedTile{tx * tw, ty * th | (cls << t360::kJobKindShift), boxX, minR});
+        // warps (4 rows each) whose every pixel column keeps its source column down the 4 rows, 1-2 source rows apart:
+        // they slide one register window down the column (gatherColumnShared) instead of fetching 4 windows
+        int shareMask = 0;
+        for (int w = 0; k >= 4 && w < th / 4; ++w) {
+          const int ya = ty * th + 4 * w;
+          bool ok = ya + 4 <= h.mapH;
+          for (int x = tx * tw; ok && x < x1; ++x)
+            for (int j = 1; j < 4 && ok; ++j) {
+              const t360::SamplePoint &a = h.samples[static_cast<size_t>(ya + j - 1) * h.mapW + x], &b = h.samples[static_cast<size_t>(ya + j) * h.mapW + x];
+              const int d = (b.rowPhase >> 10) - (a.rowPhase >> 10);
+              ok = (d == 1 || d == 2) && b.col0 == h.samples[static_cast<size_t>(ya) * h.mapW + x].col0;
+            }
+          if (ok) shareMask |= 1 << w;
+        }
+        if (cls >= 0) staged[cls].push_back(StagedTile{tx * tw, ty * th | (cls << t360::kJobKindShift), boxX | (minR << 16), shareMask});
         else fallback.push_back(StagedTile{tx * tw, ty * th | (t360::kJobGeneral << t360::kJobKindShift), 0, 0});
       }
     // order: general tiles, then the wide-box class, then the common class (see gatherPlaneKernel)
@@ -788,7 +806,7 @@ class VideoFrameTransform {
       src = lane.blurred.ptr;
       srcPitch = bp;
     }
-    w.view = t360::PlaneView{src, dOut, plan.samples.ptr, inW, inH, srcPitch, outW, outH, outPitch, plan.samplesPitch, 0};
+    w.view = t360::PlaneView{src, dOut, plan.samples.ptr, inW, inH, srcPitch, outW, outH, outPitch, plan.tilesPerRow, 0};
     // staged tiles need the plane the plan was made for (their windows were proven in-bounds for it) and a
     // TMA-describable layout (16-byte aligned base and pitch); otherwise every tile takes the general kernel
     w.staged = plan.totalStaged() > 0 && !plan.transparent && inW == plan.inW && inH == plan.inH;
@@ -817,7 +835,7 @@ class VideoFrameTransform {
       CU(t360::launchGatherFrame(fp, jobs, w.maps, numSMs_, s));
     } else {
       const t360::PlaneView& v = w.view;
-      t360::GatherParams gp{v.src, v.srcW, v.srcH, v.srcPitch, v.dst, v.dstW, v.dstH, v.dstPitch, v.samples, v.samplesPitch,
+      t360::GatherParams gp{v.src, v.srcW, v.srcH, v.srcPitch, v.dst, v.dstW, v.dstH, v.dstPitch, v.samples, v.tilesPerRow,
                             weights_[plan.kernelSize].ptr, plan.kernelSize, plan.transparent ? 1 : 0};
       CU(t360::launchGather(gp, numSMs_, s));
     }
