@@ -440,8 +440,9 @@ __device__ __forceinline__ void computeStagedTile(const PlaneView& p, const unsi
   const int y0 = outY + warp * kRowsPerThread;
   const bool active = outX + lane < p.dstW;
   // `shared` (warp-uniform, from the tile header): every active lane's 4 pixels share their columns, all 4 rows exist
-  uint8_t* const dst = p.dst;
+  // a thread's four pixels sit in ONE output column (one lane order per 32 x 4 block): one address, four row steps
   const int dstPitch = p.dstPitch;
+  uint8_t* const dst = p.dst + (size_t)y0 * dstPitch + outX + recordColumn(rec[0].x);
   if (shared) {
     if constexpr (K >= 4) {
       if (active) {
@@ -449,7 +450,7 @@ __device__ __forceinline__ void computeStagedTile(const PlaneView& p, const unsi
         gatherColumnShared<K, PITCH>(stage, boxX, boxY, rec, wsmem, acc);
 #pragma unroll
         for (int j = 0; j < kRowsPerThread; ++j)
-          dst[(size_t)(y0 + j) * dstPitch + outX + recordColumn(rec[j].x)] = (uint8_t)roundToByte(acc[j]);
+          dst[(size_t)j * dstPitch] = (uint8_t)roundToByte(acc[j]);
       }
     }
   } else if (active) {
@@ -461,7 +462,7 @@ __device__ __forceinline__ void computeStagedTile(const PlaneView& p, const unsi
       const int row0 = rec[j].y >> 10, phase = rec[j].y & 1023;
       const int off = (row0 - boxY) * PITCH + (recordCol0(rec[j].x) - boxX);
       const int acc = foldWindowShared<K, PITCH>(stageAddr, off, wAddr, phase);
-      dst[(size_t)(y0 + j) * dstPitch + outX + recordColumn(rec[j].x)] = (uint8_t)roundToByte(acc);
+      dst[(size_t)j * dstPitch] = (uint8_t)roundToByte(acc);
     }
   }
 }
