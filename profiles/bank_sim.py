@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Offline model of the shared-memory bank behaviour of gatherPlaneKernel (no GPU needed).
+"""Offline model of the shared-memory bank behaviour of the staged gather (gatherFrameKernel; no GPU needed).
 
 Takes the host plan of a BASELINE config (through libTransform360.so's host-plan API) and counts, per warp-step,
 the shared-memory wavefronts of (a) the aligned 32-bit window ("tap") loads for a given staging pitch and

@@ -1,28 +1,30 @@
 // sm_100a kernels of the projection-remap hot path.
 //
-//   gatherPlaneKernel<K>   replaces cv::remap as the reference calls it (VideoFrameTransform.cpp:748-754):
+//   gatherFrameKernel<K>   replace cv::remap as the reference calls it (VideoFrameTransform.cpp:748-754):
 //   gatherKernel<K>        per output pixel a K x K window of the 8-bit source is weighted with OpenCV's
-//                          15-bit fixed-point table and rounded with (sum + 16384) >> 15.  Bit-exact by
+//   nearestKernel          15-bit fixed-point table and rounded with (sum + 16384) >> 15.  Bit-exact by
 //                          construction: same table (host-built, sampling.cpp), same integer arithmetic.
-//   blurTileKernel         replaces cv::sepFilter2D over the reference's tiles (cpp:173-204, 579-704):
-//                          separable Gaussian, float32, fused multiply-add chain in the order cv2 4.13 uses
-//                          (see oracle/t360_oracle.c for the model and its pin), round-half-even, u8.
+//   blurStripKernel<HY>    replace cv::sepFilter2D over the reference's tiles (cpp:173-204, 579-704):
+//   blurTileKernel         separable Gaussian, float32, fused multiply-add chain in the order cv2 4.13 uses
+//   blurDirectKernel       (see oracle/t360_oracle.c for the model and its pin), round-half-even, u8.
+//   areaResizeKernel       replaces cv::resize(INTER_AREA) shrinking (cpp:770-776).
 //
 // This is a gather, not a contraction: no tensor cores.  What the design is built around:
-//   * A warp owns 32 adjacent output columns x 4 rows; lane L computes column L one row at a time, so a
-//     warp-wide tap read covers ~48 contiguous source bytes per source row.  Plan reads are 8 B per lane
-//     (256 contiguous bytes per warp), stores 1 B per lane (one full 32-byte sector per warp).
-//   * Staged path (the bulk of every plane): the source window of a 32 x 32 (K=8: 32 x 64) output tile is
-//     brought into shared memory by ONE cp.async.bulk.tensor.2d (TMA) box load from the pitch-linear
-//     plane, double-buffered against the arithmetic through mbarriers; taps are then read as aligned
-//     32-bit shared-memory words (bank-granular, no 32-byte-sector waste: the same reads through L1
+//   * A warp owns 32 adjacent output columns x 4 rows; a lane computes one column, so a warp-wide tap read
+//     covers ~48 contiguous source bytes per source row.  Plan reads are 8 B per lane (256 contiguous bytes
+//     per warp, tile-major), stores 1 B per lane (one full 32-byte sector per warp).
+//   * gatherFrameKernel: ONE persistent launch takes the tiles of all planes of a frame, handed out by an
+//     atomic counter.  Staged tiles (the bulk of every plane): the source window of a 32 x 32 (K=8: 32 x 64)
+//     output tile is brought into shared memory by ONE cp.async.bulk.tensor.2d (TMA) box load from the
+//     pitch-linear plane, double-buffered against the arithmetic through mbarriers; taps are then read as
+//     aligned 32-bit shared-memory words (bank-granular, no 32-byte-sector waste: the same reads through L1
 //     measured 13-26 sectors per request) and aligned with a funnel shift.
 //   * Every window row is folded with IDP.2A: two s16 x u8 multiply-adds per instruction.
 //   * The 1024-phase weight table sits in shared memory, transposed so that unrelated phases spread
 //     over bank groups; persistent CTAs (grid = multiple of the SM count) stage it once.
-//   * Tiles whose window does not fit the box, touches a plane border (BORDER_WRAP wraps rows AND
-//     columns, cpp:719) or belongs to a BORDER_TRANSPARENT plan go through gatherKernel, which reads taps
-//     through L1 and handles every border case.
+//   * Tiles whose window does not fit a box or touches a plane border (BORDER_WRAP wraps rows AND columns,
+//     cpp:719) read their taps through L1 inside the same launch; BORDER_TRANSPARENT plans, nearest
+//     neighbour and planes TMA cannot describe go through gatherKernel / nearestKernel.
 #include "kernels.cuh"
 
 #include <cuda.h>  // CUtensorMap (type only; no libcuda symbol is referenced)

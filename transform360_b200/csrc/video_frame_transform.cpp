@@ -136,6 +136,7 @@ bool encodePlaneMap(CUtensorMap* map, const uint8_t* base, int w, int h, int pit
 // Everything one image plane needs to be in flight independently of the others: the frame entry point runs the
 // luma plane on the caller's stream and the two chroma planes on their own lanes.
 constexpr int kPlaneLanes = 3;
+static_assert(kPlaneLanes == t360::kMaxFramePlanes, "the frame kernel takes one PlaneView per lane");
 struct PlaneLane {
   cudaStream_t main = nullptr;                       // chroma lanes only (lane 0 runs on the caller's stream)
   cudaEvent_t done = nullptr;                        // recorded when this lane's plane has been enqueued completely
@@ -598,7 +599,7 @@ class VideoFrameTransform {
         if (cls >= 0) staged[cls].push_back(StagedTile{tx * tw, ty * th | (cls << t360::kJobKindShift), boxX | (minR << 16), shareMask});
         else fallback.push_back(StagedTile{tx * tw, ty * th | (t360::kJobGeneral << t360::kJobKindShift), 0, 0});
       }
-    // order: general tiles, then the wide-box class, then the common class (see gatherPlaneKernel)
+    // order: general tiles, then the wide-box class, then the common class (see gatherFrameKernel)
     std::vector<StagedTile> jobs;
     d.numFallback = static_cast<int>(fallback.size());
     jobs.insert(jobs.end(), fallback.begin(), fallback.end());
