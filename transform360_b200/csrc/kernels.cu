@@ -473,6 +473,7 @@ template <int K>
 __global__ void __launch_bounds__(gatherThreads(K), K == 8 ? 1 : 3)
 gatherFrameKernel(const __grid_constant__ FrameGatherParams p, StagedParams jobs, const __grid_constant__ FrameTensorMaps maps) {
   static_assert(stageBoxW(K, 1) * stageBoxH(K, 1) + 64 <= 2 * stageBytes<K, 0>(), "a class-1 box must fit both stage buffers");
+  static_assert(stageBoxW(K, 0) * stageBoxH(K, 0) % 16 == 0, "the seam merge works on 16-byte vectors");
   extern __shared__ __align__(16) unsigned char smem[];
   unsigned char* wsmem = smem;
   unsigned char* stage0 = smem + weightBytes<K>();
@@ -590,6 +591,31 @@ gatherFrameKernel(const __grid_constant__ FrameGatherParams p, StagedParams jobs
       mbarWait(&bars[2], q1 & 1);
       computeStagedTile<K, stageBoxW(K, 1)>(pv, stage0, tile.outX, outY, tile.boxXY & 0xffff, tile.boxXY >> 16,
                                             K >= 4 && ((tile.shareMask >> warp) & 1), rec, wsmem, lane, warp);
+      ++q1;
+    } else if (kind == kJobSeam) {
+      // two complementary class-0 boxes (zero-filled outside the plane), one per stage buffer, OR-ed into the first
+      const int boxX = tile.boxXY & 0xffff, boxY = tile.boxXY >> 16;
+      if (threadIdx.x == 0) {
+        mbarExpectTx(&bars[2], 2 * kBox0);
+        const CUtensorMap* m = &maps.map[tile.outY >> kJobPlaneShift][0];
+        tmaLoadBox(stage0, m, boxX, boxY, &bars[2]);
+        tmaLoadBox(stage0 + kStage, m, boxX - pv.srcW, boxY, &bars[2]);
+      }
+      mbarWait(&bars[2], q1 & 1);
+      {
+        uint4* a = reinterpret_cast<uint4*>(stage0);
+        const uint4* b = reinterpret_cast<const uint4*>(stage0 + kStage);
+        for (int i = threadIdx.x; i < (int)(kBox0 / 16); i += gatherThreads(K)) {
+          uint4 x = a[i];
+          const uint4 y = b[i];
+          x.x |= y.x; x.y |= y.y; x.z |= y.z; x.w |= y.w;
+          a[i] = x;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // these writes precede later TMA writes to the stage
+      }
+      __syncthreads();
+      computeStagedTile<K, stageBoxW(K, 0)>(pv, stage0, tile.outX, outY, boxX, boxY, K >= 4 && ((tile.shareMask >> warp) & 1), rec,
+                                            wsmem, lane, warp);
       ++q1;
     } else {
       if (nextIsClass0 && issued0 == q0) {  // both stages are idle during a general tile: start the next box now

@@ -27,8 +27,13 @@ struct StagedTile {
   int boxXY;       // boxX | boxY << 16
   int shareMask;   // bit w: warp w of the tile may slide its windows down the column (see gatherColumnShared); found by the host
 };
-// job kinds of the persistent gather kernel: 0 / 1 = staged through TMA with box class 0 / 1, 2 = general (L1) path
-constexpr int kJobKindShift = 24, kJobRowMask = (1 << kJobKindShift) - 1, kJobGeneral = 2;
+// job kinds of the persistent gather kernel: 0 / 1 = staged through TMA with box class 0 / 1, 2 = general (L1) path,
+// 3 = "seam": the tile's windows cross the left/right plane border (BORDER_WRAP, the +-180 degree meridian of an
+// equirect source) but fit a class-0 box that wraps around it.  The box is fetched as TWO class-0 TMA loads, at
+// column boxX and at column boxX - srcW: whatever lies outside the plane arrives as zeros, so the two boxes are
+// complementary and their bitwise OR is the wrapped window.  The records of such a tile carry col0 relative to the
+// unwrapped box (boxX <= col0 < boxX + box width, i.e. up to srcW + box width).
+constexpr int kJobKindShift = 24, kJobRowMask = (1 << kJobKindShift) - 1, kJobGeneral = 2, kJobSeam = 3;
 constexpr int kJobPlaneShift = 28, kJobKindMask = (1 << (kJobPlaneShift - kJobKindShift)) - 1;
 
 // The persistent gather kernel takes the tiles of up to three image planes (Y, U, V of one frame) in ONE launch:

@@ -82,8 +82,8 @@ struct DevicePlan {
   // gather tiles: those whose source window fits the TMA staging box, and the rest (by tile index)
   DeviceBuffer<StagedTile> gatherJobs;  // every tile of the plane, sorted by kind (general, class 1, class 0)
   std::vector<StagedTile> hostJobs;     // the same list on the host: merged per frame by frameJobList()
-  int numJobs = 0, numStaged[t360::kNumBoxClasses] = {}, numFallback = 0;
-  int totalStaged() const { int n = 0; for (int c : numStaged) n += c; return n; }
+  int numJobs = 0, numStaged[t360::kNumBoxClasses] = {}, numSeam = 0, numFallback = 0;
+  int totalStaged() const { int n = numSeam; for (int c : numStaged) n += c; return n; }
   // low-pass: register-resident strip jobs grouped by vertical half-size 1..3, and the rest (large vertical kernels)
   DeviceBuffer<StripJob> stripJobs[t360::kStripMaxHy];
   int numStripJobs[t360::kStripMaxHy] = {};
@@ -482,11 +482,12 @@ class VideoFrameTransform {
       const int tileH = t360::gatherTileH(d.kernelSize);
       d.tilesPerRow = (h.mapW + t360::kGatherTileW - 1) / t360::kGatherTileW;
       const size_t tileRows = static_cast<size_t>((h.mapH + tileH - 1) / tileH) * tileH;
+      std::vector<int> seamBoxX(static_cast<size_t>(d.tilesPerRow) * (tileRows / tileH), -1);  // per tile; >= 0: seam tile
+      if (d.kernelSize >= 2 && !d.transparent) buildGatherTiles(h, d, seamBoxX);
       std::vector<int2> padded(static_cast<size_t>(d.tilesPerRow) * tileRows * t360::kGatherTileW, int2{0, 0});
-      buildLaneOrder(h, padded, d.tilesPerRow, tileH);
+      buildLaneOrder(h, padded, d.tilesPerRow, tileH, seamBoxX);
       d.samples.reserve(padded.size());
       CU(cudaMemcpy(d.samples.ptr, padded.data(), padded.size() * sizeof(int2), cudaMemcpyHostToDevice));
-      if (d.kernelSize >= 2 && !d.transparent) buildGatherTiles(h, d);
     }
     d.lowPass = ctx_.enable_low_pass_filter != 0;
     if (d.lowPass) buildBlurJobs(h, d);
@@ -518,7 +519,7 @@ class VideoFrameTransform {
   // different bank groups of the weight table: sort the pixels by (bank group, phase), then deal them round-robin
   // over the passes.  The window reads are unaffected (the warp still touches the same 32 windows) and the stores
   // still fill one 32-byte sector.  The pixel's column inside the segment travels in the record's top 5 bits.
-  static void buildLaneOrder(const HostPlan& h, std::vector<int2>& out, int tilesPerRow, int tileH) {
+  static void buildLaneOrder(const HostPlan& h, std::vector<int2>& out, int tilesPerRow, int tileH, const std::vector<int>& seamBoxX) {
     const int k = h.kernelSize;
     const int groups = t360::weightBankGroups(k), lanesPerPass = t360::weightLanesPerPass(k), passes = 32 / lanesPerPass;
     constexpr int kRows = 4;  // rows per thread: one lane order per 32 x 4 block, so that a thread keeps ONE column
@@ -548,7 +549,13 @@ class VideoFrameTransform {
             const int lane = deal ? (i % passes) * lanesPerPass + i / passes : i;
             const int c = order[i];
             const t360::SamplePoint& sp = row[x0 + c];
-            dst[lane] = int2{static_cast<int>((static_cast<unsigned>(sp.col0) & ((1u << t360::kRecordColumnShift) - 1)) |
+            int col0 = sp.col0;
+            if (seamBoxX[tile] >= 0) {  // seam tile: first column relative to the unwrapped box (kernels.cuh, kJobSeam)
+              int cw = col0 % h.inW;
+              if (cw < 0) cw += h.inW;
+              col0 = seamBoxX[tile] + (cw - seamBoxX[tile] + h.inW) % h.inW;
+            }
+            dst[lane] = int2{static_cast<int>((static_cast<unsigned>(col0) & ((1u << t360::kRecordColumnShift) - 1)) |
                                                    (static_cast<unsigned>(c) << t360::kRecordColumnShift)),
                                   sp.rowPhase};
           }
@@ -560,11 +567,13 @@ class VideoFrameTransform {
   // Splits the output plane into CTA tiles and finds, per tile, the bounding box of all source windows.  A tile is
   // "staged" when that box lies inside the plane (no BORDER_WRAP needed) and fits the fixed TMA box; its box is
   // anchored at a 16-byte aligned column.  Everything else is listed for the general (L1) kernel.
-  void buildGatherTiles(const HostPlan& h, DevicePlan& d) {
+  void buildGatherTiles(const HostPlan& h, DevicePlan& d, std::vector<int>& seamBoxX) {
     const int k = h.kernelSize, tw = t360::kGatherTileW, th = t360::gatherTileH(k);
     const int tilesX = (h.mapW + tw - 1) / tw, tilesY = (h.mapH + th - 1) / th;
     std::vector<StagedTile> staged[t360::kNumBoxClasses];
-    std::vector<StagedTile> fallback;
+    std::vector<StagedTile> fallback, seam;
+    // seam tiles need whole 16-byte columns on both sides of the border and a plane much wider than the box
+    const bool seamPossible = h.inW % 16 == 0 && h.inW >= 4 * t360::stageBoxW(k, 0);
     for (int ty = 0; ty < tilesY; ++ty)
       for (int tx = 0; tx < tilesX; ++tx) {
         int minC = INT32_MAX, maxC = INT32_MIN, minR = INT32_MAX, maxR = INT32_MIN;
@@ -596,13 +605,37 @@ class VideoFrameTransform {
             }
           if (ok) shareMask |= 1 << w;
         }
-        if (cls >= 0) staged[cls].push_back(StagedTile{tx * tw, ty * th | (cls << t360::kJobKindShift), boxX | (minR << 16), shareMask});
-        else fallback.push_back(StagedTile{tx * tw, ty * th | (t360::kJobGeneral << t360::kJobKindShift), 0, 0});
+        // windows that cross the left/right border only (BORDER_WRAP): do they fit a class-0 box that wraps around it?
+        int wrappedBoxX = -1;
+        if (cls < 0 && seamPossible && minR >= 0 && maxR + k <= h.inH && maxR + k - minR <= t360::stageBoxH(k, 0)) {
+          const int W = h.inW, half = W / 2;  // columns rotated by half a plane: the border is in the middle of the range
+          int lo = INT32_MAX, hi = INT32_MIN;
+          for (int y = ty * th; y < y1; ++y)
+            for (int x = tx * tw; x < x1; ++x) {
+              int cw = h.samples[static_cast<size_t>(y) * h.mapW + x].col0 % W;
+              if (cw < 0) cw += W;
+              const int rot = cw + half >= W ? cw + half - W : cw + half;
+              lo = std::min(lo, rot); hi = std::max(hi, rot);
+            }
+          const int first = lo - half < 0 ? lo - half + W : lo - half;  // leftmost first column, in plane coordinates
+          const int bx = first & ~15;
+          if (hi - lo + (first - bx) + k <= t360::stageBoxW(k, 0) && bx + t360::stageBoxW(k, 0) > W) wrappedBoxX = bx;
+        }
+        if (cls >= 0) {
+          staged[cls].push_back(StagedTile{tx * tw, ty * th | (cls << t360::kJobKindShift), boxX | (minR << 16), shareMask});
+        } else if (wrappedBoxX >= 0) {
+          seam.push_back(StagedTile{tx * tw, ty * th | (t360::kJobSeam << t360::kJobKindShift), wrappedBoxX | (minR << 16), shareMask});
+          seamBoxX[static_cast<size_t>(ty) * tilesX + tx] = wrappedBoxX;
+        } else {
+          fallback.push_back(StagedTile{tx * tw, ty * th | (t360::kJobGeneral << t360::kJobKindShift), 0, 0});
+        }
       }
-    // order: general tiles, then the wide-box class, then the common class (see gatherFrameKernel)
+    // order: general tiles, seam tiles, then the wide-box class, then the common class (see gatherFrameKernel)
     std::vector<StagedTile> jobs;
     d.numFallback = static_cast<int>(fallback.size());
+    d.numSeam = static_cast<int>(seam.size());
     jobs.insert(jobs.end(), fallback.begin(), fallback.end());
+    jobs.insert(jobs.end(), seam.begin(), seam.end());
     for (int c = t360::kNumBoxClasses - 1; c >= 0; --c) {
       d.numStaged[c] = static_cast<int>(staged[c].size());
       jobs.insert(jobs.end(), staged[c].begin(), staged[c].end());
@@ -847,7 +880,7 @@ class VideoFrameTransform {
     FrameJobList& f = frameJobs_;
     if (f.generation != planGeneration_ || f.numPlanes != numPlanes) {
       std::vector<StagedTile> merged;
-      for (int kind : {t360::kJobGeneral, 1, 0})
+      for (int kind : {t360::kJobGeneral, t360::kJobSeam, 1, 0})
         for (int p = 0; p < numPlanes; ++p)
           for (StagedTile t : work[p].plan->hostJobs) {
             if (((t.outY >> t360::kJobKindShift) & t360::kJobKindMask) != kind) continue;
