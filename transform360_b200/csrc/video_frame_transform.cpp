@@ -21,6 +21,7 @@
 #include <vector>
 
 #include "host_plan.h"
+#include "gather_plan.h"
 #include "kernels.cuh"
 #include "transform360_b200.h"
 
@@ -479,15 +480,20 @@ class VideoFrameTransform {
     d.transparent = h.transparentBorder;
     if (d.kernelSize > 0) {
       deviceWeights(ctx_.interpolation_alg);
-      const int tileH = t360::gatherTileH(d.kernelSize);
-      d.tilesPerRow = (h.mapW + t360::kGatherTileW - 1) / t360::kGatherTileW;
-      const size_t tileRows = static_cast<size_t>((h.mapH + tileH - 1) / tileH) * tileH;
-      std::vector<int> seamBoxX(static_cast<size_t>(d.tilesPerRow) * (tileRows / tileH), -1);  // per tile; >= 0: seam tile
-      if (d.kernelSize >= 2 && !d.transparent) buildGatherTiles(h, d, seamBoxX);
-      std::vector<int2> padded(static_cast<size_t>(d.tilesPerRow) * tileRows * t360::kGatherTileW, int2{0, 0});
-      buildLaneOrder(h, padded, d.tilesPerRow, tileH, seamBoxX);
-      d.samples.reserve(padded.size());
-      CU(cudaMemcpy(d.samples.ptr, padded.data(), padded.size() * sizeof(int2), cudaMemcpyHostToDevice));
+      t360::GatherPlan g;
+      t360::buildGatherPlan(h, d.kernelSize >= 2 && !d.transparent, g);
+      d.tilesPerRow = g.tilesPerRow;
+      d.samples.reserve(g.records.size());
+      CU(cudaMemcpy(d.samples.ptr, g.records.data(), g.records.size() * sizeof(int2), cudaMemcpyHostToDevice));
+      d.numFallback = g.numGeneral;
+      d.numSeam = g.numSeam;
+      for (int c = 0; c < t360::kNumBoxClasses; ++c) d.numStaged[c] = g.numStaged[c];
+      d.numJobs = static_cast<int>(g.jobs.size());
+      if (!g.jobs.empty()) {
+        d.gatherJobs.reserve(g.jobs.size());
+        CU(cudaMemcpy(d.gatherJobs.ptr, g.jobs.data(), g.jobs.size() * sizeof(StagedTile), cudaMemcpyHostToDevice));
+      }
+      d.hostJobs = std::move(g.jobs);
     }
     d.lowPass = ctx_.enable_low_pass_filter != 0;
     if (d.lowPass) buildBlurJobs(h, d);
@@ -511,141 +517,6 @@ class VideoFrameTransform {
       uploadAxis(h.resize.y, d.areaYTaps, d.areaYFirst);
     }
     return d;
-  }
-
-  // Device order of the sampling records.  Each row is cut into segments of 32 pixels (= the width of a gather
-  // tile = one warp); inside a segment the pixels are dealt to LANES so that the lanes which one shared-memory pass
-  // serves together (8 for the 128-bit weight loads of cubic / Lanczos, 16 for the 64-bit ones of bilinear) ask for
-  // different bank groups of the weight table: sort the pixels by (bank group, phase), then deal them round-robin
-  // over the passes.  The window reads are unaffected (the warp still touches the same 32 windows) and the stores
-  // still fill one 32-byte sector.  The pixel's column inside the segment travels in the record's top 5 bits.
-  static void buildLaneOrder(const HostPlan& h, std::vector<int2>& out, int tilesPerRow, int tileH, const std::vector<int>& seamBoxX) {
-    const int k = h.kernelSize;
-    const int groups = t360::weightBankGroups(k), lanesPerPass = t360::weightLanesPerPass(k), passes = 32 / lanesPerPass;
-    constexpr int kRows = 4;  // rows per thread: one lane order per 32 x 4 block, so that a thread keeps ONE column
-    for (int yb = 0; yb < h.mapH; yb += kRows) {
-      for (int x0 = 0; x0 < h.mapW; x0 += 32) {
-        const int n = std::min(32, h.mapW - x0);
-        int order[32];
-        for (int i = 0; i < n; ++i) order[i] = i;
-        const bool deal = k >= 2 && n == 32;
-        if (deal) {
-          // the bank group depends on fracX only, and fracX is the same down a column wherever the source column
-          // does not depend on the output row (the four equatorial cube faces): order by the block's first row
-          const t360::SamplePoint* row = &h.samples[static_cast<size_t>(yb) * h.mapW];
-          auto keyOf = [&](int c) {
-            const int phase = row[x0 + c].rowPhase & 1023;
-            return ((t360::weightSlotOf(k, phase) & (groups - 1)) << 10) | phase;
-          };
-          std::stable_sort(order, order + n, [&](int a, int b) { return keyOf(a) < keyOf(b); });
-        }
-        for (int y = yb; y < std::min(h.mapH, yb + kRows); ++y) {
-          const t360::SamplePoint* row = &h.samples[static_cast<size_t>(y) * h.mapW];
-          // tile-major: the records of tile (ty, tx) are contiguous, [rowInTile][lane]
-          const size_t tile = static_cast<size_t>(y / tileH) * tilesPerRow + x0 / 32;
-          int2* dst = &out[(tile * tileH + y % tileH) * 32];
-          for (int i = 0; i < n; ++i) {
-            // i-th pixel of the sorted sequence -> pass i % passes, position i / passes inside the pass
-            const int lane = deal ? (i % passes) * lanesPerPass + i / passes : i;
-            const int c = order[i];
-            const t360::SamplePoint& sp = row[x0 + c];
-            int col0 = sp.col0;
-            if (seamBoxX[tile] >= 0) {  // seam tile: first column relative to the unwrapped box (kernels.cuh, kJobSeam)
-              int cw = col0 % h.inW;
-              if (cw < 0) cw += h.inW;
-              col0 = seamBoxX[tile] + (cw - seamBoxX[tile] + h.inW) % h.inW;
-            }
-            dst[lane] = int2{static_cast<int>((static_cast<unsigned>(col0) & ((1u << t360::kRecordColumnShift) - 1)) |
-                                                   (static_cast<unsigned>(c) << t360::kRecordColumnShift)),
-                                  sp.rowPhase};
-          }
-        }
-      }
-    }
-  }
-
-  // Splits the output plane into CTA tiles and finds, per tile, the bounding box of all source windows.  A tile is
-  // "staged" when that box lies inside the plane (no BORDER_WRAP needed) and fits the fixed TMA box; its box is
-  // anchored at a 16-byte aligned column.  Everything else is listed for the general (L1) kernel.
-  void buildGatherTiles(const HostPlan& h, DevicePlan& d, std::vector<int>& seamBoxX) {
-    const int k = h.kernelSize, tw = t360::kGatherTileW, th = t360::gatherTileH(k);
-    const int tilesX = (h.mapW + tw - 1) / tw, tilesY = (h.mapH + th - 1) / th;
-    std::vector<StagedTile> staged[t360::kNumBoxClasses];
-    std::vector<StagedTile> fallback, seam;
-    // seam tiles need whole 16-byte columns on both sides of the border and a plane much wider than the box
-    const bool seamPossible = h.inW % 16 == 0 && h.inW >= 4 * t360::stageBoxW(k, 0);
-    for (int ty = 0; ty < tilesY; ++ty)
-      for (int tx = 0; tx < tilesX; ++tx) {
-        int minC = INT32_MAX, maxC = INT32_MIN, minR = INT32_MAX, maxR = INT32_MIN;
-        const int y1 = std::min(h.mapH, (ty + 1) * th), x1 = std::min(h.mapW, (tx + 1) * tw);
-        for (int y = ty * th; y < y1; ++y) {
-          const t360::SamplePoint* row = &h.samples[static_cast<size_t>(y) * h.mapW];
-          for (int x = tx * tw; x < x1; ++x) {
-            const int c = row[x].col0, r = row[x].rowPhase >> 10;
-            minC = std::min(minC, c); maxC = std::max(maxC, c);
-            minR = std::min(minR, r); maxR = std::max(maxR, r);
-          }
-        }
-        const int boxX = minC >= 0 ? (minC & ~15) : -1;
-        const bool inPlane = minC >= 0 && minR >= 0 && maxC + k <= h.inW && maxR + k <= h.inH;
-        int cls = -1;
-        for (int c = 0; c < t360::kNumBoxClasses && inPlane && cls < 0; ++c)
-          if (maxC + k - boxX <= t360::stageBoxW(k, c) && maxR + k - minR <= t360::stageBoxH(k, c)) cls = c;
-        // warps (4 rows each) whose every pixel column keeps its source column down the 4 rows, 1-2 source rows apart:
-        // they slide one register window down the column (gatherColumnShared) instead of fetching 4 windows
-        int shareMask = 0;
-        for (int w = 0; k >= 4 && w < th / 4; ++w) {
-          const int ya = ty * th + 4 * w;
-          bool ok = ya + 4 <= h.mapH;
-          for (int x = tx * tw; ok && x < x1; ++x)
-            for (int j = 1; j < 4 && ok; ++j) {
-              const t360::SamplePoint &a = h.samples[static_cast<size_t>(ya + j - 1) * h.mapW + x], &b = h.samples[static_cast<size_t>(ya + j) * h.mapW + x];
-              const int d = (b.rowPhase >> 10) - (a.rowPhase >> 10);
-              ok = (d == 1 || d == 2) && b.col0 == h.samples[static_cast<size_t>(ya) * h.mapW + x].col0;
-            }
-          if (ok) shareMask |= 1 << w;
-        }
-        // windows that cross the left/right border only (BORDER_WRAP): do they fit a class-0 box that wraps around it?
-        int wrappedBoxX = -1;
-        if (cls < 0 && seamPossible && minR >= 0 && maxR + k <= h.inH && maxR + k - minR <= t360::stageBoxH(k, 0)) {
-          const int W = h.inW, half = W / 2;  // columns rotated by half a plane: the border is in the middle of the range
-          int lo = INT32_MAX, hi = INT32_MIN;
-          for (int y = ty * th; y < y1; ++y)
-            for (int x = tx * tw; x < x1; ++x) {
-              int cw = h.samples[static_cast<size_t>(y) * h.mapW + x].col0 % W;
-              if (cw < 0) cw += W;
-              const int rot = cw + half >= W ? cw + half - W : cw + half;
-              lo = std::min(lo, rot); hi = std::max(hi, rot);
-            }
-          const int first = lo - half < 0 ? lo - half + W : lo - half;  // leftmost first column, in plane coordinates
-          const int bx = first & ~15;
-          if (hi - lo + (first - bx) + k <= t360::stageBoxW(k, 0) && bx + t360::stageBoxW(k, 0) > W) wrappedBoxX = bx;
-        }
-        if (cls >= 0) {
-          staged[cls].push_back(StagedTile{tx * tw, ty * th | (cls << t360::kJobKindShift), boxX | (minR << 16), shareMask});
-        } else if (wrappedBoxX >= 0) {
-          seam.push_back(StagedTile{tx * tw, ty * th | (t360::kJobSeam << t360::kJobKindShift), wrappedBoxX | (minR << 16), shareMask});
-          seamBoxX[static_cast<size_t>(ty) * tilesX + tx] = wrappedBoxX;
-        } else {
-          fallback.push_back(StagedTile{tx * tw, ty * th | (t360::kJobGeneral << t360::kJobKindShift), 0, 0});
-        }
-      }
-    // order: general tiles, seam tiles, then the wide-box class, then the common class (see gatherFrameKernel)
-    std::vector<StagedTile> jobs;
-    d.numFallback = static_cast<int>(fallback.size());
-    d.numSeam = static_cast<int>(seam.size());
-    jobs.insert(jobs.end(), fallback.begin(), fallback.end());
-    jobs.insert(jobs.end(), seam.begin(), seam.end());
-    for (int c = t360::kNumBoxClasses - 1; c >= 0; --c) {
-      d.numStaged[c] = static_cast<int>(staged[c].size());
-      jobs.insert(jobs.end(), staged[c].begin(), staged[c].end());
-    }
-    d.numJobs = static_cast<int>(jobs.size());
-    if (!jobs.empty()) {
-      d.gatherJobs.reserve(jobs.size());
-      CU(cudaMemcpy(d.gatherJobs.ptr, jobs.data(), jobs.size() * sizeof(StagedTile), cudaMemcpyHostToDevice));
-    }
-    d.hostJobs = std::move(jobs);
   }
 
   // Tiles of the plan, applied once (mono) or to both halves of a stereo frame (reference cpp:630-691), cut
@@ -963,6 +834,8 @@ T360_API int VideoFrameTransform_transformFramePlane(VideoFrameTransform* transf
 // ---- extensions (transform360_b200.h) --------------------------------------------------------------------
 struct T360HostPlan {
   HostPlan plan;
+  t360::GatherPlan gather;  // built on first use by T360B200_hostPlanGather
+  bool gatherBuilt = false;
 };
 
 T360_API T360HostPlan* T360B200_hostPlanCreate(const FrameTransformContext* ctx, int inW, int inH, int outW, int outH) {
@@ -990,6 +863,24 @@ T360_API int T360B200_hostPlanInfo(const T360HostPlan* plan, int info[6]) {
 T360_API const float* T360B200_hostPlanMap(const T360HostPlan* plan) { return plan ? plan->plan.map.data() : nullptr; }
 T360_API const int32_t* T360B200_hostPlanSamples(const T360HostPlan* plan) {
   return plan && !plan->plan.samples.empty() ? reinterpret_cast<const int32_t*>(plan->plan.samples.data()) : nullptr;
+}
+T360_API int T360B200_hostPlanGather(T360HostPlan* plan, int info[8], const int32_t** jobs, const int32_t** records) {
+  if (!plan || !info || plan->plan.kernelSize <= 0) return 0;
+  try {
+    if (!plan->gatherBuilt) {
+      t360::buildGatherPlan(plan->plan, plan->plan.kernelSize >= 2 && !plan->plan.transparentBorder, plan->gather);
+      plan->gatherBuilt = true;
+    }
+  } catch (const std::exception& ex) {
+    std::printf("Could not build the gather plan. Error: %s\n", ex.what());
+    return 0;
+  }
+  const t360::GatherPlan& g = plan->gather;
+  info[0] = g.tilesPerRow; info[1] = g.tileRows; info[2] = g.tileH; info[3] = static_cast<int>(g.jobs.size());
+  info[4] = g.numStaged[0]; info[5] = g.numStaged[1]; info[6] = g.numSeam; info[7] = g.numGeneral;
+  if (jobs) *jobs = g.jobs.empty() ? nullptr : reinterpret_cast<const int32_t*>(g.jobs.data());
+  if (records) *records = reinterpret_cast<const int32_t*>(g.records.data());
+  return 1;
 }
 T360_API int T360B200_hostPlanSegment(const T360HostPlan* plan, int i, int rect[4], int numTaps[2], const float** kx,
                                       const float** ky) {

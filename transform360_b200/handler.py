@@ -96,6 +96,8 @@ def load(path: os.PathLike | None = None):
     L.T360B200_hostPlanSamples.argtypes = [vp]
     L.T360B200_hostPlanSegment.restype = ci
     L.T360B200_hostPlanSegment.argtypes = [vp, ci, C.POINTER(ci), C.POINTER(ci), C.POINTER(vp), C.POINTER(vp)]
+    L.T360B200_hostPlanGather.restype = ci
+    L.T360B200_hostPlanGather.argtypes = [vp, C.POINTER(ci), C.POINTER(vp), C.POINTER(vp)]
     L.T360B200_remapTable.restype = ci
     L.T360B200_remapTable.argtypes = [ci, C.POINTER(vp)]
     L.T360B200_transformFramePlaneAsync.restype = ci
@@ -126,6 +128,7 @@ EXPORTED_SYMBOLS = [
     "VideoFrameTransform_new", "VideoFrameTransform_delete", "VideoFrameTransform_generateMapForPlane",
     "VideoFrameTransform_transformFramePlane", "T360B200_hostPlanCreate", "T360B200_hostPlanDestroy",
     "T360B200_hostPlanInfo", "T360B200_hostPlanMap", "T360B200_hostPlanSamples", "T360B200_hostPlanSegment",
+    "T360B200_hostPlanGather",
     "T360B200_remapTable", "T360B200_transformFramePlaneAsync", "T360B200_transformFrameAsync",
     "T360B200_lowPassPlaneAsync",
     "T360B200_setPinHostPlanes", "T360B200_synchronize", "T360B200_stream", "T360B200_kernelLaunchCount", "T360B200_planDeviceBytes",
@@ -261,6 +264,23 @@ class HostPlan:
         p = self._lib.T360B200_hostPlanSamples(self._h)
         n = self.map_w * self.map_h * 2
         return np.frombuffer((C.c_int32 * n).from_address(p), np.int32).reshape(self.map_h, self.map_w, 2).copy()
+
+    def gather_plan(self):
+        """Jobs and record layout the persistent gather kernel works from (T360B200_hostPlanGather).  Returns a dict:
+        tiles_per_row, tile_rows, tile_h, counts {class0, class1, seam, general}, jobs int32[n][4] (None when the plan
+        is not staged), records int32[tiles][tile_h][32][2]."""
+        info = (C.c_int * 8)()
+        jobs, recs = C.c_void_p(), C.c_void_p()
+        if not self._lib.T360B200_hostPlanGather(self._h, info, C.byref(jobs), C.byref(recs)):
+            raise ValueError("T360B200_hostPlanGather failed")
+        tpr, trows, th, nj = info[0], info[1], info[2], info[3]
+        n = tpr * trows * th * 32 * 2
+        records = np.frombuffer((C.c_int32 * n).from_address(recs.value), np.int32).reshape(tpr * trows, th, 32, 2).copy()
+        j = None
+        if nj and jobs.value:
+            j = np.frombuffer((C.c_int32 * (nj * 4)).from_address(jobs.value), np.int32).reshape(nj, 4).copy()
+        return dict(tiles_per_row=tpr, tile_rows=trows, tile_h=th, jobs=j, records=records,
+                    counts=dict(class0=info[4], class1=info[5], seam=info[6], general=info[7]))
 
     def segments(self):
         out = []
