@@ -4,9 +4,27 @@
 #include <algorithm>
 #include <climits>
 #include <cstdint>
+#include <thread>
 
 namespace t360 {
 namespace {
+
+// fn(begin, end) over [0, n) on up to 32 host threads (the work items are independent and write disjoint outputs)
+template <class F>
+void parallelRanges(int n, size_t workPerItem, F fn) {
+  unsigned nt = std::thread::hardware_concurrency();
+  if (nt == 0) nt = 1;
+  if (nt > 32) nt = 32;
+  if (static_cast<size_t>(n) * workPerItem < (1u << 16)) nt = 1;
+  const int chunk = (n + static_cast<int>(nt) - 1) / static_cast<int>(nt);
+  std::vector<std::thread> pool;
+  for (unsigned t = 1; t < nt; ++t) {
+    const int b = static_cast<int>(t) * chunk, e = std::min(n, b + chunk);
+    if (b < e) pool.emplace_back(fn, b, e);
+  }
+  fn(0, std::min(n, chunk));
+  for (auto& th : pool) th.join();
+}
 
 // Device order of the sampling records.  Each row is cut into segments of 32 pixels (= the width of a gather
 // tile = one warp); inside a segment the pixels are dealt to LANES so that the lanes which one shared-memory pass
@@ -18,7 +36,8 @@ void buildLaneOrder(const HostPlan& h, std::vector<int2>& out, int tilesPerRow, 
   const int k = h.kernelSize;
   const int groups = weightBankGroups(k), lanesPerPass = weightLanesPerPass(k), passes = 32 / lanesPerPass;
   constexpr int kRows = 4;  // rows per thread: one lane order per 32 x 4 block, so that a thread keeps ONE column
-  for (int yb = 0; yb < h.mapH; yb += kRows) {
+  parallelRanges((h.mapH + kRows - 1) / kRows, static_cast<size_t>(h.mapW) * kRows, [&](int blockBegin, int blockEnd) {
+  for (int yb = blockBegin * kRows; yb < blockEnd * kRows; yb += kRows) {
     for (int x0 = 0; x0 < h.mapW; x0 += 32) {
       const int n = std::min(32, h.mapW - x0);
       int order[32];
@@ -57,6 +76,7 @@ void buildLaneOrder(const HostPlan& h, std::vector<int2>& out, int tilesPerRow, 
       }
     }
   }
+  });
 }
 
 // Splits the output plane into CTA tiles and finds, per tile, the bounding box of all source windows.  A tile is
@@ -65,11 +85,11 @@ void buildLaneOrder(const HostPlan& h, std::vector<int2>& out, int tilesPerRow, 
 void buildGatherTiles(const HostPlan& h, GatherPlan& d, std::vector<int>& seamBoxX) {
   const int k = h.kernelSize, tw = kGatherTileW, th = gatherTileH(k);
   const int tilesX = (h.mapW + tw - 1) / tw, tilesY = (h.mapH + th - 1) / th;
-  std::vector<StagedTile> staged[kNumBoxClasses];
-  std::vector<StagedTile> fallback, seam;
   // seam tiles need whole 16-byte columns on both sides of the border and a plane much wider than the box
   const bool seamPossible = h.inW % 16 == 0 && h.inW >= 4 * stageBoxW(k, 0);
-  for (int ty = 0; ty < tilesY; ++ty)
+  std::vector<StagedTile> perTile(static_cast<size_t>(tilesX) * tilesY);  // classified in parallel, collected in raster order
+  parallelRanges(tilesY, static_cast<size_t>(h.mapW) * th, [&](int tyBegin, int tyEnd) {
+  for (int ty = tyBegin; ty < tyEnd; ++ty)
     for (int tx = 0; tx < tilesX; ++tx) {
       int minC = INT32_MAX, maxC = INT32_MIN, minR = INT32_MAX, maxR = INT32_MIN;
       const int y1 = std::min(h.mapH, (ty + 1) * th), x1 = std::min(h.mapW, (tx + 1) * tw);
@@ -116,15 +136,23 @@ void buildGatherTiles(const HostPlan& h, GatherPlan& d, std::vector<int>& seamBo
         const int bx = first & ~15;
         if (hi - lo + (first - bx) + k <= stageBoxW(k, 0) && bx + stageBoxW(k, 0) > W) wrappedBoxX = bx;
       }
+      StagedTile& job = perTile[static_cast<size_t>(ty) * tilesX + tx];
       if (cls >= 0) {
-        staged[cls].push_back(StagedTile{tx * tw, ty * th | (cls << kJobKindShift), boxX | (minR << 16), shareMask});
+        job = StagedTile{tx * tw, ty * th | (cls << kJobKindShift), boxX | (minR << 16), shareMask};
       } else if (wrappedBoxX >= 0) {
-        seam.push_back(StagedTile{tx * tw, ty * th | (kJobSeam << kJobKindShift), wrappedBoxX | (minR << 16), shareMask});
+        job = StagedTile{tx * tw, ty * th | (kJobSeam << kJobKindShift), wrappedBoxX | (minR << 16), shareMask};
         seamBoxX[static_cast<size_t>(ty) * tilesX + tx] = wrappedBoxX;
       } else {
-        fallback.push_back(StagedTile{tx * tw, ty * th | (kJobGeneral << kJobKindShift), 0, 0});
+        job = StagedTile{tx * tw, ty * th | (kJobGeneral << kJobKindShift), 0, 0};
       }
     }
+  });
+  std::vector<StagedTile> staged[kNumBoxClasses];
+  std::vector<StagedTile> fallback, seam;
+  for (const StagedTile& job : perTile) {
+    const int kind = (job.outY >> kJobKindShift) & kJobKindMask;
+    (kind == kJobGeneral ? fallback : kind == kJobSeam ? seam : staged[kind]).push_back(job);
+  }
   // order: general tiles, seam tiles, then the wide-box class, then the common class (see gatherFrameKernel)
   d.numGeneral = static_cast<int>(fallback.size());
   d.numSeam = static_cast<int>(seam.size());
