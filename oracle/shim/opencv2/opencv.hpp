@@ -161,6 +161,9 @@ class Mat {
  private:
   static size_t esz(int type) { return type == CV_8U ? 1 : (type == CV_32F ? 4 : 8); }
   void create(int r, int c, int type) {
+    // OpenCV refuses negative sizes (cv::Mat::create -> CV_Assert / error -211); the reference then returns false, e.g.
+    // when a band's horizontal sigma comes out negative because cosf(angle) is -4e-8 at the pole (cpp:219, 78-81)
+    if (r < 0 || c < 0) throw std::runtime_error("shim cv::Mat: negative size");
     rows = r; cols = c; type_ = type;
     step = esz(type) * static_cast<size_t>(c);
     size_t bytes = step * static_cast<size_t>(r);

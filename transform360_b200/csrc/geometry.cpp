@@ -16,6 +16,7 @@
 //   -> eye re-pack.
 #include <cmath>
 #include <cstdio>
+#include <algorithm>
 #include <thread>
 #include <vector>
 
@@ -164,15 +165,18 @@ class Projector {
     switch (c_.output_layout) {
       case LAYOUT_CUBEMAP_32:
       case LAYOUT_EAC_32: {  // cpp:943-950, 1069-1078
+        // (x == 1 happens: the centre column of a side-by-side stereo output of odd width folds to exactly 1.  The
+        // reference then switches on a face number past BACK and uses an uninitialised face basis; here, as in
+        // oracle/t360_oracle.c, such a pixel takes the last face's basis -- DESIGN.md 7.)
         const int row = static_cast<int>(y * 2), col = static_cast<int>(x * 3);
         float fx = x * 3.0f - col, fy = y * 2.0f - row;
         if (c_.output_layout == LAYOUT_EAC_32) { fx = equiAngular(fx); fy = equiAngular(fy); }
-        q = onCube(kFrames32, col + (1 - row) * 3, fx, fy);
+        q = onCube(kFrames32, std::min(std::max(col + (1 - row) * 3, 0), 5), fx, fy);
         return true;
       }
       case LAYOUT_CUBEMAP_23_OFFCENTER: {  // cpp:951-958
         const int row = static_cast<int>(y * 3), col = static_cast<int>(x * 2);
-        q = onCube(kFrames23, col + (2 - row) * 2, x * 2.0f - col, y * 3.0f - row);
+        q = onCube(kFrames23, std::min(std::max(col + (2 - row) * 2, 0), 5), x * 2.0f - col, y * 3.0f - row);  // see above
         return true;
       }
       case LAYOUT_EQUIRECT:  // cpp:965-969

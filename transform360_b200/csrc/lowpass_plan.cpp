@@ -11,6 +11,8 @@
 #include <cmath>
 #include <cstdio>
 
+#include <stdexcept>
+
 #include "host_plan.h"
 
 namespace t360 {
@@ -25,6 +27,9 @@ std::pair<int, int> appendGaussian(std::vector<float>& pool, float sigma) {
   const int half = static_cast<int>(sigma * 2);
   const int n = half * 2 + 1;
   const int offset = static_cast<int>(pool.size());
+  // (sigma can come out hugely negative: sigma_x = sigma_y / (cosf(angle) + 1e-9) and cosf is -4e-8 at the pole; the
+  // reference's cv::Mat::zeros(1, negative) throws there and generateMapForPlane returns 0 -- same here)
+  if (n <= 0) throw std::runtime_error("low-pass kernel with a negative number of taps (negative sigma)");
   pool.resize(pool.size() + static_cast<size_t>(n));
   float* k = pool.data() + offset;
   float total = 0;
