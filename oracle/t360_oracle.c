@@ -579,6 +579,16 @@ static int border_idx(int p, int n, int border) {
   return -1; /* constant */
 }
 
+/* cvRound(float) as OpenCV computes it on x86 (cvtss2si / cvtps2dq, also in its SIMD paths): round half to even, and
+ * the "integer indefinite" value INT_MIN for NaN and for values outside the int range.  It matters: an off-centre
+ * projection with is_horizontal_offset divides by zero at the poles (ref:1203-1206), the map holds NaN there, and
+ * cv::remap then samples column/row sat16(INT_MIN >> 5) = -32768 under BORDER_WRAP (pinned against cv2 in
+ * tests/test_oracle_pin.py). */
+static int cv_round_f32(float v) {
+  if (!(v >= -2147483648.0f && v < 2147483648.0f)) return (-2147483647 - 1);
+  return (int)lrintf(v);
+}
+
 static int sat_i16(int v) { return v < -32768 ? -32768 : (v > 32767 ? 32767 : v); }
 
 void t360o_remap_u8(const uint8_t* src, int sw, int sh, size_t spitch, uint8_t* dst, int dw, int dh, size_t dpitch,
@@ -595,7 +605,7 @@ void t360o_remap_u8(const uint8_t* src, int sw, int sh, size_t spitch, uint8_t* 
     for (int dx = 0; dx < dw; dx++) {
       float fx = M[dx * 2], fy = M[dx * 2 + 1];
       if (k == 1) {
-        int sx = sat_i16((int)lrintf(fx)), sy = sat_i16((int)lrintf(fy));
+        int sx = sat_i16(cv_round_f32(fx)), sy = sat_i16(cv_round_f32(fy));
         if ((unsigned)sx < (unsigned)sw && (unsigned)sy < (unsigned)sh) {
           D[dx] = src[(size_t)sy * spitch + sx];
         } else if (border == T360O_BORDER_TRANSPARENT) {
@@ -609,7 +619,7 @@ void t360o_remap_u8(const uint8_t* src, int sw, int sh, size_t spitch, uint8_t* 
         }
         continue;
       }
-      int X = (int)lrintf(fx * 32.0f), Y = (int)lrintf(fy * 32.0f);
+      int X = cv_round_f32(fx * 32.0f), Y = cv_round_f32(fy * 32.0f);
       int a = (Y & 31) * 32 + (X & 31);
       int sx = sat_i16(X >> 5) - (k / 2 - 1), sy = sat_i16(Y >> 5) - (k / 2 - 1);
       const int16_t* w = itab + (size_t)a * k * k;

@@ -341,6 +341,28 @@ def test_frame_entry_point_survives_map_regeneration(torch_cuda):
     ft.close()
 
 
+def test_nan_map_entries_sample_like_opencv(torch_cuda):
+    """Off-centre + is_horizontal_offset divides by zero at the poles (ref:1203-1206): the map holds NaN for a few
+    pixels, which cv::remap rounds to INT_MIN and saturates to column / row -32768 under BORDER_WRAP.  Parameters
+    found by the random sweep against the compiled reference (tests/test_host_plan.py)."""
+    ov = dict(input_layout=3, output_layout=6, input_stereo_format=1, output_stereo_format=1, input_expand_coef=1.03,
+              expand_coef=1.01, interpolation_alg=2, fixed_yaw=-164.79200291974115, fixed_pitch=13.155720951654928,
+              fixed_roll=-42.12975619832986, fixed_cube_offcenter_x=0.2557402424642103, fixed_cube_offcenter_y=-0.15772665724832016,
+              fixed_cube_offcenter_z=-0.41284091691208313, is_horizontal_offset=1, enable_low_pass_filter=0)
+    iw, ih, ow, oh = 194, 240, 198, 142
+    for interp in (t360.NEAREST, t360.LINEAR, t360.CUBIC, t360.LANCZOS4):
+        ov["interpolation_alg"] = interp
+        ctx, octx = t360.make_context(**ov), rh.default_context(**ov)
+        plan = co.OraclePlan(octx, iw, ih, ow, oh)
+        assert np.isnan(plan.map).any(), "this case is here for its NaN map entries"
+        src = co.noise_plane(iw, ih, plane=0, frame=3)
+        want = co.transform_plane(octx, plan, src, ow, oh, map_index=0)
+        with t360.VideoFrameTransform(ctx) as vft:
+            assert vft.generateMapForPlane(iw, ih, ow, oh, 0)
+            got = vft.transform_plane(src, ow, oh, 0)
+        assert np.array_equal(got, want), f"interp {interp}: {(got != want).sum()} px differ"
+
+
 def _rank_worker(rank, world, port, q):
     import os
     import torch

@@ -90,6 +90,39 @@ def test_remap_arithmetic_vs_cv2(interp):
     assert np.array_equal(got, want)
 
 
+@pytest.mark.parametrize("border", [cv2.BORDER_WRAP, cv2.BORDER_TRANSPARENT])
+@pytest.mark.parametrize("interp", [rh.NEAREST, rh.LINEAR, rh.CUBIC, rh.LANCZOS4])
+def test_remap_of_nan_and_out_of_range_coordinates_vs_cv2(interp, border):
+    """Maps can hold NaN (off-centre + is_horizontal_offset divides by zero at the poles, ref:1203-1206) and values far
+    outside the int range: cv2 rounds them to INT_MIN (cvtss2si) before saturating to 16 bits.  Bit-exact."""
+    rng = np.random.default_rng(5 + interp)
+    src = rng.integers(0, 256, (97, 131), dtype=np.uint8)
+    m = np.empty((64, 96, 2), np.float32)
+    m[..., 0] = rng.uniform(-9, 140, (64, 96))
+    m[..., 1] = rng.uniform(-9, 106, (64, 96))
+    specials = [np.nan, np.inf, -np.inf, 1e12, -1e12, 3e9, -3e9, 2147483648.0, -2147483648.0, 7e7, -7e7, 1e6, -1e6, 40000.5, -40000.5]
+    k = 0
+    for yy in range(0, 64, 4):
+        for xx in range(0, 96, 3):
+            v = specials[k % len(specials)]
+            k += 1
+            if k % 3 == 0:
+                m[yy, xx, 0] = v
+            elif k % 3 == 1:
+                m[yy, xx, 1] = v
+            else:
+                m[yy, xx] = v
+    if border == cv2.BORDER_TRANSPARENT:
+        want = np.full((64, 96), 77, np.uint8)
+        cv2.remap(src, m, None, interp, dst=want, borderMode=border)
+        got = np.full((64, 96), 77, np.uint8)
+        co.remap_u8(src, m, interp, 5, dst=got)
+    else:
+        want = cv2.remap(src, m, None, interp, borderMode=border)
+        got = co.remap_u8(src, m, interp, 3)
+    assert np.array_equal(got, want)
+
+
 @pytest.mark.parametrize("interp", [rh.NEAREST, rh.LINEAR, rh.CUBIC, rh.LANCZOS4])
 def test_remap_transparent_vs_cv2(interp):
     rng = np.random.default_rng(99 + interp)

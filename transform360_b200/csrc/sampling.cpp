@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
+#include <cstdint>
 #include <cstdio>
 #include <memory>
 #include <mutex>
@@ -22,7 +23,14 @@ namespace {
 constexpr int kFracBits = 5, kPhases1D = 1 << kFracBits, kPhases2D = kPhases1D * kPhases1D;
 constexpr int kWeightOne = 1 << 15;
 
-inline int roundHalfEven(float v) { return static_cast<int>(std::lrintf(v)); }  // default FP environment
+// cvRound(float) as OpenCV computes it on x86 (cvtss2si, also in its SIMD paths): round half to even in the default FP
+// environment, and INT_MIN ("integer indefinite") for NaN and for values outside the int range.  It matters: an
+// off-centre projection with is_horizontal_offset divides by zero at the poles (reference cpp:1203-1206), the map
+// holds NaN there, and cv::remap samples column / row sat16(INT_MIN >> 5) = -32768 under BORDER_WRAP.
+inline int roundHalfEven(float v) {
+  if (!(v >= -2147483648.0f && v < 2147483648.0f)) return INT32_MIN;
+  return static_cast<int>(std::lrintf(v));
+}
 inline int clampToShort(int v) { return v < -32768 ? -32768 : (v > 32767 ? 32767 : v); }
 
 // 1-D interpolation kernels at offset t in [0,1): taps for positions -(k/2-1) .. k/2
