@@ -214,3 +214,42 @@ def test_oracle_vs_live_reference(name):
         got = co.transform_plane(ctx, plan, src, ow, oh, map_index=idx, prefill=9 if barrel else 0)
         assert np.array_equal(got, want)
     ref.close()
+
+
+@pytest.mark.skipif(not rh.ref_available(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("seed", [11, 12])
+def test_random_end_to_end_sweep_against_the_live_reference(seed):
+    """Random contexts over the whole option space, end to end: the C restatement must produce the bytes the reference's
+    own object code + cv2 produce.  (1300 cases of this sweep, offline, found the NaN-coordinate rule pinned above; the
+    only remaining difference is the centre column of side-by-side stereo outputs of odd render width, where the
+    reference reads an uninitialised face basis -- those contexts are skipped here)"""
+    from tests.test_host_plan import _random_context
+    rng = np.random.default_rng(1000 + seed)
+    compared = 0
+    for _ in range(25):
+        ov = _random_context(rng)
+        iw, ih = int(rng.integers(64, 300)) * 2, int(rng.integers(32, 150)) * 2
+        ow, oh = int(rng.integers(24, 120)) * 2 + int(rng.random() < 0.25), int(rng.integers(16, 90)) * 2 + int(rng.random() < 0.25)
+        idx = int(rng.integers(0, 2))
+        ctx = rh.default_context(**ov)
+        sw, _ = co.scaled_dims(ctx, ow, oh)
+        if ov["input_stereo_format"] != rh.STEREO_FORMAT_MONO and ov["output_stereo_format"] == rh.STEREO_FORMAT_LR and sw % 2 == 1:
+            continue
+        ref = rh.RefTransform(ctx)
+        if not ref.generate_map(iw, ih, ow, oh, idx):
+            ref.close()
+            continue
+        plan = co.OraclePlan(ctx, iw, ih, ow, oh)
+        src = co.noise_plane(iw, ih, plane=idx, frame=seed)
+        pre = 9 if ctx.output_layout in (rh.LAYOUT_BARREL, rh.LAYOUT_BARREL_SPLIT) else 0
+        try:
+            want = ref.transform_plane(src, ow, oh, idx, image_plane=idx, prefill=pre)
+            got = co.transform_plane(ctx, plan, src, ow, oh, map_index=idx, prefill=pre)
+        except RuntimeError:  # scale factors < 1 are not restated (INTER_AREA enlarging)
+            ref.close()
+            continue
+        assert np.array_equal(got, want), f"{(got != want).sum()} px differ for {ov} {(iw, ih, ow, oh)} plan {idx}"
+        compared += 1
+        ref.close()
+    assert compared >= 15
+
