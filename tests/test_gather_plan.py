@@ -135,3 +135,26 @@ def test_tile_counts_of_the_headline_plan():
     for plane, want in ((0, dict(class0=8808, class1=432, seam=112, general=248)), (1, dict(class0=2168, class1=104, seam=56, general=72))):
         _, hp, _, _ = _plan(FULL["cfg2"], plane)
         assert hp.gather_plan()["counts"] == want
+
+
+def test_gather_plan_invariants_on_random_contexts():
+    """The same invariants over random contexts (all layouts, stereo, rotation, off-centre incl. NaN map entries, scale
+    factors, odd sizes, input widths with and without whole 16-byte columns)."""
+    from tests.test_host_plan import _random_context
+    rng = np.random.default_rng(500)
+    checked = 0
+    for _ in range(30):
+        ov = _random_context(rng)
+        iw, ih = int(rng.integers(200, 700)) * 2, int(rng.integers(100, 300)) * 2
+        ow, oh = int(rng.integers(40, 200)) * 2 + int(rng.random() < 0.3), int(rng.integers(30, 150)) * 2 + int(rng.random() < 0.3)
+        if rng.random() < 0.5:
+            iw = (iw + 15) // 16 * 16
+        SMALL["__random"] = dict(ov=ov, inp=(iw, ih), out=(ow, oh))
+        try:
+            test_gather_plan_invariants("small", "__random", int(rng.integers(0, 2)))
+            checked += 1
+        except ValueError:  # the planner refuses what the reference refuses
+            pass
+        finally:
+            SMALL.pop("__random", None)
+    assert checked >= 25
