@@ -243,7 +243,7 @@ def main():
         gframe = rank + f * world  # global frame index handled by this rank (round-robin sharding)
         planes = []
         for p in range(3):
-            iw, ih, ow, oh, _ = spec.plane_dims(p)
+            iw, ih = spec.plane_dims(p)[:2]
             planes.append(synth.noise_plane_torch(iw, ih, plane=p, frame=gframe, device=dev, pitch=pitch(iw)))
         d_in.append(planes)
     for f in range(2):
@@ -255,7 +255,6 @@ def main():
     tstream = torch.cuda.Stream(device=dev)
     stream = tstream.cuda_stream
     assert stream != 0
-    liw, lih, low, loh, _ = spec.plane_dims(0)
 
     def barrier():
         torch.cuda.synchronize()
