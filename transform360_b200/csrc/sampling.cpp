@@ -14,6 +14,8 @@
 #include <cstdio>
 #include <memory>
 #include <mutex>
+#include <thread>
+#include <vector>
 
 #include "host_plan.h"
 
@@ -122,7 +124,14 @@ void quantizeWarpMap(HostPlan& plan) {
   const size_t n = static_cast<size_t>(plan.mapW) * plan.mapH;
   plan.samples.resize(n);
   const float* m = plan.map.data();
-  for (size_t i = 0; i < n; ++i) {
+  // independent per pixel: rows are split over up to 32 host threads like the warp map itself
+  unsigned nt = std::thread::hardware_concurrency();
+  if (nt == 0) nt = 1;
+  if (nt > 32) nt = 32;
+  if (n < (1u << 16)) nt = 1;
+  const size_t chunk = (n + nt - 1) / nt;
+  auto range = [&plan, m, k](size_t begin, size_t end) {
+  for (size_t i = begin; i < end; ++i) {
     const float fx = m[2 * i], fy = m[2 * i + 1];
     SamplePoint s;
     if (k == 1) {
@@ -136,6 +145,12 @@ void quantizeWarpMap(HostPlan& plan) {
     }
     plan.samples[i] = s;
   }
+  };
+  std::vector<std::thread> pool;
+  for (unsigned t = 1; t < nt; ++t)
+    if (t * chunk < n) pool.emplace_back(range, t * chunk, std::min(n, (t + 1) * chunk));
+  range(0, std::min(n, chunk));
+  for (auto& th : pool) th.join();
 }
 
 namespace {
