@@ -235,3 +235,22 @@ def test_random_parameter_sweep_against_the_compiled_reference(seed):
         ref.close()
         hp.close()
     assert compared >= 40
+
+
+@pytest.mark.skipif(not rh.ref_available(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("nh,adjust", [(0, 1), (-2, 1), (0, 0), (-3, 0)])
+def test_non_positive_horizontal_segment_counts_follow_the_reference(nh, adjust):
+    """Not an error in the reference: with adjust_kernel its tile loop does not run (no tiles: the low-pass output stays
+    zero), without adjust_kernel the value is ignored (cpp:224-235)."""
+    ov = dict(interpolation_alg=2, enable_low_pass_filter=1, num_vertical_segments=5, num_horizontal_segments=nh, adjust_kernel=adjust)
+    ctx, rctx = t360.make_context(**ov), rh.default_context(**ov)
+    ref = rh.RefTransform(rctx)
+    assert ref.generate_map(320, 160, 96, 64, 0)
+    hp = t360.HostPlan(ctx, 320, 160, 96, 64)
+    a, b = hp.segments(), ref.segments(0)
+    assert len(a) == len(b) == (0 if adjust else 5)
+    for s, r in zip(a, b):
+        assert s[:4] == r[:4] and np.array_equal(s[4].view(np.uint32), r[4].view(np.uint32)) and np.array_equal(s[5].view(np.uint32), r[5].view(np.uint32))
+    assert np.array_equal(hp.map.view(np.uint32), ref.map(0).view(np.uint32))
+    ref.close()
+    hp.close()

@@ -85,6 +85,7 @@ class BandWalker {
     const float sigmaX = static_cast<float>(std::min(0.5 * w_, sigmaY_ / (std::cos(angle) + kTiny)));
     const std::pair<int, int> baseKx = appendGaussian(plan_.taps, sigmaX);
     const int columns = c_.adjust_kernel ? c_.num_horizontal_segments : 1;
+    if (columns <= 0) return;  // the reference's loop (cpp:235) does not run: a band without tiles
     const int tileW = static_cast<int>(std::ceil(1.0 * w_ / columns));
     for (int i = 0; i < columns && i * tileW < w_; ++i) {
       LowPassSegment s{};

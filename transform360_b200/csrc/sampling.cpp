@@ -216,8 +216,11 @@ bool buildHostPlan(const FrameTransformContext& ctx, int inW, int inH, int outW,
   if (plan.kernelSize > 0) quantizeWarpMap(plan);
   buildAreaResizePlan(plan);
   if (ctx.enable_low_pass_filter) {
-    if (ctx.num_vertical_segments < 1 || ctx.num_horizontal_segments < 1) {
-      std::printf("Could not generate map: segment counts must be positive.\n");
+    // (num_horizontal_segments <= 0 is not an error in the reference: with adjust_kernel its tile loop simply does not
+    // run, cpp:235, so every band is left without tiles and the "blurred" plane stays zero; without adjust_kernel the
+    // value is ignored, cpp:224-225.  num_vertical_segments <= 0 divides by zero there; refused here.)
+    if (ctx.num_vertical_segments < 1) {
+      std::printf("Could not generate map: num_vertical_segments must be positive.\n");
       return false;
     }
     if (!buildLowPassPlan(plan)) return false;
