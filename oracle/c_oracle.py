@@ -148,7 +148,7 @@ def transform_plane(ctx, plan: OraclePlan, src: np.ndarray, out_w, out_h, map_in
                                      dst.ctypes.data, out_w, out_h, dst.strides[0], plan.map.ctypes.data, mw, mh,
                                      map_index, plan.segs, plan.nsegs, plan.taps.ctypes.data)
     if not ok:
-        raise RuntimeError("oracle: the area resize would enlarge (scale factor < 1): not restated")
+        raise RuntimeError("oracle: t360o_transform_plane failed")
     return dst
 
 

@@ -756,9 +756,66 @@ static int area_tab(int ssize, int dsize, double scale, AreaTap* tab) {
   return k;
 }
 
+/* cv::resize(INTER_AREA) when at least one axis ENLARGES (scale < 1): OpenCV 4.x imgproc/resize.cpp emulates it with its
+ * 8-bit fixed-point bilinear kernel and "area mode" coefficients on BOTH axes:
+ *   sx = floor(dx * scale);  fx = (float)((dx + 1) - (sx + 1) * inv_scale);  fx = fx <= 0 ? 0 : fx - floor(fx)
+ *   (clamped at the last source sample; dx >= xmax copies S[sx] * 2048), coefficients = cvRound({1 - fx, fx} * 2048),
+ *   rows:    H[dx] = S[sx] * a0 + S[sx + 1] * a1                                  (HResizeLinear, int)
+ *   columns: dst   = (((b0 * (H0 >> 4)) >> 16) + ((b1 * (H1 >> 4)) >> 16) + 2) >> 2   (VResizeLinear<uchar> specialisation)
+ * Pinned bit-exact against cv2 4.13 in tests/test_oracle_pin.py (the reference reaches it with *_scale_factor < 1,
+ * ref:755-777). */
+static void area_linear_axis(int dn, int sn, double scale, double inv, int* ofs, short* coef, int* dmax) {
+  *dmax = dn;
+  for (int d = 0; d < dn; d++) {
+    int s = (int)floor(d * scale);
+    float f = (float)((d + 1) - (s + 1) * inv);
+    f = f <= 0 ? 0.f : f - (float)floor(f);
+    if (s < 0) { f = 0; s = 0; }
+    if (s + 1 >= sn) {
+      if (d < *dmax) *dmax = d;
+      if (s >= sn - 1) { f = 0; s = sn - 1; }
+    }
+    ofs[d] = s;
+    long c0 = lrintf((1.f - f) * 2048.f), c1 = lrintf(f * 2048.f);
+    coef[2 * d] = (short)(c0 > 32767 ? 32767 : c0);
+    coef[2 * d + 1] = (short)(c1 > 32767 ? 32767 : c1);
+  }
+}
+
+static int resize_area_enlarge_u8(const uint8_t* src, int sw, int sh, size_t spitch, uint8_t* dst, int dw, int dh, size_t dpitch) {
+  const double inv_x = (double)dw / sw, inv_y = (double)dh / sh, scale_x = 1.0 / inv_x, scale_y = 1.0 / inv_y;
+  int* xofs = (int*)malloc(sizeof(int) * ((size_t)dw + dh));
+  int* yofs = xofs + dw;
+  short* xa = (short*)malloc(sizeof(short) * 2 * ((size_t)dw + dh));
+  short* yb = xa + 2 * (size_t)dw;
+  int* rows = (int*)malloc(sizeof(int) * 2 * (size_t)dw);
+  int xmax, ymax;
+  area_linear_axis(dw, sw, scale_x, inv_x, xofs, xa, &xmax);
+  area_linear_axis(dh, sh, scale_y, inv_y, yofs, yb, &ymax);
+  for (int dy = 0; dy < dh; dy++) {
+    for (int k = 0; k < 2; k++) {
+      int sy = yofs[dy] + k;
+      sy = sy < 0 ? 0 : (sy > sh - 1 ? sh - 1 : sy);
+      const uint8_t* S = src + (size_t)sy * spitch;
+      int* H = rows + (size_t)k * dw;
+      for (int dx = 0; dx < dw; dx++) {
+        const int sx = xofs[dx];
+        H[dx] = dx < xmax ? S[sx] * xa[2 * dx] + S[sx + 1] * xa[2 * dx + 1] : S[sx] * 2048;
+      }
+    }
+    const int b0 = yb[2 * dy], b1 = yb[2 * dy + 1];
+    for (int dx = 0; dx < dw; dx++) {
+      const int v = (((b0 * (rows[dx] >> 4)) >> 16) + ((b1 * (rows[dw + dx] >> 4)) >> 16) + 2) >> 2;
+      dst[(size_t)dy * dpitch + dx] = (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v));
+    }
+  }
+  free(rows); free(xa); free(xofs);
+  return 1;
+}
+
 int t360o_resize_area_u8(const uint8_t* src, int sw, int sh, size_t spitch, uint8_t* dst, int dw, int dh, size_t dpitch) {
   const double scale_x = 1.0 / ((double)dw / sw), scale_y = 1.0 / ((double)dh / sh); /* cv::resize: 1./inv_scale */
-  if (scale_x < 1.0 || scale_y < 1.0) return 0;
+  if (scale_x < 1.0 || scale_y < 1.0) return resize_area_enlarge_u8(src, sw, sh, spitch, dst, dw, dh, dpitch);
   const int isx = (int)lrint(scale_x), isy = (int)lrint(scale_y);
   if (fabs(scale_x - isx) < DBL_EPSILON && fabs(scale_y - isy) < DBL_EPSILON) { /* resizeAreaFast_ */
     const int area = isx * isy;
@@ -813,7 +870,6 @@ int t360o_transform_plane(const T360OContext* c, const uint8_t* src, int inW, in
   int interp = c->interpolation_alg;
   if (t360o_remap_ksize(interp) == 0) return 1; /* ref:780-784: prints, still returns true */
   const int needResize = outW != mapW || outH != mapH; /* ref:735-737 */
-  if (needResize && (mapW < outW || mapH < outH)) return 0;
   const int barrel = c->output_layout == T360O_BARREL || c->output_layout == T360O_BARREL_SPLIT;
   int border = barrel ? T360O_BORDER_TRANSPARENT : T360O_BORDER_WRAP;
   const uint8_t* in = src;

@@ -163,6 +163,39 @@ def test_area_resize_vs_cv2(dims):
     assert np.array_equal(co.resize_area(src, dw, dh), cv2.resize(src, (dw, dh), interpolation=cv2.INTER_AREA))
 
 
+def test_area_resize_enlarging_vs_cv2():
+    """cv::resize(INTER_AREA) with at least one enlarging axis (the reference reaches it with *_scale_factor < 1): OpenCV
+    falls back to its 8-bit fixed-point bilinear kernel with "area mode" coefficients.  300 random size pairs (shrinking,
+    enlarging, mixed, tiny), bit-exact."""
+    rng = np.random.default_rng(3)
+    for _ in range(300):
+        sw, sh = int(rng.integers(2, 200)), int(rng.integers(2, 150))
+        dw, dh = int(rng.integers(max(1, sw // 3), sw * 3 + 2)), int(rng.integers(max(1, sh // 3), sh * 3 + 2))
+        src = rng.integers(0, 256, (sh, sw), dtype=np.uint8)
+        assert np.array_equal(co.resize_area(src, dw, dh), cv2.resize(src, (dw, dh), interpolation=cv2.INTER_AREA)), (sw, sh, dw, dh)
+
+
+@pytest.mark.skipif(not rh.ref_available(), reason="oracle/_ref not built")
+def test_scale_factors_below_one_end_to_end_vs_live_reference():
+    """width/height_scale_factor < 1: render at the smaller map size, then INTER_AREA *up* (ref:755-777)."""
+    for ov, dims in ((dict(width_scale_factor=0.5, height_scale_factor=0.5, interpolation_alg=2), (320, 160, 96, 64)),
+                     (dict(width_scale_factor=0.75, height_scale_factor=1.0, interpolation_alg=1, enable_low_pass_filter=0), (256, 128, 96, 64)),
+                     (dict(width_scale_factor=2.0, height_scale_factor=0.6, interpolation_alg=4, output_layout=rh.LAYOUT_EAC_32), (300, 150, 60, 50)),
+                     (dict(width_scale_factor=0.9, height_scale_factor=0.8, interpolation_alg=0, output_layout=rh.LAYOUT_BARREL), (256, 128, 100, 40))):
+        ctx = rh.default_context(**ov)
+        iw, ih, ow, oh = dims
+        ref = rh.RefTransform(ctx)
+        for idx in (0, 1):
+            assert ref.generate_map(iw, ih, ow, oh, idx)
+            plan = co.OraclePlan(ctx, iw, ih, ow, oh)
+            src = co.noise_plane(iw, ih, plane=idx, frame=5)
+            pre = 9 if ctx.output_layout in (rh.LAYOUT_BARREL, rh.LAYOUT_BARREL_SPLIT) else 0
+            want = ref.transform_plane(src, ow, oh, idx, image_plane=idx, prefill=pre)
+            got = co.transform_plane(ctx, plan, src, ow, oh, map_index=idx, prefill=pre)
+            assert np.array_equal(got, want), (ov, idx)
+        ref.close()
+
+
 def test_itab_sums():
     for interp in (rh.LINEAR, rh.CUBIC, rh.LANCZOS4):
         t = co.build_itab(interp)
