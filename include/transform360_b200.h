@@ -30,12 +30,18 @@ const float* T360B200_hostPlanMap(const T360HostPlan* plan);
  * word1 = (first tap row << 10) | phase, phase = (fracY32 << 5) | fracX32 (0 for nearest). */
 const int32_t* T360B200_hostPlanSamples(const T360HostPlan* plan);
 /* The gather plan of the host plan (no GPU needed): how the output plane is cut into jobs for the persistent gather
- * kernel and how the sampling records are laid out for it.  info = {tilesPerRow, tileRows, tileH, numJobs,
- * jobs of box class 0, of box class 1, seam jobs, general jobs}; *jobs: numJobs x 4 ints {outX, outY | kind << 24,
- * boxX | boxY << 16, shareMask} in launch order (NULL when the plan is not staged: nearest neighbour, barrel layouts);
- * *records: tilesPerRow * tileRows * tileH * 32 pairs {col0 | column << 27, row0 << 10 | phase}, tile-major.
- * Returns 1 on success.  The pointers stay valid until T360B200_hostPlanDestroy. */
-int T360B200_hostPlanGather(T360HostPlan* plan, int info[8], const int32_t** jobs, const int32_t** records);
+ * kernel and how the sampling records are laid out for it (formats: csrc/kernels.cuh).  info = {tilesPerRow, tileRows,
+ * tileH of the full records, numJobs, class-0 jobs, class-1 jobs, seam jobs, general jobs, share jobs, words of compact
+ * records}; *jobs: numJobs x 4 ints {outX, outY | kind << 24, boxX | boxY << 16, recordOffset (16-byte units)} in launch
+ * order (NULL when the plan is not staged: nearest neighbour, barrel layouts); *records: the full records,
+ * tilesPerRow * tileRows * tileH * 32 pairs {col0 | column << 27, row0 << 10 | phase}, tile-major; *compact: the compact
+ * records of the staged jobs (32-bit words).  Returns 1 on success.  The pointers stay valid until
+ * T360B200_hostPlanDestroy. */
+int T360B200_hostPlanGather(T360HostPlan* plan, int info[10], const int32_t** jobs, const int32_t** records,
+                            const uint32_t** compact);
+/* The frame kernel's shared-memory image of the interpolation table (csrc/kernels.cuh: "Weight tables in shared
+ * memory"); returns its size in bytes (0 if unsupported). */
+int T360B200_weightImage(int interpolationAlg, const uint8_t** image);
 /* low-pass segment i in the reference's order: rect = left, top, width, height; taps = kx then ky */
 int T360B200_hostPlanSegment(const T360HostPlan* plan, int i, int rect[4], int numTaps[2], const float** kx,
                              const float** ky);

@@ -1,11 +1,12 @@
 """CPU checks of the gather plan (job classification + record layout) the persistent CUDA gather kernel works from.
 
-The kernel trusts the host for everything it does not re-check on the device: that every window of a staged tile lies
+The kernel trusts the host for everything it does not re-check on the device: that every window of a staged job lies
 inside its TMA box, that a seam tile's box wraps around the left/right border and its records are re-based onto the
-unwrapped box, that the warps flagged in shareMask really keep their source column down their four rows, that a
-thread's four records sit in one output column, and that every output pixel has exactly one record.  All of that is
-host code (csrc/gather_plan.cpp) and is verified here without a GPU, against the plain row-major sampling records
-(T360B200_hostPlanSamples), which tests/test_host_plan.py pins against the reference.
+unwrapped box, that a share job's columns really keep their source column with row steps of 0-2, that the slot field
+of a record addresses the weights of the pixel's phase in the shared-memory image, and that every output pixel is
+produced exactly once.  All of that is host code (csrc/gather_plan.cpp) and is verified here without a GPU: the
+compact records are decoded exactly the way gather_frame.cu decodes them and compared with the plain row-major
+sampling records (T360B200_hostPlanSamples), which tests/test_host_plan.py pins against the reference.
 """
 import numpy as np
 import pytest
@@ -14,11 +15,24 @@ import transform360_b200 as t360
 from tests.golden.cases import FULL, SMALL, plane_dims
 
 KIND_SHIFT, PLANE_SHIFT, ROW_MASK = 24, 28, (1 << 24) - 1
-BOX_W = {0: 192, 1: 240}
+CLASS0, CLASS1, GENERAL, SEAM, SHARE = 0, 1, 2, 3, 4
+ORDER = {GENERAL: 0, SEAM: 1, CLASS1: 2, SHARE: 3, CLASS0: 4}
+SLOT_MASK = 0x7FF0
+INTERP = {2: t360.LINEAR, 4: t360.CUBIC, 8: t360.LANCZOS4}
 
 
-def box_h(k, cls):
-    return (112 if cls == 0 else 144) if k == 8 else (64 if cls == 0 else 96)
+def box_w(kind):
+    return 192 if kind == SHARE else (240 if kind == CLASS1 else 208)
+
+
+def box_h(k, kind):
+    if k == 8:
+        return 80 if kind == SHARE else (128 if kind == CLASS1 else 72)
+    return 72 if kind == SHARE else (96 if kind == CLASS1 else 64)
+
+
+def copies_of(k):
+    return 2 if k == 4 else 1
 
 
 def _plan(case, plane):
@@ -28,16 +42,64 @@ def _plan(case, plane):
     return ctx, hp, iw, ih
 
 
-def _unpack(records):
-    x, y = records[..., 0].astype(np.int64), records[..., 1].astype(np.int64)
-    col_in_seg = (x >> 27) & 31
+class WeightImage:
+    """Reads a pixel's weights the way the kernel does: vector v of the slot at byte v * stride + field."""
+
+    def __init__(self, k):
+        self.k = k
+        self.table = t360.remap_table(INTERP[k]).reshape(1024, k * k)
+        self.image = t360.weight_image(INTERP[k])
+        self.stride = (8192 if k == 2 else 16384) * copies_of(k)
+        assert self.image.size == (8192 if k == 2 else (k * k // 8) * 16384 * copies_of(k))
+
+    def weights_at(self, field):
+        """field: int array of record slot fields -> int16 [n][k*k]"""
+        field = np.asarray(field, np.int64)
+        img16 = self.image.view(np.int16)
+        if self.k == 2:
+            idx = (field >> 1)[:, None] // 2 + np.arange(4)[None, :]
+            return img16[idx]
+        nv = self.k * self.k // 8
+        idx = (field[:, None, None] + np.arange(nv)[None, :, None] * self.stride) // 2 + np.arange(8)[None, None, :]
+        return img16[idx].reshape(len(field), -1)
+
+    def check(self, field, phase):
+        assert ((np.asarray(field) & ~SLOT_MASK) == 0).all()
+        assert (self.weights_at(field) == self.table[np.asarray(phase)]).all(), "slot field does not address the pixel's weights"
+
+
+def _check_full_records(g, s, k):
+    """Full records (general kernels / general jobs): every pixel once, lane order constant inside a 32 x 4 block."""
+    mh, mw = s.shape[:2]
+    tpr, th = g["tiles_per_row"], g["tile_h"]
+    assert th == (64 if k == 8 else 32) and tpr == -(-mw // 32) and g["tile_rows"] == -(-mh // th)
+    x, y = g["records"][..., 0].astype(np.int64), g["records"][..., 1].astype(np.int64)
+    colseg = (x >> 27) & 31
     col0 = ((x & ((1 << 27) - 1)) ^ (1 << 26)) - (1 << 26)  # sign-extend 27 bits
-    return col_in_seg, col0, y >> 10, y & 1023
+    for ty in range(g["tile_rows"]):
+        for tx in range(tpr):
+            tile = ty * tpr + tx
+            y0, x0 = ty * th, tx * 32
+            hh, ww = min(th, mh - y0), min(32, mw - x0)
+            cs, c0, rp = colseg[tile, :hh], col0[tile, :hh], y[tile, :hh]
+            want = s[y0:y0 + hh, x0:x0 + ww]
+            if ww == 32:
+                assert (np.sort(cs, axis=1) == np.arange(32)).all(), "a row segment must hold every column once"
+                blk = cs[:hh // 4 * 4].reshape(-1, 4, 32)
+                assert (blk == blk[:, :1]).all(), "lane order must be constant inside a 32 x 4 block"
+                order = np.argsort(cs, axis=1)
+            else:
+                assert (cs[:, :ww] == np.arange(ww)).all() and (g["records"][tile, :hh, ww:] == 0).all()
+                order = np.argsort(cs[:, :ww], axis=1)
+            assert (np.take_along_axis(rp, order, axis=1)[:, :ww] == want[..., 1]).all()
+            assert (np.take_along_axis(c0, order, axis=1)[:, :ww] == want[..., 0]).all()
+            if hh < th:
+                assert (g["records"][tile, hh:] == 0).all(), "rows below the plane are padded with zero records"
 
 
 CASES = [("small", n, p) for n in ("cube_cubic", "cube_linear", "cube_lanczos", "cube_cubic_odd", "lp_tiles", "lr_stereo", "rotated",
-                                   "eac_tb_lanczos", "cube_to_equirect", "cfg1", "barrel") for p in (0, 1)] + \
-        [("full", "cfg2", 0), ("full", "cfg2", 1), ("full", "cfg4", 1)]
+                                   "eac_tb_lanczos", "eac_mono_cubic", "cube_to_equirect", "equirect_to_equirect_rot", "cfg1", "barrel")
+         for p in (0, 1)] + [("full", "cfg2", 0), ("full", "cfg2", 1), ("full", "cfg4", 1)]
 
 
 @pytest.mark.parametrize("group,name,plane", CASES)
@@ -48,93 +110,113 @@ def test_gather_plan_invariants(group, name, plane):
     g = hp.gather_plan()
     s = hp.samples.astype(np.int64)  # [mapH][mapW][2] = {col0, row0 << 10 | phase}, row-major
     mh, mw = s.shape[:2]
-    tpr, th = g["tiles_per_row"], g["tile_h"]
-    assert th == (64 if k == 8 else 32) and tpr == -(-mw // 32) and g["tile_rows"] == -(-mh // th)
-    colseg, col0, row0, phase = _unpack(g["records"])
+    _check_full_records(g, s, k)
 
-    # -- which tiles are re-based (seam), from the job list
     jobs = g["jobs"]
     staged_plan = k >= 2 and ctx.output_layout not in (t360.LAYOUT_BARREL, t360.LAYOUT_BARREL_SPLIT)
     assert (jobs is not None) == staged_plan
-    seam_box = {}
-    if jobs is not None:
-        cnt = g["counts"]
-        assert len(jobs) == tpr * g["tile_rows"] == cnt["class0"] + cnt["class1"] + cnt["seam"] + cnt["general"]
-        kinds = (jobs[:, 1] >> KIND_SHIFT) & 15
-        assert list(kinds) == sorted(kinds, key=lambda v: {2: 0, 3: 1, 1: 2, 0: 3}[int(v)]), "launch order: general, seam, class 1, class 0"
-        assert (np.bincount(kinds, minlength=4)[[0, 1, 3, 2]] == [cnt["class0"], cnt["class1"], cnt["seam"], cnt["general"]]).all()
-        assert ((jobs[:, 1] >> PLANE_SHIFT) == 0).all()
-        seen = set()
-        for ox, oy, boxxy, share in jobs:
-            tile = ((oy & ROW_MASK) // th) * tpr + ox // 32
-            assert tile not in seen and ox % 32 == 0 and (oy & ROW_MASK) % th == 0
-            seen.add(tile)
-            if (oy >> KIND_SHIFT) & 15 == 3:
-                seam_box[tile] = boxxy & 0xFFFF
-        assert len(seen) == len(jobs)
-
-    # -- every output pixel has exactly one record, with its own phase / row and (re-based) first column
-    for ty in range(g["tile_rows"]):
-        for tx in range(tpr):
-            tile = ty * tpr + tx
-            y0, x0 = ty * th, tx * 32
-            hh, ww = min(th, mh - y0), min(32, mw - x0)
-            cs, c0, r0, ph = colseg[tile, :hh], col0[tile, :hh], row0[tile, :hh], phase[tile, :hh]
-            want = s[y0:y0 + hh, x0:x0 + ww]
-            if ww == 32:
-                assert (np.sort(cs, axis=1) == np.arange(32)).all(), "a row segment must hold every column once"
-                # a thread (lane) keeps one output column through the four rows of its block
-                blk = cs[:hh // 4 * 4].reshape(-1, 4, 32)
-                assert (blk == blk[:, :1]).all(), "lane order must be constant inside a 32 x 4 block"
-            else:
-                assert (cs[:, :ww] == np.arange(ww)).all() and (g["records"][tile, :hh, ww:] == 0).all()
-            got_rowphase = np.take_along_axis((r0 << 10) | ph, np.argsort(cs[:, :ww] if ww < 32 else cs, axis=1), axis=1)[:, :ww]
-            got_col0 = np.take_along_axis(c0, np.argsort(cs[:, :ww] if ww < 32 else cs, axis=1), axis=1)[:, :ww]
-            assert (got_rowphase == want[..., 1]).all()
-            if tile in seam_box:
-                bx = seam_box[tile]
-                assert (got_col0 % iw == want[..., 0] % iw).all() and (got_col0 >= bx).all() and (got_col0 + k <= bx + BOX_W[0]).all()
-            else:
-                assert (got_col0 == want[..., 0]).all()
-            if hh < th:
-                assert (g["records"][tile, hh:] == 0).all(), "rows below the plane are padded with zero records"
-
     if jobs is None:
         return
-    # -- boxes and share masks
-    for ox, oy, boxxy, share in jobs:
-        kind, yy = (oy >> KIND_SHIFT) & 15, oy & ROW_MASK
-        blk = s[yy:yy + th, ox:ox + 32]
-        c, r = blk[..., 0], blk[..., 1] >> 10
+    cnt = g["counts"]
+    kinds = (jobs[:, 1] >> KIND_SHIFT) & 15
+    assert list(kinds) == sorted(kinds, key=lambda v: ORDER[int(v)]), "launch order: general, seam, class 1, share, class 0"
+    assert (np.bincount(kinds, minlength=5) == [cnt["class0"], cnt["class1"], cnt["general"], cnt["seam"], cnt["share"]]).all()
+    assert ((jobs[:, 1] >> PLANE_SHIFT) == 0).all()
+    if k < 4:
+        assert cnt["share"] == 0
+    wimg = WeightImage(k)
+    compact = g["compact"]
+    produced = np.zeros((mh, mw), np.int32)
+    next_offset = 0
+    for ox, oy, boxxy, rec_off in jobs:
+        kind, y0 = (oy >> KIND_SHIFT) & 15, oy & ROW_MASK
         bx, by = boxxy & 0xFFFF, boxxy >> 16
-        if kind in (0, 1):
-            assert bx % 16 == 0 and c.min() >= bx and c.max() + k <= bx + BOX_W[kind] and bx + BOX_W[kind] <= iw + BOX_W[kind]
-            assert c.min() >= 0 and c.max() + k <= iw, "a staged tile never needs BORDER_WRAP"
-            assert r.min() >= by >= 0 and r.max() + k <= by + box_h(k, kind) and r.max() + k <= ih
-        elif kind == 3:
-            assert iw % 16 == 0 and bx % 16 == 0 and bx < iw < bx + BOX_W[0], "the box of a seam tile wraps around the border"
-            rel = (c % iw - bx) % iw
-            assert rel.max() + k <= BOX_W[0] and r.min() >= by >= 0 and r.max() + k <= by + box_h(k, 0) and r.max() + k <= ih
-        if kind == 2:
-            assert boxxy == 0 and share == 0  # general tiles: taps through L1, nothing for the host to promise
+        assert ox % 32 == 0 and y0 % 32 == 0
+        if kind == GENERAL:
+            assert boxxy == 0 and rec_off == 0  # taps through L1 from the full records: nothing for the host to promise
+            produced[y0:y0 + 32, ox:ox + 32] += 1
             continue
-        # share mask: bit w <=> all four rows exist and every column keeps its first column, 1-2 source rows apart
-        for w in range(th // 4):
-            ya = yy + 4 * w
-            if k < 4 or ya + 4 > mh:
-                ok = False
-            else:
-                q = s[ya:ya + 4, ox:ox + 32]
-                d = np.diff(q[..., 1] >> 10, axis=0)
-                ok = bool(((d == 1) | (d == 2)).all() and (q[..., 0] == q[:1, :, 0]).all())
-            assert bool((share >> w) & 1) == ok, f"tile ({ox},{yy}) warp {w}"
+        pitch, bh = box_w(kind), box_h(k, kind)
+        assert bx % 16 == 0 and rec_off == next_offset, "records are laid out in launch order, 16-byte units"
+        if kind == SHARE:
+            assert ox % 64 == 0 and ox + 64 <= mw and y0 + 32 <= mh
+            words = compact[rec_off * 4:rec_off * 4 + 8 * 160].reshape(8, 160).astype(np.int64)
+            next_offset += 8 * 160 // 4
+            for w in range(8):
+                wx, wy = w & 1, w >> 1
+                px = words[w, :128].reshape(32, 4)      # [lane][word]
+                hdr = words[w, 128:]                    # [lane]
+                col, off = hdr >> 27, hdr & 0x3FFF
+                assert ((hdr & ((1 << 27) - 1)) == off).all() and (np.sort(col) == np.arange(32)).all()
+                rec = np.stack([px[:, j >> 1] >> (16 * (j & 1)) & 0xFFFF for j in range(8)], axis=1)  # [lane][row]
+                d, field = rec & 3, rec & SLOT_MASK
+                assert ((rec & ~(SLOT_MASK | 3)) == 0).all() and (d[:, 0] == 0).all() and (d <= 2).all()
+                row0 = by + off[:, None] // pitch + np.cumsum(d, axis=1)
+                col0 = bx + off % pitch
+                want = s[y0 + wy * 8:y0 + wy * 8 + 8, ox + wx * 32:ox + wx * 32 + 32]  # [row][column]
+                got_rows = np.empty((8, 32), np.int64); got_rows[:, col] = row0.T
+                got_cols = np.empty(32, np.int64); got_cols[col] = col0
+                got_field = np.empty((8, 32), np.int64); got_field[:, col] = field.T
+                assert (got_rows == want[..., 1] >> 10).all() and (got_cols[None, :] == want[..., 0]).all()
+                wimg.check(got_field.ravel(), (want[..., 1] & 1023).ravel())
+                # the whole column's windows stay inside the box and the plane
+                assert (col0 - bx + k <= pitch).all() and (row0[:, -1] - by + k <= bh).all() and (off < (1 << 14)).all()
+                assert (col0 >= 0).all() and (col0 + k <= iw).all() and (row0 >= 0).all() and (row0 + k <= ih).all()
+            produced[y0:y0 + 32, ox:ox + 64] += 1
+            continue
+        # 32 x 32 jobs: class 0, class 1, seam
+        words = compact[rec_off * 4:rec_off * 4 + 8 * 128].reshape(8, 32, 4).astype(np.int64)  # [warp][lane][row in warp]
+        next_offset += 8 * 128 // 4
+        w = words.transpose(0, 2, 1).reshape(32, 32)  # [row in tile][lane]
+        off, col, field = w & 0x7FFF, (w >> 16) & 31, (w >> 17) & SLOT_MASK
+        assert ((w >> 15) & 1 == 0).all()
+        hh, ww = min(32, mh - y0), min(32, mw - ox)
+        assert (np.sort(col, axis=1) == np.arange(32)).all(), "a row holds every column once (also the skipped ones)"
+        order = np.argsort(col, axis=1)
+        off, field = np.take_along_axis(off, order, axis=1)[:hh, :ww], np.take_along_axis(field, order, axis=1)[:hh, :ww]
+        want = s[y0:y0 + hh, ox:ox + ww]
+        row0, col0 = by + off // pitch, bx + off % pitch
+        assert (row0 == want[..., 1] >> 10).all()
+        wimg.check(field.ravel(), (want[..., 1] & 1023).ravel())
+        assert (off % pitch + k <= pitch).all() and (off // pitch + k <= bh).all() and (row0 >= 0).all() and (row0 + k <= ih).all()
+        if kind == SEAM:
+            assert iw % 16 == 0 and bx < iw < bx + pitch, "the box of a seam tile wraps around the border"
+            assert (col0 % iw == want[..., 0] % iw).all()
+        else:
+            assert (col0 == want[..., 0]).all() and (col0 >= 0).all() and (col0 + k <= iw).all(), "a staged tile never needs BORDER_WRAP"
+        produced[y0:y0 + hh, ox:ox + ww] += 1
+    assert (produced == 1).all(), "every output pixel belongs to exactly one job"
+    assert compact is None or next_offset * 4 == compact.size
 
 
-def test_tile_counts_of_the_headline_plan():
+def test_job_counts_of_the_headline_plan():
     """cfg2 (8K equirect -> 3840x2560 cubemap, bicubic): the numbers DESIGN.md quotes."""
-    for plane, want in ((0, dict(class0=8808, class1=432, seam=112, general=248)), (1, dict(class0=2168, class1=104, seam=56, general=72))):
+    for plane, want in ((0, dict(class0=2584, class1=416, seam=112, general=248, share=3120)),
+                        (1, dict(class0=664, class1=88, seam=56, general=72, share=760))):
         _, hp, _, _ = _plan(FULL["cfg2"], plane)
         assert hp.gather_plan()["counts"] == want
+
+
+def test_weight_bank_balance_of_the_headline_plan():
+    """The point of the second copy of the cubic table: modelled wavefronts of a 128-bit weight load (a quarter-warp of
+    8 lanes per pass, cost = the fullest 16-byte bank group) over the share jobs of the cfg2 luma plan."""
+    _, hp, _, _ = _plan(FULL["cfg2"], 0)
+    g = hp.gather_plan()
+    jobs, compact = g["jobs"], g["compact"]
+    share = jobs[((jobs[:, 1] >> KIND_SHIFT) & 15) == SHARE][::16]
+    total = n = 0
+    for ox, oy, boxxy, rec_off in share:
+        words = compact[rec_off * 4:rec_off * 4 + 8 * 160].reshape(8, 160).astype(np.int64)
+        for w in range(8):
+            px = words[w, :128].reshape(32, 4)
+            for j in range(8):
+                field = (px[:, j >> 1] >> (16 * (j & 1))) & SLOT_MASK
+                group = (field >> 4) & 7
+                for q in range(4):
+                    lanes = slice(q * 8, q * 8 + 8)
+                    total += max(len(set(field[lanes][group[lanes] == b])) for b in range(8))
+                n += 1
+    assert total / n < 5.0, f"{total / n:.2f} wavefronts per weight load"
 
 
 def test_gather_plan_invariants_on_random_contexts():

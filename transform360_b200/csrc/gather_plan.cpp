@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <climits>
 #include <cstdint>
+#include <cstring>
 #include <thread>
 
 namespace t360 {
@@ -26,50 +27,70 @@ void parallelRanges(int n, size_t workPerItem, F fn) {
   for (auto& th : pool) th.join();
 }
 
-// Device order of the sampling records.  Each row is cut into segments of 32 pixels (= the width of a gather
-// tile = one warp); inside a segment the pixels are dealt to LANES so that the lanes which one shared-memory pass
-// serves together (8 for the 128-bit weight loads of cubic / Lanczos, 16 for the 64-bit ones of bilinear) ask for
-// different bank groups of the weight table: sort the pixels by (bank group, phase), then deal them round-robin
-// over the passes.  The window reads are unaffected (the warp still touches the same 32 windows) and the stores
-// still fill one 32-byte sector.  The pixel's column inside the segment travels in the record's top 5 bits.
-void buildLaneOrder(const HostPlan& h, std::vector<int2>& out, int tilesPerRow, int tileH, const std::vector<int>& seamBoxX) {
+// ---- bank-group balancing ------------------------------------------------------------------------------------
+// Pixel i may read its weights from copy c of the table, which puts it into bank group (base[i] + c) & 7.  Finds an
+// assignment in which no group takes more than `cap` pixels (augmenting paths; 32 pixels, 8 groups).
+struct GroupMatcher {
+  int n, copies, cap;
+  const int* base;
+  int groupOf[32], load[8];
+  bool visited[8];
+
+  bool place(int i) {
+    for (int c = 0; c < copies; ++c) {
+      const int g = (base[i] + c) & 7;
+      if (visited[g]) continue;
+      visited[g] = true;
+      if (load[g] < cap) {
+        ++load[g];
+        groupOf[i] = g;
+        return true;
+      }
+      for (int j = 0; j < n; ++j) {
+        if (j == i || groupOf[j] != g) continue;
+        groupOf[j] = -1;  // try to move j elsewhere (its other choices; g itself is marked visited)
+        if (place(j)) {   // j took a seat in another group: g keeps its load, i takes j's seat
+          groupOf[i] = g;
+          return true;
+        }
+        groupOf[j] = g;
+      }
+    }
+    return false;
+  }
+  bool run() {
+    std::fill(groupOf, groupOf + 32, -1);
+    std::fill(load, load + 8, 0);
+    for (int i = 0; i < n; ++i) {
+      std::fill(visited, visited + 8, false);
+      if (!place(i)) return false;
+    }
+    return true;
+  }
+};
+
+// Full records: device order of the 8-byte sampling records the general kernels read.  Each row is cut into segments
+// of 32 pixels (= one warp); inside a segment the pixels are dealt to LANES by weight bank group (one order per
+// 32 x 4 block, so that a thread keeps one output column).  The pixel's column travels in the record's top 5 bits.
+void buildFullRecords(const HostPlan& h, std::vector<int2>& out, int tilesPerRow, int tileH) {
   const int k = h.kernelSize;
-  const int groups = weightBankGroups(k), lanesPerPass = weightLanesPerPass(k), passes = 32 / lanesPerPass;
-  constexpr int kRows = 4;  // rows per thread: one lane order per 32 x 4 block, so that a thread keeps ONE column
+  constexpr int kRows = 4;
   parallelRanges((h.mapH + kRows - 1) / kRows, static_cast<size_t>(h.mapW) * kRows, [&](int blockBegin, int blockEnd) {
   for (int yb = blockBegin * kRows; yb < blockEnd * kRows; yb += kRows) {
     for (int x0 = 0; x0 < h.mapW; x0 += 32) {
       const int n = std::min(32, h.mapW - x0);
-      int order[32];
-      for (int i = 0; i < n; ++i) order[i] = i;
-      const bool deal = k >= 2 && n == 32;
-      if (deal) {
-        // the bank group depends on fracX only, and fracX is the same down a column wherever the source column
-        // does not depend on the output row (the four equatorial cube faces): order by the block's first row
-        const SamplePoint* row = &h.samples[static_cast<size_t>(yb) * h.mapW];
-        auto keyOf = [&](int c) {
-          const int phase = row[x0 + c].rowPhase & 1023;
-          return ((weightSlotOf(k, phase) & (groups - 1)) << 10) | phase;
-        };
-        std::stable_sort(order, order + n, [&](int a, int b) { return keyOf(a) < keyOf(b); });
-      }
+      int laneOf[32], copyOf[32], slot[32];
+      const SamplePoint* first = &h.samples[static_cast<size_t>(yb) * h.mapW];
+      for (int i = 0; i < n; ++i) slot[i] = k >= 2 ? weightSlotOf(k, first[x0 + i].rowPhase & 1023) : 0;
+      if (k >= 2) dealLanes(k, 1, n, slot, laneOf, copyOf);
+      else for (int i = 0; i < n; ++i) laneOf[i] = i;
       for (int y = yb; y < std::min(h.mapH, yb + kRows); ++y) {
         const SamplePoint* row = &h.samples[static_cast<size_t>(y) * h.mapW];
-        // tile-major: the records of tile (ty, tx) are contiguous, [rowInTile][lane]
         const size_t tile = static_cast<size_t>(y / tileH) * tilesPerRow + x0 / 32;
         int2* dst = &out[(tile * tileH + y % tileH) * 32];
-        for (int i = 0; i < n; ++i) {
-          // i-th pixel of the sorted sequence -> pass i % passes, position i / passes inside the pass
-          const int lane = deal ? (i % passes) * lanesPerPass + i / passes : i;
-          const int c = order[i];
+        for (int c = 0; c < n; ++c) {
           const SamplePoint& sp = row[x0 + c];
-          int col0 = sp.col0;
-          if (seamBoxX[tile] >= 0) {  // seam tile: first column relative to the unwrapped box (kernels.cuh, kJobSeam)
-            int cw = col0 % h.inW;
-            if (cw < 0) cw += h.inW;
-            col0 = seamBoxX[tile] + (cw - seamBoxX[tile] + h.inW) % h.inW;
-          }
-          dst[lane] = int2{static_cast<int>((static_cast<unsigned>(col0) & ((1u << kRecordColumnShift) - 1)) |
+          dst[laneOf[c]] = int2{static_cast<int>((static_cast<unsigned>(sp.col0) & ((1u << kRecordColumnShift) - 1)) |
                                                  (static_cast<unsigned>(c) << kRecordColumnShift)),
                                 sp.rowPhase};
         }
@@ -79,103 +100,299 @@ void buildLaneOrder(const HostPlan& h, std::vector<int2>& out, int tilesPerRow, 
   });
 }
 
-// Splits the output plane into CTA tiles and finds, per tile, the bounding box of all source windows.  A tile is
-// "staged" when that box lies inside the plane (no BORDER_WRAP needed) and fits the fixed TMA box; its box is
-// anchored at a 16-byte aligned column.  Everything else is listed for the general (L1) kernel.
-void buildGatherTiles(const HostPlan& h, GatherPlan& d, std::vector<int>& seamBoxX) {
-  const int k = h.kernelSize, tw = kGatherTileW, th = gatherTileH(k);
-  const int tilesX = (h.mapW + tw - 1) / tw, tilesY = (h.mapH + th - 1) / th;
-  // seam tiles need whole 16-byte columns on both sides of the border and a plane much wider than the box
-  const bool seamPossible = h.inW % 16 == 0 && h.inW >= 4 * stageBoxW(k, 0);
-  std::vector<StagedTile> perTile(static_cast<size_t>(tilesX) * tilesY);  // classified in parallel, collected in raster order
-  parallelRanges(tilesY, static_cast<size_t>(h.mapW) * th, [&](int tyBegin, int tyEnd) {
-  for (int ty = tyBegin; ty < tyEnd; ++ty)
-    for (int tx = 0; tx < tilesX; ++tx) {
-      int minC = INT32_MAX, maxC = INT32_MIN, minR = INT32_MAX, maxR = INT32_MIN;
-      const int y1 = std::min(h.mapH, (ty + 1) * th), x1 = std::min(h.mapW, (tx + 1) * tw);
-      for (int y = ty * th; y < y1; ++y) {
-        const SamplePoint* row = &h.samples[static_cast<size_t>(y) * h.mapW];
-        for (int x = tx * tw; x < x1; ++x) {
-          const int c = row[x].col0, r = row[x].rowPhase >> 10;
-          minC = std::min(minC, c); maxC = std::max(maxC, c);
-          minR = std::min(minR, r); maxR = std::max(maxR, r);
+struct TileClass {
+  int kind = -1;  // kJob*; -1: covered by the share job that starts at the tile to its left (or at this tile)
+  int boxX = 0, boxY = 0;
+  bool shareStart = false;
+};
+
+// Bounding box of the source windows of a block of output pixels.
+struct Extent {
+  int minC = INT32_MAX, maxC = INT32_MIN, minR = INT32_MAX, maxR = INT32_MIN;
+};
+Extent extentOf(const HostPlan& h, int x0, int y0, int x1, int y1) {
+  Extent e;
+  for (int y = y0; y < y1; ++y) {
+    const SamplePoint* row = &h.samples[static_cast<size_t>(y) * h.mapW];
+    for (int x = x0; x < x1; ++x) {
+      const int c = row[x].col0, r = row[x].rowPhase >> 10;
+      e.minC = std::min(e.minC, c); e.maxC = std::max(e.maxC, c);
+      e.minR = std::min(e.minR, r); e.maxR = std::max(e.maxR, r);
+    }
+  }
+  return e;
+}
+
+// A 64 x 32 block qualifies as a share job when every column keeps its first source column down the 32 rows, steps
+// 0-2 source rows per output row, and the windows of the whole block fit one 192-byte-wide box inside the plane.
+bool shareBlock(const HostPlan& h, int x0, int y0, TileClass& out) {
+  const int k = h.kernelSize;
+  if (k < 4 || x0 + kShareW > h.mapW || y0 + kShareH > h.mapH) return false;
+  for (int y = y0 + 1; y < y0 + kShareH; ++y) {
+    const SamplePoint* a = &h.samples[static_cast<size_t>(y - 1) * h.mapW + x0];
+    const SamplePoint* b = a + h.mapW;
+    for (int x = 0; x < kShareW; ++x) {
+      const int d = (b[x].rowPhase >> 10) - (a[x].rowPhase >> 10);
+      if (b[x].col0 != a[x].col0 || d < 0 || d > 2) return false;
+    }
+  }
+  const Extent e = extentOf(h, x0, y0, x0 + kShareW, y0 + kShareH);
+  if (e.minC < 0 || e.minR < 0 || e.maxC + k > h.inW || e.maxR + k > h.inH) return false;
+  const int boxX = e.minC & ~15;
+  if (e.maxC + k - boxX > stageBoxW(k, 2) || e.maxR + k - e.minR > stageBoxH(k, 2)) return false;
+  out.kind = kJobShare;
+  out.boxX = boxX;
+  out.boxY = e.minR;
+  out.shareStart = true;
+  return true;
+}
+
+void classifyTile(const HostPlan& h, int x0, int y0, bool seamPossible, TileClass& out) {
+  const int k = h.kernelSize;
+  const int x1 = std::min(h.mapW, x0 + kGatherTileW), y1 = std::min(h.mapH, y0 + kFrameTileH);
+  const Extent e = extentOf(h, x0, y0, x1, y1);
+  const bool inPlane = e.minC >= 0 && e.minR >= 0 && e.maxC + k <= h.inW && e.maxR + k <= h.inH;
+  if (inPlane) {
+    const int boxX = e.minC & ~15;
+    for (int cls = 0; cls < 2; ++cls)
+      if (e.maxC + k - boxX <= stageBoxW(k, cls) && e.maxR + k - e.minR <= stageBoxH(k, cls)) {
+        out.kind = cls == 0 ? kJobClass0 : kJobClass1;
+        out.boxX = boxX;
+        out.boxY = e.minR;
+        return;
+      }
+  }
+  // windows that cross the left/right border only (BORDER_WRAP): do they fit a class-0 box that wraps around it?
+  if (seamPossible && e.minR >= 0 && e.maxR + k <= h.inH && e.maxR + k - e.minR <= stageBoxH(k, 0)) {
+    const int W = h.inW, half = W / 2;  // columns rotated by half a plane: the border is in the middle of the range
+    int lo = INT32_MAX, hi = INT32_MIN;
+    for (int y = y0; y < y1; ++y)
+      for (int x = x0; x < x1; ++x) {
+        int cw = h.samples[static_cast<size_t>(y) * h.mapW + x].col0 % W;
+        if (cw < 0) cw += W;
+        const int rot = cw + half >= W ? cw + half - W : cw + half;
+        lo = std::min(lo, rot); hi = std::max(hi, rot);
+      }
+    const int first = lo - half < 0 ? lo - half + W : lo - half;  // leftmost first column, in plane coordinates
+    const int bx = first & ~15;
+    if (hi - lo + (first - bx) + k <= stageBoxW(k, 0) && bx + stageBoxW(k, 0) > W) {
+      out.kind = kJobSeam;
+      out.boxX = bx;
+      out.boxY = e.minR;
+      return;
+    }
+  }
+  out.kind = kJobGeneral;
+  out.boxX = out.boxY = 0;
+}
+
+inline uint32_t slotField(int k, int phase, int copy) { return static_cast<uint32_t>(weightSlotField(k, phase, copy)); }
+
+// compact records of a share job (kernels.cuh)
+void writeShareRecords(const HostPlan& h, const GatherJob& job, uint32_t* out) {
+  const int k = h.kernelSize, copies = weightCopies(k);
+  const int x0 = job.outX, y0 = job.outY & kJobRowMask, boxX = job.boxXY & 0xffff, boxY = job.boxXY >> 16;
+  const int pitch = stageBoxW(k, 2);
+  for (int wx = 0; wx < kShareW / 32; ++wx) {
+    // the bank group of a pixel's weights depends on fracX only, which a column keeps (up to rounding jitter of the
+    // map): one lane order and one copy choice per column, found on the block's first row
+    int slot[32], laneOf[32], copyOf[32];
+    const SamplePoint* first = &h.samples[static_cast<size_t>(y0) * h.mapW + x0 + wx * 32];
+    for (int i = 0; i < 32; ++i) slot[i] = weightSlotOf(k, first[i].rowPhase & 1023);
+    dealLanes(k, copies, 32, slot, laneOf, copyOf);
+    for (int wy = 0; wy < kShareH / kShareRows; ++wy) {
+      const int w = wy * (kShareW / 32) + wx;
+      uint32_t* words = out + static_cast<size_t>(w) * (kShareJobRecordBytes / kGroupWarps / 4);
+      uint32_t* headers = words + 32 * 4;
+      for (int c = 0; c < 32; ++c) {
+        const int lane = laneOf[c], x = x0 + wx * 32 + c, ya = y0 + wy * kShareRows;
+        const SamplePoint* col = &h.samples[static_cast<size_t>(ya) * h.mapW + x];
+        const int off = ((col->rowPhase >> 10) - boxY) * pitch + (col->col0 - boxX);
+        headers[lane] = static_cast<uint32_t>(off) | (static_cast<uint32_t>(c) << kRecordColumnShift);
+        for (int j = 0; j < kShareRows; ++j) {
+          const SamplePoint& sp = col[static_cast<size_t>(j) * h.mapW];
+          const int d = j == 0 ? 0 : (sp.rowPhase >> 10) - (col[static_cast<size_t>(j - 1) * h.mapW].rowPhase >> 10);
+          const uint32_t rec = slotField(k, sp.rowPhase & 1023, copyOf[c]) | static_cast<uint32_t>(d);
+          uint32_t& word = words[lane * 4 + (j >> 1)];
+          word = (j & 1) ? (word | (rec << 16)) : rec;
         }
       }
-      const int boxX = minC >= 0 ? (minC & ~15) : -1;
-      const bool inPlane = minC >= 0 && minR >= 0 && maxC + k <= h.inW && maxR + k <= h.inH;
-      int cls = -1;
-      for (int c = 0; c < kNumBoxClasses && inPlane && cls < 0; ++c)
-        if (maxC + k - boxX <= stageBoxW(k, c) && maxR + k - minR <= stageBoxH(k, c)) cls = c;
-      // warps (4 rows each) whose every pixel column keeps its source column down the 4 rows, 1-2 source rows apart:
-      // they slide one register window down the column (gatherColumnShared) instead of fetching 4 windows
-      int shareMask = 0;
-      for (int w = 0; k >= 4 && w < th / 4; ++w) {
-        const int ya = ty * th + 4 * w;
-        bool ok = ya + 4 <= h.mapH;
-        for (int x = tx * tw; ok && x < x1; ++x)
-          for (int j = 1; j < 4 && ok; ++j) {
-            const SamplePoint &a = h.samples[static_cast<size_t>(ya + j - 1) * h.mapW + x], &b = h.samples[static_cast<size_t>(ya + j) * h.mapW + x];
-            const int d = (b.rowPhase >> 10) - (a.rowPhase >> 10);
-            ok = (d == 1 || d == 2) && b.col0 == h.samples[static_cast<size_t>(ya) * h.mapW + x].col0;
-          }
-        if (ok) shareMask |= 1 << w;
-      }
-      // windows that cross the left/right border only (BORDER_WRAP): do they fit a class-0 box that wraps around it?
-      int wrappedBoxX = -1;
-      if (cls < 0 && seamPossible && minR >= 0 && maxR + k <= h.inH && maxR + k - minR <= stageBoxH(k, 0)) {
-        const int W = h.inW, half = W / 2;  // columns rotated by half a plane: the border is in the middle of the range
-        int lo = INT32_MAX, hi = INT32_MIN;
-        for (int y = ty * th; y < y1; ++y)
-          for (int x = tx * tw; x < x1; ++x) {
-            int cw = h.samples[static_cast<size_t>(y) * h.mapW + x].col0 % W;
-            if (cw < 0) cw += W;
-            const int rot = cw + half >= W ? cw + half - W : cw + half;
-            lo = std::min(lo, rot); hi = std::max(hi, rot);
-          }
-        const int first = lo - half < 0 ? lo - half + W : lo - half;  // leftmost first column, in plane coordinates
-        const int bx = first & ~15;
-        if (hi - lo + (first - bx) + k <= stageBoxW(k, 0) && bx + stageBoxW(k, 0) > W) wrappedBoxX = bx;
-      }
-      StagedTile& job = perTile[static_cast<size_t>(ty) * tilesX + tx];
-      if (cls >= 0) {
-        job = StagedTile{tx * tw, ty * th | (cls << kJobKindShift), boxX | (minR << 16), shareMask};
-      } else if (wrappedBoxX >= 0) {
-        job = StagedTile{tx * tw, ty * th | (kJobSeam << kJobKindShift), wrappedBoxX | (minR << 16), shareMask};
-        seamBoxX[static_cast<size_t>(ty) * tilesX + tx] = wrappedBoxX;
-      } else {
-        job = StagedTile{tx * tw, ty * th | (kJobGeneral << kJobKindShift), 0, 0};
-      }
     }
-  });
-  std::vector<StagedTile> staged[kNumBoxClasses];
-  std::vector<StagedTile> fallback, seam;
-  for (const StagedTile& job : perTile) {
-    const int kind = (job.outY >> kJobKindShift) & kJobKindMask;
-    (kind == kJobGeneral ? fallback : kind == kJobSeam ? seam : staged[kind]).push_back(job);
   }
-  // order: general tiles, seam tiles, then the wide-box class, then the common class (see gatherFrameKernel)
-  d.numGeneral = static_cast<int>(fallback.size());
-  d.numSeam = static_cast<int>(seam.size());
-  d.jobs = fallback;
-  d.jobs.insert(d.jobs.end(), seam.begin(), seam.end());
-  for (int c = kNumBoxClasses - 1; c >= 0; --c) {
-    d.numStaged[c] = static_cast<int>(staged[c].size());
-    d.jobs.insert(d.jobs.end(), staged[c].begin(), staged[c].end());
+}
+
+// compact records of a 32 x 32 job (class 0, class 1, seam)
+void writeTileRecords(const HostPlan& h, const GatherJob& job, uint32_t* out) {
+  const int k = h.kernelSize, copies = weightCopies(k);
+  const int kind = (job.outY >> kJobKindShift) & kJobKindMask;
+  const int x0 = job.outX, y0 = job.outY & kJobRowMask, boxX = job.boxXY & 0xffff, boxY = job.boxXY >> 16;
+  const int pitch = stageBoxW(k, boxClassOf(kind));
+  const int n = std::min(32, h.mapW - x0);
+  for (int yy = 0; yy < kFrameTileH; ++yy) {
+    const int y = y0 + yy, w = yy / 4, j = yy % 4;
+    uint32_t* words = out + static_cast<size_t>(w) * 32 * 4;
+    if (y >= h.mapH) {  // below the plane: the kernel skips the row (y >= dstH)
+      for (int lane = 0; lane < 32; ++lane) words[lane * 4 + j] = static_cast<uint32_t>(lane) << 16;
+      continue;
+    }
+    const SamplePoint* row = &h.samples[static_cast<size_t>(y) * h.mapW + x0];
+    int slot[32], laneOf[32], copyOf[32];
+    for (int i = 0; i < n; ++i) slot[i] = weightSlotOf(k, row[i].rowPhase & 1023);
+    dealLanes(k, copies, n, slot, laneOf, copyOf);
+    for (int c = n; c < 32; ++c) words[c * 4 + j] = static_cast<uint32_t>(c) << 16;  // right of the plane: skipped (x >= dstW)
+    for (int c = 0; c < n; ++c) {
+      int col0 = row[c].col0;
+      if (kind == kJobSeam) {  // first column relative to the unwrapped box (boxX <= col0 < boxX + box width)
+        int cw = col0 % h.inW;
+        if (cw < 0) cw += h.inW;
+        col0 = boxX + (cw - boxX + h.inW) % h.inW;
+      }
+      const int off = ((row[c].rowPhase >> 10) - boxY) * pitch + (col0 - boxX);
+      words[laneOf[c] * 4 + j] = static_cast<uint32_t>(off) | (static_cast<uint32_t>(c) << 16) |
+                                 (slotField(k, row[c].rowPhase & 1023, copyOf[c]) << 17);
+    }
   }
 }
 
 }  // namespace
 
+int dealLanes(int k, int copies, int n, const int* slot, int* laneOf, int* copyOf) {
+  const int groups = weightBankGroups(k), lanesPerPass = weightLanesPerPass(k), passes = 32 / lanesPerPass;
+  for (int i = 0; i < n; ++i) { laneOf[i] = i; copyOf[i] = 0; }
+  if (n < 32) return 0;
+  int group[32];
+  if (copies > 1 && groups == 8) {
+    int base[32];
+    for (int i = 0; i < n; ++i) base[i] = slot[i] & 7;
+    GroupMatcher m{n, copies, 0, base, {}, {}, {}};
+    for (m.cap = 4; m.cap <= 32; ++m.cap)
+      if (m.run()) break;
+    for (int i = 0; i < n; ++i) {
+      group[i] = m.groupOf[i];
+      copyOf[i] = (m.groupOf[i] - base[i]) & 7;
+    }
+  } else {
+    for (int i = 0; i < n; ++i) group[i] = slot[i] & (groups - 1);
+  }
+  // How many pixels of each group go to each pass (quarter-warp).  A pass costs as many wavefronts as its fullest group
+  // holds pixels, so a group with more pixels than passes should put its surplus into the pass where another group
+  // already did: groups in order of decreasing load, every pixel to the pass (with a free lane) where it raises the
+  // cost least, then where the group has fewest pixels, then the emptiest.
+  int load[16] = {}, byLoad[16];
+  for (int i = 0; i < n; ++i) ++load[group[i]];
+  for (int g = 0; g < groups; ++g) byLoad[g] = g;
+  std::stable_sort(byLoad, byLoad + groups, [&](int a, int b) { return load[a] > load[b]; });
+  int height[4] = {}, fill[4] = {}, share[16][4] = {};
+  for (int gi = 0; gi < groups; ++gi) {
+    const int g = byLoad[gi];
+    for (int item = 0; item < load[g]; ++item) {
+      int best = -1;
+      for (int q = 0; q < passes; ++q) {
+        if (fill[q] >= lanesPerPass) continue;
+        if (best < 0) { best = q; continue; }
+        const int raiseQ = share[g][q] + 1 > height[q], raiseB = share[g][best] + 1 > height[best];
+        if (raiseQ != raiseB ? raiseQ < raiseB : (share[g][q] != share[g][best] ? share[g][q] < share[g][best] : fill[q] < fill[best])) best = q;
+      }
+      ++fill[best];
+      ++share[g][best];
+      height[best] = std::max(height[best], share[g][best]);
+    }
+  }
+  // Which pixels: neighbouring columns of a group stay in one pass -- they tend to carry the same phase (the same slot:
+  // one broadcast read), in this row and in the rows below that reuse the order.
+  int nextLane[4];
+  for (int q = 0; q < passes; ++q) nextLane[q] = q * lanesPerPass;
+  for (int g = 0; g < groups; ++g) {
+    int q = 0;
+    for (int i = 0; i < n; ++i) {
+      if (group[i] != g) continue;
+      while (share[g][q] == 0) ++q;
+      --share[g][q];
+      laneOf[i] = nextLane[q]++;
+    }
+  }
+  int wavefronts = 0;
+  for (int q = 0; q < passes; ++q) wavefronts += height[q];
+  return wavefronts;
+}
+
+std::vector<uint8_t> buildWeightImage(int k, const int16_t* table) {
+  const int copies = weightCopies(k), vs = weightVectorStride(k, copies);
+  std::vector<uint8_t> img(static_cast<size_t>(weightImageBytes(k, copies)), 0);
+  for (int phase = 0; phase < 1024; ++phase) {
+    const int slot = weightSlotOf(k, phase);
+    const int16_t* cell = table + static_cast<size_t>(phase) * k * k;
+    if (k == 2) {
+      std::memcpy(&img[static_cast<size_t>(slot) * 8], cell, 8);
+      continue;
+    }
+    for (int c = 0; c < copies; ++c)
+      for (int v = 0; v < k * k / 8; ++v)  // vector v = the 8 weights 8v .. 8v+7 of the row-major window
+        std::memcpy(&img[static_cast<size_t>(v) * vs + static_cast<size_t>(c) * 16384 + static_cast<size_t>(weightSlotInCopy(slot, c)) * 16],
+                    cell + v * 8, 16);
+  }
+  return img;
+}
+
 void buildGatherPlan(const HostPlan& h, bool stageTiles, GatherPlan& g) {
   g = GatherPlan{};
-  if (h.kernelSize <= 0) return;
-  g.tileH = gatherTileH(h.kernelSize);
+  const int k = h.kernelSize;
+  if (k <= 0) return;
+  g.tileH = gatherTileH(k);
   g.tilesPerRow = (h.mapW + kGatherTileW - 1) / kGatherTileW;
   g.tileRows = (h.mapH + g.tileH - 1) / g.tileH;
-  std::vector<int> seamBoxX(static_cast<size_t>(g.tilesPerRow) * g.tileRows, -1);  // per tile; >= 0: seam tile
-  if (stageTiles) buildGatherTiles(h, g, seamBoxX);
   g.records.assign(static_cast<size_t>(g.tilesPerRow) * g.tileRows * g.tileH * kGatherTileW, int2{0, 0});
-  buildLaneOrder(h, g.records, g.tilesPerRow, g.tileH, seamBoxX);
+  buildFullRecords(h, g.records, g.tilesPerRow, g.tileH);
+  if (!stageTiles) return;
+
+  // ---- cut the plane into jobs: 64 x 32 share blocks where the geometry allows, 32 x 32 tiles elsewhere
+  const int tilesX = g.tilesPerRow, tilesY = (h.mapH + kFrameTileH - 1) / kFrameTileH;
+  // seam tiles need whole 16-byte columns on both sides of the border and a plane much wider than the box
+  const bool seamPossible = h.inW % 16 == 0 && h.inW >= 4 * stageBoxW(k, 0);
+  std::vector<TileClass> cls(static_cast<size_t>(tilesX) * tilesY);
+  parallelRanges(tilesY, static_cast<size_t>(h.mapW) * kFrameTileH, [&](int tyBegin, int tyEnd) {
+    for (int ty = tyBegin; ty < tyEnd; ++ty)
+      for (int tx = 0; tx < tilesX; tx += 2) {
+        TileClass* c = &cls[static_cast<size_t>(ty) * tilesX + tx];
+        if (shareBlock(h, tx * 32, ty * kFrameTileH, c[0])) continue;  // c[1] stays -1: covered
+        classifyTile(h, tx * 32, ty * kFrameTileH, seamPossible, c[0]);
+        if (tx + 1 < tilesX) classifyTile(h, (tx + 1) * 32, ty * kFrameTileH, seamPossible, c[1]);
+      }
+  });
+  // launch order: general tiles (latency-bound: they run while every group of the SM is busy), seam, class 1 (both
+  // need the two stage buffers), then the share jobs and finally the small class-0 tiles through the double-buffered
+  // TMA pipeline, which leaves a short, fine-grained tail
+  const int order[5] = {kJobGeneral, kJobSeam, kJobClass1, kJobShare, kJobClass0};
+  size_t offset = 0;  // bytes
+  for (int kind : order)
+    for (int ty = 0; ty < tilesY; ++ty)
+      for (int tx = 0; tx < tilesX; ++tx) {
+        const TileClass& c = cls[static_cast<size_t>(ty) * tilesX + tx];
+        if (c.kind != kind) continue;
+        GatherJob job{tx * 32, ty * kFrameTileH | (kind << kJobKindShift), c.boxX | (c.boxY << 16), 0};
+        if (kind != kJobGeneral) {
+          job.recordOffset = static_cast<int>(offset / 16);
+          offset += kind == kJobShare ? kShareJobRecordBytes : kTileJobRecordBytes;
+        }
+        g.jobs.push_back(job);
+        switch (kind) {
+          case kJobGeneral: ++g.numGeneral; break;
+          case kJobSeam: ++g.numSeam; break;
+          case kJobShare: ++g.numShare; break;
+          default: ++g.numStaged[kind]; break;
+        }
+      }
+  g.compact.assign(offset / 4, 0u);
+  parallelRanges(static_cast<int>(g.jobs.size()), 2048, [&](int begin, int end) {
+    for (int i = begin; i < end; ++i) {
+      const GatherJob& job = g.jobs[i];
+      const int kind = (job.outY >> kJobKindShift) & kJobKindMask;
+      if (kind == kJobGeneral) continue;
+      uint32_t* out = g.compact.data() + static_cast<size_t>(job.recordOffset) * 4;
+      if (kind == kJobShare) writeShareRecords(h, job, out);
+      else writeTileRecords(h, job, out);
+    }
+  });
 }
 
 }  // namespace t360

@@ -20,30 +20,96 @@ struct GatherParams {
   int transparent;         // BORDER_TRANSPARENT (barrel layouts) instead of BORDER_WRAP
 };
 
-// One tile of the TMA-staged gather: a gatherTileW x gatherTileH block of output pixels whose whole source
-// window fits the fixed staging box placed at (boxX, boxY) of the source plane (boxX % 16 == 0).
-struct StagedTile {
-  int outX, outY;  // outY carries the job kind (kJobKindShift) and the image plane (kJobPlaneShift)
-  int boxXY;       // boxX | boxY << 16
-  int shareMask;   // bit w: warp w of the tile may slide its windows down the column (see gatherColumnShared); found by the host
+// ---- the persistent frame gather (gatherFrameKernel) -------------------------------------------------------------
+// A CTA holds kGatherGroups independent GROUPS of 256 threads (8 warps); every group runs its own job pipeline
+// (claim -> header -> records -> TMA box -> compute) on its own pair of stage buffers, synchronised with a named
+// barrier, while all groups share ONE copy of the weight tables in shared memory.  One CTA per SM.
+//
+// A JOB is a block of output pixels of one image plane:
+//   kJobShare    64 x 32 pixels on which every output column keeps its source column down the rows and consecutive
+//                rows start 0, 1 or 2 source rows apart (the four equatorial cube faces, equirect -> equirect ...).
+//                A warp owns 32 columns x 8 rows, a thread one column: it slides ONE K-row register window down its
+//                column, fetching only the 0-2 new rows per pixel.  Source window: one 192 x boxH TMA box.
+//   kJobClass0   32 x 32 pixels, any geometry whose windows fit a 208 x boxH box: a thread computes 4 pixels, each
+//   kJobClass1   from its own window.  Class 1: a 240 x boxH1 box that takes both stage buffers.
+//   kJobSeam     like class 0, but the windows cross the left/right plane border (BORDER_WRAP at the +-180 degree
+//                meridian): two class-0 boxes, at boxX and boxX - srcW, zero-filled outside the plane, OR-ed together.
+//   kJobGeneral  32 x 32 pixels read through L1 with full border handling (pole caps, anything that fits no box).
+struct GatherJob {
+  int outX, outY;    // outY carries the job kind (kJobKindShift) and the image plane (kJobPlaneShift)
+  int boxXY;         // boxX | boxY << 16 (boxX % 16 == 0)
+  int recordOffset;  // of the job's compact records, in 16-byte units from the plane's record buffer
 };
-// job kinds of the persistent gather kernel: 0 / 1 = staged through TMA with box class 0 / 1, 2 = general (L1) path,
-// 3 = "seam": the tile's windows cross the left/right plane border (BORDER_WRAP, the +-180 degree meridian of an
-// equirect source) but fit a class-0 box that wraps around it.  The box is fetched as TWO class-0 TMA loads, at
-// column boxX and at column boxX - srcW: whatever lies outside the plane arrives as zeros, so the two boxes are
-// complementary and their bitwise OR is the wrapped window.  The records of such a tile carry col0 relative to the
-// unwrapped box (boxX <= col0 < boxX + box width, i.e. up to srcW + box width).
-constexpr int kJobKindShift = 24, kJobRowMask = (1 << kJobKindShift) - 1, kJobGeneral = 2, kJobSeam = 3;
+using StagedTile = GatherJob;
+constexpr int kJobClass0 = 0, kJobClass1 = 1, kJobGeneral = 2, kJobSeam = 3, kJobShare = 4;
+constexpr int kJobKindShift = 24, kJobRowMask = (1 << kJobKindShift) - 1;
 constexpr int kJobPlaneShift = 28, kJobKindMask = (1 << (kJobPlaneShift - kJobKindShift)) - 1;
 
-// The persistent gather kernel takes the tiles of up to three image planes (Y, U, V of one frame) in ONE launch:
+constexpr int kGroupThreads = 256, kGroupWarps = kGroupThreads / 32;
+constexpr int kGatherGroups = 3;  // job pipelines per CTA (768 threads, one CTA per SM)
+constexpr int kGatherTileW = 32, kFrameTileH = 32;  // generic jobs: 32 x 32, four rows per thread
+constexpr int kShareW = 64, kShareH = 32, kShareRows = 8;  // share jobs: 2 x 4 warps of 32 columns x 8 rows
+// Staging boxes (bytes x rows).  The shared-memory row pitch is the box width (TMA writes dense rows).  192 B = 48 words
+// puts consecutive rows 16 banks apart: the 32 adjacent pixels of a share-job warp span <= 13 words of 1-2 source rows,
+// so their window loads are conflict-free (1.10 wavefronts per load in the bank model, 1.57 at 96 B).  Polar tiles
+// (a warp's pixels drift over many rows) are worst at 192 B (2.9) and want a pitch that is 4 * odd words: 208 B (2.3).
+constexpr int kNumBoxClasses = 3;  // tensor map index: 0 = class 0 / seam, 1 = class 1, 2 = share
+__host__ __device__ constexpr int boxClassOf(int kind) { return kind == kJobShare ? 2 : (kind == kJobClass1 ? 1 : 0); }
+__host__ __device__ constexpr int stageBoxW(int /*k*/, int cls) { return cls == 2 ? 192 : (cls == 0 ? 208 : 240); }
+__host__ __device__ constexpr int stageBoxH(int k, int cls) {
+  return k == 8 ? (cls == 2 ? 80 : (cls == 0 ? 72 : 128)) : (cls == 2 ? 72 : (cls == 0 ? 64 : 96));
+}
+// one stage buffer (TMA destinations need 128-byte alignment; the tail absorbs the over-read of a window's last word)
+__host__ __device__ constexpr int stageBytesOf(int k) { return (stageBoxW(k, 2) * stageBoxH(k, 2) + 64 + 127) & ~127; }
+
+// Weight tables in shared memory.  Phase a = (fracY << 5) | fracX lives in SLOT weightSlotOf(k, a); the K*K int16
+// weights of a slot are K*K/8 16-byte vectors (k >= 4), vector v of copy c at byte
+//     v * weightVectorStride(k, copies) + c * 16384 + slot * 16
+// A 128-bit shared load is served 8 lanes (one quarter-warp) at a time out of 8 bank groups of 16 bytes, the group
+// being slot & 7.  With 32 pixels per warp the fullest group holds ~6-7 of them whatever the hash (bank model: 6.3
+// wavefronts per load instead of 4).  So the cubic table is kept TWICE, the second copy rotated by one bank group
+// (slot s of copy 1 sits where slot (s & ~7) | ((s + 1) & 7) of copy 0 would), and the host -- which already deals the
+// pixels of a row segment to lanes -- picks the copy per pixel so that no group is asked more than ~4 times: 4.2-4.5.
+__host__ __device__ constexpr int weightSlotOf(int k, int phase) {
+  return k == 2 ? ((phase & ~31) | ((phase & 1) << 4) | ((phase & 31) >> 1))
+                : ((phase & ~31) | ((phase & 3) << 3) | ((phase & 31) >> 2));
+}
+__host__ __device__ constexpr int weightCopies(int k) { return k == 4 ? 2 : 1; }
+__host__ __device__ constexpr int weightVectorStride(int k, int copies) { return (k == 2 ? 8192 : 16384) * copies; }
+__host__ __device__ constexpr int weightImageBytes(int k, int copies) { return k == 2 ? 8192 * copies : (k * k / 8) * 16384 * copies; }
+// position of slot s inside copy c (the rotation by one bank group)
+__host__ __device__ constexpr int weightSlotInCopy(int slot, int copy) { return copy ? ((slot & ~7) | ((slot + copy) & 7)) : slot; }
+// the slot field of a compact record: (position << 4) | (copy << 14), i.e. the byte offset of the slot's first vector
+__host__ __device__ constexpr int weightSlotField(int k, int phase, int copy) {
+  return (weightSlotInCopy(weightSlotOf(k, phase), copy) << 4) | (copy << 14);
+}
+constexpr int kSlotFieldMask = 0x7FF0;
+__host__ __device__ constexpr int weightBankGroups(int k) { return k == 2 ? 16 : 8; }
+__host__ __device__ constexpr int weightLanesPerPass(int k) { return k == 2 ? 16 : 8; }
+
+// Compact sampling records of the staged jobs (32-bit words, one buffer per plan, GatherJob::recordOffset):
+//   share job    per warp w (columns 32 * (w & 1) .., rows 8 * (w >> 1) ..): 32 x uint4, then 32 x uint32, by lane.
+//                uint32 = header of the lane's column: off | column << 27, off = (row0 - boxY) * 192 + (col0 - boxX) of
+//                the column's first pixel; uint4 = 8 x 16-bit pixel records, row j in half j & 1 of word j >> 1:
+//                slotField | d, d = source rows between this pixel's window and the previous one's (0 for the first).
+//                2.5 bytes per pixel.
+//   other jobs   per warp w (rows 4 * w ..): 32 x uint4 by lane, word j = pixel of row 4 * w + j:
+//                off (15 bits) | column << 16 (5 bits) | slotField << 17.  4 bytes per pixel.  Inside a 32-pixel row the
+//                pixels are dealt to lanes (and copies) per row; pixels outside the plane carry a column / row that
+//                fails the bounds check.
+// General jobs read the full records below.
+constexpr int kShareJobRecordBytes = kGroupWarps * (32 * 16 + 32 * 4), kTileJobRecordBytes = kGroupWarps * 32 * 16;
+constexpr int kRecordColumnShift = 27;
+
+// The persistent gather kernel takes the jobs of up to three image planes (Y, U, V of one frame) in ONE launch:
 // one weight-table prologue and one tail per frame instead of per plane, and the dynamic scheduler balances the
-// planes against each other.  Everything that differs between the planes sits in a PlaneView (+ two tensor maps).
+// planes against each other.  Everything that differs between the planes sits in a PlaneView (+ its tensor maps).
 constexpr int kMaxFramePlanes = 3;
 struct PlaneView {
   const uint8_t* src;   // (blurred) input plane
   uint8_t* dst;
-  const int2* samples;  // lane-ordered, tile-major records
+  const int2* samples;  // full records (general jobs): lane-ordered, tile-major, see below
+  const uint4* records; // compact records (staged jobs)
   int srcW, srcH, srcPitch;
   int dstW, dstH, dstPitch;
   int tilesPerRow;
@@ -51,49 +117,22 @@ struct PlaneView {
 };
 struct FrameGatherParams {
   PlaneView plane[kMaxFramePlanes];
-  const int16_t* weights;
+  const uint4* weightImage;  // device copy of the shared-memory image of the tables (weightImageBytes)
   int kernelSize, numPlanes;
 };
 
-constexpr int kGatherTileW = 32;                                   // one warp = 32 adjacent columns
+// The general (whole plane, L1) kernels and the general jobs of the frame kernel use FULL records, 8 bytes per pixel:
+// {col0 | column << 27, row0 << 10 | phase}, tile-major over tiles of 32 x gatherTileH(k) pixels:
+//   records[((ty * tilesPerRow + tx) * gatherTileH(k) + rowInTile) * 32 + lane]
+// (tiles that stick out of the plane are padded with zero records).  Inside a 32-pixel row segment the records are in
+// LANE order: the host deals the pixels of a segment to lanes by weight bank group (one order per 32 x 4 block).
 __host__ __device__ constexpr int gatherThreads(int k) { return k == 8 ? 512 : 256; }
 __host__ __device__ constexpr int gatherTileH(int k) { return gatherThreads(k) / 32 * 4; }  // 4 rows per thread
-// Staging boxes (bytes x rows), two classes per kernel size: the common one, and a larger one for tiles whose
-// source window is wide (towards the poles).  Shared-memory row pitch = box width (TMA writes dense rows):
-// 192 B = 48 words puts consecutive rows 16 banks apart, so a warp whose 32 adjacent pixels drift over 2-4
-// source rows still reads conflict-free; 240 B = 60 words puts them 28 banks apart.
-constexpr int kNumBoxClasses = 2;
-__host__ __device__ constexpr int stageBoxW(int /*k*/, int cls) { return cls == 0 ? 192 : 240; }
-// (three 256-thread CTAs of the common class share an SM: 32 KB of cubic weights + two 12 KB stages each.  A fourth
-// fits with 63-row boxes but measured no faster -- the kernel is bound by shared-memory wavefronts, not by latency
-// -- and it leaves no room for the concurrently running minority-tile kernels.)
-__host__ __device__ constexpr int stageBoxH(int k, int cls) { return k == 8 ? (cls == 0 ? 112 : 144) : (cls == 0 ? 64 : 96); }
-
-// Shared-memory slot of the weights of phase a = (fracY << 5) | fracX.  A 128-bit shared load is served 8 lanes
-// (one quarter-warp) at a time out of 8 bank groups of 16 bytes -- a 64-bit one 16 lanes out of 16 groups -- and
-// the group is the low bits of the slot.  The slot takes fracX's HIGH bits as its low bits: of the hashes tried in
-// the offline bank simulator this one balances the phases of 32 adjacent pixels best.
-__host__ __device__ constexpr int weightSlotOf(int k, int phase) {
-  return k == 2 ? ((phase & ~31) | ((phase & 1) << 4) | ((phase & 31) >> 1))
-                : ((phase & ~31) | ((phase & 3) << 3) | ((phase & 31) >> 2));
-}
-__host__ __device__ constexpr int weightBankGroups(int k) { return k == 2 ? 16 : 8; }
-__host__ __device__ constexpr int weightLanesPerPass(int k) { return k == 2 ? 16 : 8; }
-
-// Sampling records.  Tile-major: the gatherTileH(k) x 32 records of output tile (ty, tx) are contiguous,
-//   records[((ty * tilesPerRow + tx) * gatherTileH(k) + rowInTile) * 32 + lane]
-// (tiles that stick out of the plane are padded with zero records), so a warp fetches the records of its four rows
-// from one base address with immediate offsets and needs no bounds checks.  Inside a 32-pixel row segment the records
-// are in LANE order, not column order: the host deals the pixels of a segment to lanes so that the lanes served
-// together by one shared-memory pass ask for different bank groups (see buildLaneOrder in video_frame_transform.cpp).
-// Record word 0 therefore carries the pixel's column inside the segment in its top 5 bits:
-// x = segmentX + (word0 >> 27), col0 = (word0 << 5) >> 5.
-constexpr int kRecordColumnShift = 27;
 
 struct StagedParams {
-  const StagedTile* tiles;  // device list
+  const GatherJob* tiles;  // device list
   int numTiles;
-  int* claimCounter;        // two device ints, zero before the first launch (the kernel re-arms them): tile scheduler
+  int* claimCounter;        // two device ints, zero before the first launch (the kernel re-arms them): job scheduler
 };
 
 // One tile of the segmented low-pass: output rectangle and the taps to use.
@@ -153,9 +192,9 @@ constexpr int kBlurMaxSmem = 96 * 1024;
 // Launchers: enqueue on `stream`, return the CUDA status of the launch.  Each counts the kernels it launches.
 // General path for a whole plane: taps through L1, every border mode (BORDER_WRAP, BORDER_TRANSPARENT), nearest.
 cudaError_t launchGather(const GatherParams& p, int numSMs, cudaStream_t stream);
-// Whole planes in one persistent kernel: `jobs` lists the tiles of every plane, sorted by kind (general, class 1,
-// class 0).  tensorMaps: per plane two CUtensorMap (128 bytes each) describing its source with the staging boxes of
-// class 0 and 1 of p.kernelSize, i.e. [numPlanes][kNumBoxClasses].  BORDER_WRAP only.
+// Whole planes in one persistent kernel: `jobs` lists the jobs of every plane, sorted by kind (general, seam, class 1,
+// share, class 0).  tensorMaps: per plane kNumBoxClasses CUtensorMap (128 bytes each) describing its source with the
+// staging boxes of p.kernelSize, i.e. [numPlanes][kNumBoxClasses].  BORDER_WRAP only.
 cudaError_t launchGatherFrame(const FrameGatherParams& p, const StagedParams& jobs, const void* tensorMaps, int numSMs,
                               cudaStream_t stream);
 cudaError_t launchBlurStrips(const StripParams& p, int hy, cudaStream_t stream);  // register-resident, hy <= kStripMaxHy

@@ -30,8 +30,8 @@
 namespace {
 
 using t360::BlurJob;
+using t360::GatherJob;
 using t360::HostPlan;
-using t360::StagedTile;
 using t360::StripJob;
 
 struct CudaFail {
@@ -78,13 +78,14 @@ struct DevicePlan {
   int inW = 0, inH = 0, outW = 0, outH = 0, mapW = 0, mapH = 0;
   int kernelSize = 0;
   bool transparent = false, lowPass = false, blurNeedsClear = false;
-  DeviceBuffer<int2> samples;  // tile-major, lane-ordered records (kernels.cuh)
+  DeviceBuffer<int2> samples;      // full records: tile-major, lane-ordered, 8 bytes per pixel (general kernels / jobs)
+  DeviceBuffer<uint32_t> records;  // compact records of the staged jobs (kernels.cuh): 2.5 - 4 bytes per pixel
   int tilesPerRow = 0;
-  // gather tiles: those whose source window fits the TMA staging box, and the rest (by tile index)
-  DeviceBuffer<StagedTile> gatherJobs;  // every tile of the plane, sorted by kind (general, class 1, class 0)
-  std::vector<StagedTile> hostJobs;     // the same list on the host: merged per frame by frameJobList()
-  int numJobs = 0, numStaged[t360::kNumBoxClasses] = {}, numSeam = 0, numFallback = 0;
-  int totalStaged() const { int n = numSeam; for (int c : numStaged) n += c; return n; }
+  // gather jobs: share blocks and tiles whose source windows fit a TMA staging box, and the rest
+  DeviceBuffer<GatherJob> gatherJobs;  // every job of the plane, sorted by kind (general, seam, class 1, share, class 0)
+  std::vector<GatherJob> hostJobs;     // the same list on the host: merged per frame by gatherFrame()
+  int numJobs = 0, numStaged[2] = {}, numSeam = 0, numShare = 0, numFallback = 0;
+  int totalStaged() const { return numSeam + numShare + numStaged[0] + numStaged[1]; }
   // low-pass: register-resident strip jobs grouped by vertical half-size 1..3, and the rest (large vertical kernels)
   DeviceBuffer<StripJob> stripJobs[t360::kStripMaxHy];
   int numStripJobs[t360::kStripMaxHy] = {};
@@ -97,7 +98,7 @@ struct DevicePlan {
   DeviceBuffer<int2> areaXTaps, areaYTaps;
   DeviceBuffer<int> areaXFirst, areaYFirst;
   size_t deviceBytes() const {
-    return samples.bytes() + gatherJobs.bytes() + stripJobs[0].bytes() + stripJobs[1].bytes() + stripJobs[2].bytes() + tileJobs.bytes() + directJobs.bytes() + taps.bytes();
+    return samples.bytes() + records.bytes() + gatherJobs.bytes() + stripJobs[0].bytes() + stripJobs[1].bytes() + stripJobs[2].bytes() + tileJobs.bytes() + directJobs.bytes() + taps.bytes();
   }
 };
 
@@ -120,7 +121,7 @@ EncodeTiledFn tensorMapEncoder() {
   return fn;
 }
 
-// Describes a pitch-linear 8-bit plane to the TMA unit with the staging box of kernel size k.
+// Describes a pitch-linear 8-bit plane to the TMA unit with the staging box of class `cls` of kernel size k.
 bool encodePlaneMap(CUtensorMap* map, const uint8_t* base, int w, int h, int pitch, int k, int cls) {
   EncodeTiledFn enc = tensorMapEncoder();
   if (!enc) return false;
@@ -159,7 +160,7 @@ struct GatherWork {
 // The tiles of all planes of a frame in one list (general, class 1, class 0; luma first inside each kind), rebuilt
 // when a map is regenerated.
 struct FrameJobList {
-  DeviceBuffer<StagedTile> tiles;
+  DeviceBuffer<GatherJob> tiles;
   int numTiles = 0, numPlanes = 0;
   unsigned long long generation = ~0ull;
   DeviceBuffer<int> claimCounter;
@@ -184,6 +185,7 @@ class VideoFrameTransform {
       cudaSetDevice(device_);
       plans_.clear();
       for (auto& w : weights_) w.release();
+      for (auto& w : weightImages_) w.release();
       stagingIn_.release(); stagingOut_.release();
       for (HostRange& r : hostRanges_)
         if (r.pinned) cudaHostUnregister(reinterpret_cast<void*>(r.base));
@@ -469,6 +471,10 @@ class VideoFrameTransform {
     if (!buf.ptr) {
       buf.reserve(static_cast<size_t>(1024) * k * k);
       CU(cudaMemcpy(buf.ptr, host, buf.bytes(), cudaMemcpyHostToDevice));
+      // the frame kernel's shared-memory image of the same table (slot-permuted; two copies for the cubic table)
+      const std::vector<uint8_t> image = t360::buildWeightImage(k, host);
+      weightImages_[k].reserve(image.size());
+      CU(cudaMemcpy(weightImages_[k].ptr, image.data(), image.size(), cudaMemcpyHostToDevice));
     }
     return buf.ptr;
   }
@@ -487,11 +493,16 @@ class VideoFrameTransform {
       CU(cudaMemcpy(d.samples.ptr, g.records.data(), g.records.size() * sizeof(int2), cudaMemcpyHostToDevice));
       d.numFallback = g.numGeneral;
       d.numSeam = g.numSeam;
-      for (int c = 0; c < t360::kNumBoxClasses; ++c) d.numStaged[c] = g.numStaged[c];
+      d.numShare = g.numShare;
+      for (int c = 0; c < 2; ++c) d.numStaged[c] = g.numStaged[c];
       d.numJobs = static_cast<int>(g.jobs.size());
       if (!g.jobs.empty()) {
         d.gatherJobs.reserve(g.jobs.size());
-        CU(cudaMemcpy(d.gatherJobs.ptr, g.jobs.data(), g.jobs.size() * sizeof(StagedTile), cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(d.gatherJobs.ptr, g.jobs.data(), g.jobs.size() * sizeof(GatherJob), cudaMemcpyHostToDevice));
+      }
+      if (!g.compact.empty()) {
+        d.records.reserve(g.compact.size());
+        CU(cudaMemcpy(d.records.ptr, g.compact.data(), g.compact.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
       }
       d.hostJobs = std::move(g.jobs);
     }
@@ -711,7 +722,8 @@ class VideoFrameTransform {
       src = lane.blurred.ptr;
       srcPitch = bp;
     }
-    w.view = t360::PlaneView{src, dOut, plan.samples.ptr, inW, inH, srcPitch, outW, outH, outPitch, plan.tilesPerRow, 0};
+    w.view = t360::PlaneView{src, dOut, plan.samples.ptr, reinterpret_cast<const uint4*>(plan.records.ptr), inW, inH, srcPitch,
+                             outW, outH, outPitch, plan.tilesPerRow, 0};
     // staged tiles need the plane the plan was made for (their windows were proven in-bounds for it) and a
     // TMA-describable layout (16-byte aligned base and pitch); otherwise every tile takes the general kernel
     w.staged = plan.totalStaged() > 0 && !plan.transparent && inW == plan.inW && inH == plan.inH;
@@ -733,7 +745,7 @@ class VideoFrameTransform {
       armScheduler(lane.claimCounter, s);
       t360::FrameGatherParams fp{};
       fp.plane[0] = w.view;
-      fp.weights = weights_[plan.kernelSize].ptr;
+      fp.weightImage = reinterpret_cast<const uint4*>(weightImages_[plan.kernelSize].ptr);
       fp.kernelSize = plan.kernelSize;
       fp.numPlanes = 1;
       t360::StagedParams jobs{plan.gatherJobs.ptr, plan.numJobs, lane.claimCounter.ptr};
@@ -750,17 +762,17 @@ class VideoFrameTransform {
   void gatherFrame(const GatherWork* work, int numPlanes, cudaStream_t s) {
     FrameJobList& f = frameJobs_;
     if (f.generation != planGeneration_ || f.numPlanes != numPlanes) {
-      std::vector<StagedTile> merged;
-      for (int kind : {t360::kJobGeneral, t360::kJobSeam, 1, 0})
+      std::vector<GatherJob> merged;
+      for (int kind : {t360::kJobGeneral, t360::kJobSeam, t360::kJobClass1, t360::kJobShare, t360::kJobClass0})
         for (int p = 0; p < numPlanes; ++p)
-          for (StagedTile t : work[p].plan->hostJobs) {
+          for (GatherJob t : work[p].plan->hostJobs) {
             if (((t.outY >> t360::kJobKindShift) & t360::kJobKindMask) != kind) continue;
             t.outY |= p << t360::kJobPlaneShift;
             merged.push_back(t);
           }
       CU(cudaStreamSynchronize(s));  // a previous frame may still be reading the old list
       f.tiles.reserve(merged.size());
-      CU(cudaMemcpy(f.tiles.ptr, merged.data(), merged.size() * sizeof(StagedTile), cudaMemcpyHostToDevice));
+      CU(cudaMemcpy(f.tiles.ptr, merged.data(), merged.size() * sizeof(GatherJob), cudaMemcpyHostToDevice));
       f.numTiles = static_cast<int>(merged.size());
       f.numPlanes = numPlanes;
       f.generation = planGeneration_;
@@ -772,7 +784,7 @@ class VideoFrameTransform {
       fp.plane[p] = work[p].view;
       for (int c = 0; c < t360::kNumBoxClasses; ++c) maps[p][c] = work[p].maps[c];
     }
-    fp.weights = weights_[work[0].plan->kernelSize].ptr;
+    fp.weightImage = reinterpret_cast<const uint4*>(weightImages_[work[0].plan->kernelSize].ptr);
     fp.kernelSize = work[0].plan->kernelSize;
     fp.numPlanes = numPlanes;
     t360::StagedParams jobs{f.tiles.ptr, f.numTiles, f.claimCounter.ptr};
@@ -791,7 +803,8 @@ class VideoFrameTransform {
   FrameTransformContext ctx_;
   std::mutex mu_;
   std::map<int, DevicePlan> plans_;
-  DeviceBuffer<int16_t> weights_[9];
+  DeviceBuffer<int16_t> weights_[9];       // OpenCV's tables [1024][k][k] (general kernels), by kernel size
+  DeviceBuffer<uint8_t> weightImages_[9];  // their shared-memory images for the frame kernel
   DeviceBuffer<uint8_t> stagingIn_, stagingOut_;
   // opt-in page-locking of recurring pageable caller planes (ffmpeg recycles its frame pool): see pinIfRecurring()
   struct HostRange { uintptr_t base; size_t bytes; int seen; bool pinned; };
@@ -864,7 +877,8 @@ T360_API const float* T360B200_hostPlanMap(const T360HostPlan* plan) { return pl
 T360_API const int32_t* T360B200_hostPlanSamples(const T360HostPlan* plan) {
   return plan && !plan->plan.samples.empty() ? reinterpret_cast<const int32_t*>(plan->plan.samples.data()) : nullptr;
 }
-T360_API int T360B200_hostPlanGather(T360HostPlan* plan, int info[8], const int32_t** jobs, const int32_t** records) {
+T360_API int T360B200_hostPlanGather(T360HostPlan* plan, int info[10], const int32_t** jobs, const int32_t** records,
+                                     const uint32_t** compact) {
   if (!plan || !info || plan->plan.kernelSize <= 0) return 0;
   try {
     if (!plan->gatherBuilt) {
@@ -878,8 +892,10 @@ T360_API int T360B200_hostPlanGather(T360HostPlan* plan, int info[8], const int3
   const t360::GatherPlan& g = plan->gather;
   info[0] = g.tilesPerRow; info[1] = g.tileRows; info[2] = g.tileH; info[3] = static_cast<int>(g.jobs.size());
   info[4] = g.numStaged[0]; info[5] = g.numStaged[1]; info[6] = g.numSeam; info[7] = g.numGeneral;
+  info[8] = g.numShare; info[9] = static_cast<int>(g.compact.size());
   if (jobs) *jobs = g.jobs.empty() ? nullptr : reinterpret_cast<const int32_t*>(g.jobs.data());
   if (records) *records = reinterpret_cast<const int32_t*>(g.records.data());
+  if (compact) *compact = g.compact.empty() ? nullptr : g.compact.data();
   return 1;
 }
 T360_API int T360B200_hostPlanSegment(const T360HostPlan* plan, int i, int rect[4], int numTaps[2], const float** kx,
@@ -893,6 +909,18 @@ T360_API int T360B200_hostPlanSegment(const T360HostPlan* plan, int i, int rect[
   return 1;
 }
 T360_API int T360B200_remapTable(int interpolationAlg, const int16_t** table) { return t360::remapTable(interpolationAlg, table); }
+T360_API int T360B200_weightImage(int interpolationAlg, const uint8_t** image) {
+  static std::mutex mu;
+  static std::map<int, std::vector<uint8_t>> images;
+  const int16_t* table = nullptr;
+  const int k = t360::remapTable(interpolationAlg, &table);
+  if (k < 2 || !image) return 0;
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = images.find(k);
+  if (it == images.end()) it = images.emplace(k, t360::buildWeightImage(k, table)).first;
+  *image = it->second.data();
+  return static_cast<int>(it->second.size());
+}
 
 T360_API int T360B200_transformFramePlaneAsync(VideoFrameTransform* t, const uint8_t* dIn, uint8_t* dOut, int inW, int inH,
                                                int inPitch, int outW, int outH, int outPitch, int planIndex, void* stream) {

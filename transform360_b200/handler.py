@@ -97,7 +97,9 @@ def load(path: os.PathLike | None = None):
     L.T360B200_hostPlanSegment.restype = ci
     L.T360B200_hostPlanSegment.argtypes = [vp, ci, C.POINTER(ci), C.POINTER(ci), C.POINTER(vp), C.POINTER(vp)]
     L.T360B200_hostPlanGather.restype = ci
-    L.T360B200_hostPlanGather.argtypes = [vp, C.POINTER(ci), C.POINTER(vp), C.POINTER(vp)]
+    L.T360B200_hostPlanGather.argtypes = [vp, C.POINTER(ci), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
+    L.T360B200_weightImage.restype = ci
+    L.T360B200_weightImage.argtypes = [ci, C.POINTER(vp)]
     L.T360B200_remapTable.restype = ci
     L.T360B200_remapTable.argtypes = [ci, C.POINTER(vp)]
     L.T360B200_transformFramePlaneAsync.restype = ci
@@ -128,7 +130,7 @@ EXPORTED_SYMBOLS = [
     "VideoFrameTransform_new", "VideoFrameTransform_delete", "VideoFrameTransform_generateMapForPlane",
     "VideoFrameTransform_transformFramePlane", "T360B200_hostPlanCreate", "T360B200_hostPlanDestroy",
     "T360B200_hostPlanInfo", "T360B200_hostPlanMap", "T360B200_hostPlanSamples", "T360B200_hostPlanSegment",
-    "T360B200_hostPlanGather",
+    "T360B200_hostPlanGather", "T360B200_weightImage",
     "T360B200_remapTable", "T360B200_transformFramePlaneAsync", "T360B200_transformFrameAsync",
     "T360B200_lowPassPlaneAsync",
     "T360B200_setPinHostPlanes", "T360B200_synchronize", "T360B200_stream", "T360B200_kernelLaunchCount", "T360B200_planDeviceBytes",
@@ -267,20 +269,23 @@ class HostPlan:
 
     def gather_plan(self):
         """Jobs and record layout the persistent gather kernel works from (T360B200_hostPlanGather).  Returns a dict:
-        tiles_per_row, tile_rows, tile_h, counts {class0, class1, seam, general}, jobs int32[n][4] (None when the plan
-        is not staged), records int32[tiles][tile_h][32][2]."""
-        info = (C.c_int * 8)()
-        jobs, recs = C.c_void_p(), C.c_void_p()
-        if not self._lib.T360B200_hostPlanGather(self._h, info, C.byref(jobs), C.byref(recs)):
+        tiles_per_row, tile_rows, tile_h (grid of the full records), counts {class0, class1, seam, general, share},
+        jobs int32[n][4] = {outX, outY | kind << 24, boxX | boxY << 16, recordOffset / 16} (None when the plan is not
+        staged), records int32[tiles][tile_h][32][2] (full records), compact uint32[] (compact records)."""
+        info = (C.c_int * 10)()
+        jobs, recs, comp = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        if not self._lib.T360B200_hostPlanGather(self._h, info, C.byref(jobs), C.byref(recs), C.byref(comp)):
             raise ValueError("T360B200_hostPlanGather failed")
         tpr, trows, th, nj = info[0], info[1], info[2], info[3]
         n = tpr * trows * th * 32 * 2
         records = np.frombuffer((C.c_int32 * n).from_address(recs.value), np.int32).reshape(tpr * trows, th, 32, 2).copy()
-        j = None
+        j = compact = None
         if nj and jobs.value:
             j = np.frombuffer((C.c_int32 * (nj * 4)).from_address(jobs.value), np.int32).reshape(nj, 4).copy()
-        return dict(tiles_per_row=tpr, tile_rows=trows, tile_h=th, jobs=j, records=records,
-                    counts=dict(class0=info[4], class1=info[5], seam=info[6], general=info[7]))
+        if info[9] and comp.value:
+            compact = np.frombuffer((C.c_uint32 * info[9]).from_address(comp.value), np.uint32).copy()
+        return dict(tiles_per_row=tpr, tile_rows=trows, tile_h=th, jobs=j, records=records, compact=compact,
+                    counts=dict(class0=info[4], class1=info[5], seam=info[6], general=info[7], share=info[8]))
 
     def segments(self):
         out = []
@@ -301,6 +306,16 @@ def remap_table(interpolation_alg: int) -> np.ndarray | None:
     if k < 2:
         return None
     return np.frombuffer((C.c_int16 * (1024 * k * k)).from_address(p.value), np.int16).reshape(1024, k, k).copy()
+
+
+def weight_image(interpolation_alg: int) -> np.ndarray | None:
+    """The frame kernel's shared-memory image of the interpolation table (bytes)."""
+    L = load()
+    p = C.c_void_p()
+    n = L.T360B200_weightImage(interpolation_alg, C.byref(p))
+    if n <= 0:
+        return None
+    return np.frombuffer((C.c_uint8 * n).from_address(p.value), np.uint8).copy()
 
 
 def kernel_launch_count() -> int:
