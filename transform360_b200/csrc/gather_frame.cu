@@ -148,39 +148,53 @@ __device__ __forceinline__ int biasedToByte(int acc) { return min(max(acc >> 15,
 template <int K>
 __device__ __forceinline__ uint32_t slotOffset(uint32_t field) { return K == 2 ? field >> 1 : field; }
 
-// ---- share job: one register window per output column, slid down 8 rows ---------------------------------------------
-template <int K, int PITCH, int VS>
-__device__ __forceinline__ void computeShareJob(const PlaneView& pv, uint32_t stageAddr, int outX, int outY, const uint4& rec,
-                                                uint32_t header, uint32_t wAddr, int warp) {
-  static_assert(PITCH % 4 == 0 && (K == 4 || K == 8), "");
-  const int wx = warp & 1, wy = warp >> 1;
-  const int dstPitch = pv.dstPitch;
-  uint8_t* const dst = pv.dst + (size_t)(outY + wy * kShareRows) * dstPitch + (outX + wx * 32 + (int)(header >> kRecordColumnShift));
-  uint32_t rowAddr = stageAddr + (header & 0x3ffcu);
+// ---- share job: one register window per output column, slid down ROWS rows -------------------------------------------
+// Consecutive pixels of a column start 1 or 2 source rows apart (bit 0 of the pixel record: the second row).  The part
+// of the window's address that is known at compile time (one row per pixel) lives in the immediate offsets of the
+// loads; `base` only takes up the second rows.  No branch: the row that only a two-row step needs is a predicated load.
+__device__ __forceinline__ uint32_t packBytes(int hi, int lo) {  // sat_u8(hi) << 8 | sat_u8(lo): I2IP.U8.S32.SAT
+  uint32_t r;
+  asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(hi), "r"(lo), "r"(0));
+  return r;
+}
+
+template <int K, int PITCH, int VS, int ROWS>
+__device__ __forceinline__ void computeShareJob(uint8_t* dst, int dstPitch, uint32_t stageAddr, const uint4 (&rec)[ROWS / 8],
+                                                uint32_t header, uint32_t wAddr) {
+  static_assert(PITCH % 4 == 0 && (K == 4 || K == 8) && ROWS % 8 == 0, "");
+  uint32_t base = stageAddr + (header & 0x7ffcu);
   const int sh = (int)(header << 3);  // the funnel shift takes the low five bits: 8 * (offset & 3)
   RowBytes<K> W[K];
-  staticFor<K>([&](auto R) { W[decltype(R)::value] = loadRow<K, decltype(R)::value * PITCH>(rowAddr, sh); });
-  const uint32_t words[4] = {rec.x, rec.y, rec.z, rec.w};
-  staticFor<kShareRows>([&](auto J) {
+  staticFor<K>([&](auto R) { W[decltype(R)::value] = loadRow<K, decltype(R)::value * PITCH>(base, sh); });
+  int accPrev = 0;
+  staticFor<ROWS>([&](auto J) {
     constexpr int j = decltype(J)::value;
-    const uint32_t r = (j & 1) ? words[j >> 1] >> 16 : words[j >> 1];
+    const uint4& block = rec[j >> 3];
+    const uint32_t word = ((j >> 1) & 3) == 0 ? block.x : (((j >> 1) & 3) == 1 ? block.y : (((j >> 1) & 3) == 2 ? block.z : block.w));
+    const uint32_t r = (j & 1) ? word >> 16 : word;
     if constexpr (j > 0) {
-      const uint32_t d = r & 3u;  // source rows between this pixel's window and the previous one's: 0, 1 or 2
-      if (d != 0) {
-        rowAddr += d * PITCH;
-        const RowBytes<K> last = loadRow<K, (K - 1) * PITCH>(rowAddr, sh);
-        RowBytes<K> prev = W[K - 1];
-        if (d == 2) prev = loadRow<K, (K - 2) * PITCH>(rowAddr, sh);
+      const bool two = (r & 1u) != 0;
+      // the previous window starts at base + (j - 1) * PITCH; this one 1 (+ 1) rows below
+      const RowBytes<K> below = loadRow<K, (j - 1 + K) * PITCH>(base, sh);
+      RowBytes<K> below2 = below;
+      if (two) below2 = loadRow<K, (j + K) * PITCH>(base, sh);
 #pragma unroll
-        for (int q = 0; q + 2 < K; ++q)
+      for (int q = 0; q + 2 < K; ++q)
 #pragma unroll
-          for (int i = 0; i < (K == 8 ? 2 : 1); ++i) W[q].b[i] = d == 1 ? W[q + 1].b[i] : W[q + 2].b[i];
-        W[K - 2] = prev;
-        W[K - 1] = last;
-      }
+        for (int i = 0; i < (K == 8 ? 2 : 1); ++i) W[q].b[i] = two ? W[q + 2].b[i] : W[q + 1].b[i];
+#pragma unroll
+      for (int i = 0; i < (K == 8 ? 2 : 1); ++i) W[K - 2].b[i] = two ? below.b[i] : W[K - 1].b[i];
+      W[K - 1] = below2;
+      if (two) base += PITCH;
     }
-    const int acc = foldRows<K, VS>(W, wAddr + (r & kSlotFieldMask));
-    dst[(size_t)j * dstPitch] = (uint8_t)biasedToByte(acc);
+    const int acc = foldRows<K, VS>(W, wAddr + (r & kSlotFieldMask)) >> 15;
+    if constexpr (j & 1) {
+      const uint32_t pair = packBytes(acc, accPrev);
+      dst[(size_t)(j - 1) * dstPitch] = (uint8_t)pair;
+      dst[(size_t)j * dstPitch] = (uint8_t)(pair >> 8);
+    } else {
+      accPrev = acc;
+    }
   });
 }
 
@@ -208,230 +222,266 @@ __device__ __forceinline__ void computeTileJob(const PlaneView& pv, uint32_t sta
   });
 }
 
+// ---- general job: taps through L1, any border case ------------------------------------------------------------------
+// Pole caps and whatever else fits no staging box: latency-bound.  So the four records of a thread are requested
+// together, then the windows of all (K = 8: two) pixels, and only then the arithmetic starts: two round trips to L2 /
+// DRAM per job instead of eight.  Windows that touch a plane border (rare) take the per-tap path of gatherPixel.
+template <int K, int VS>
+__device__ __forceinline__ void computeGeneralJob(const PlaneView& pv, int outX, int outY, const unsigned char* wsmem, uint32_t wAddr,
+                                                  int lane, int warp) {
+  SrcView sv;
+  sv.bytes = pv.src;
+  sv.misalign = (int)(reinterpret_cast<uintptr_t>(pv.src) & 3);
+  sv.words = reinterpret_cast<const uint32_t*>(pv.src - sv.misalign);
+  sv.w = pv.srcW; sv.h = pv.srcH; sv.pitch = pv.srcPitch;
+  const int y0 = outY + warp * kRowsPerThread;
+  if (outX + lane >= pv.dstW) return;
+  // full records, tile-major over tiles of 32 x gatherTileH(K) pixels
+  const int2* segment = pv.samples + ((size_t)(y0 / gatherTileH(K)) * pv.tilesPerRow + outX / kGatherTileW) * gatherTileH(K) * kGatherTileW +
+                        (y0 % gatherTileH(K)) * kGatherTileW + lane;
+  int2 full[kRowsPerThread];
+#pragma unroll
+  for (int j = 0; j < kRowsPerThread; ++j) full[j] = y0 + j < pv.dstH ? loadPlan(segment + j * kGatherTileW) : make_int2(0, 0);
+  constexpr int kBatch = K == 8 ? 2 : 4;  // windows in flight per thread (registers)
+#pragma unroll
+  for (int jb = 0; jb < kRowsPerThread; jb += kBatch) {
+    RowBytes<K> W[kBatch][K];
+    bool interior[kBatch];
+#pragma unroll
+    for (int b = 0; b < kBatch; ++b) {
+      const int col0 = recordCol0(full[jb + b].x), row0 = full[jb + b].y >> 10;
+      // no wrapping, and the aligned word reads stay inside the row even when the pitch equals the width
+      interior[b] = y0 + jb + b < pv.dstH && col0 >= 0 && row0 >= 0 && col0 + (K == 2 ? 8 : K + 4) <= sv.w && row0 + K <= sv.h;
+#pragma unroll
+      for (int r = 0; r < K; ++r) {
+        W[b][r].b[0] = 0;
+        if constexpr (K == 8) W[b][r].b[1] = 0;
+        if (interior[b]) {
+          const int off = (row0 + r) * sv.pitch + col0 + sv.misalign;
+          const uint32_t* q = sv.words + (off >> 2);
+          const int sh = (off & 3) * 8;
+          const uint32_t q0 = __ldg(q), q1 = __ldg(q + 1);
+          W[b][r].b[0] = __funnelshift_r(q0, q1, sh);
+          if constexpr (K == 8) W[b][r].b[1] = __funnelshift_r(q1, __ldg(q + 2), sh);
+        }
+      }
+    }
+#pragma unroll
+    for (int b = 0; b < kBatch; ++b) {
+      const int j = jb + b;
+      if (y0 + j >= pv.dstH) continue;
+      int v;
+      if (interior[b]) v = biasedToByte(foldRows<K, VS>(W[b], wAddr + slotOffset<K>((uint32_t)weightSlotOf(K, full[j].y & 1023) << 4)));
+      else v = gatherPixel<K, false, VS>(sv, wsmem, recordCol0(full[j].x), full[j].y);
+      pv.dst[(size_t)(y0 + j) * pv.dstPitch + outX + recordColumn(full[j].x)] = (uint8_t)v;
+    }
+  }
+}
+
 struct FrameTensorMaps {
   CUtensorMap map[kMaxFramePlanes][kNumBoxClasses];
 };
 
-template <int K, int COPIES, int GROUPS>
-__host__ __device__ constexpr int frameSmemBytes() {
-  return weightImageBytes(K, COPIES) + GROUPS * 2 * stageBytesOf(K) + (GROUPS + 1) * 64;
+__device__ __forceinline__ void mbarArrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smemAddr(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbarTest(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(smemAddr(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ uint4 ldsVec(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint32_t ldsWord(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
 }
 
+// shared-memory layout: weights | per group {box 0, box 1, records 0, records 1} | planes | barriers
 template <int K, int COPIES, int GROUPS>
-__global__ void __launch_bounds__(GROUPS * kGroupThreads, 1)
+struct FrameLayout {
+  static constexpr int kWeights = weightImageBytes(K, COPIES);
+  static constexpr int kStage = stageBytesOf(K), kRec = stageRecordBytes(K);
+  static constexpr int kGroupBytes = 2 * kStage + 2 * kRec;
+  static constexpr int kPlanes = kWeights + GROUPS * kGroupBytes;
+  static constexpr int kBars = kPlanes + 256;  // per group: full[2], empty[2]; then the weight barrier
+  static constexpr int kTotal = kBars + GROUPS * 32 + 16;
+  static_assert(sizeof(PlaneView) * kMaxFramePlanes <= 256, "");
+  static_assert(kStage % 128 == 0 && kRec % 128 == 0 && kWeights % 128 == 0, "TMA / bulk-copy destinations");
+};
+
+template <int K, int COPIES, int GROUPS>
+__global__ void __launch_bounds__(GROUPS * (kGroupWarps + 1) * 32, 1)
 gatherFrameKernel(const __grid_constant__ FrameGatherParams p, StagedParams jobs, const __grid_constant__ FrameTensorMaps maps) {
-  constexpr int VS = weightVectorStride(K, COPIES), kWeights = weightImageBytes(K, COPIES), kStage = stageBytesOf(K);
+  using L = FrameLayout<K, COPIES, GROUPS>;
+  constexpr int VS = weightVectorStride(K, COPIES), kStage = L::kStage, kRec = L::kRec;
   constexpr uint32_t kBox0 = stageBoxW(K, 0) * stageBoxH(K, 0), kBox1 = stageBoxW(K, 1) * stageBoxH(K, 1),
                      kBoxShare = stageBoxW(K, 2) * stageBoxH(K, 2);
   static_assert(kBox1 + 64 <= 2 * kStage && kBox0 + 64 <= kStage && kBoxShare + 64 <= kStage, "boxes must fit their stage buffers");
-  static_assert(kBox0 % 16 == 0 && kStage % 128 == 0 && kWeights % 128 == 0, "alignment of the seam merge / TMA destinations");
   extern __shared__ __align__(128) unsigned char smem[];
-  const int group = threadIdx.x / kGroupThreads, t = threadIdx.x % kGroupThreads;
-  const int lane = t & 31, warp = t >> 5;
   unsigned char* wsmem = smem;
-  unsigned char* stage0 = smem + kWeights + group * (2 * kStage);
-  uint64_t* barBase = reinterpret_cast<uint64_t*>(smem + kWeights + GROUPS * 2 * kStage);
-  uint64_t* bars = barBase + group * 8;  // [0], [1]: stage buffers, [2]: both buffers together, [3]: two claim slots
-  uint64_t* weightBar = barBase + GROUPS * 8;
+  PlaneView* planes = reinterpret_cast<PlaneView*>(smem + L::kPlanes);
+  uint64_t* barBase = reinterpret_cast<uint64_t*>(smem + L::kBars);  // group g: full[0], full[1], empty[0], empty[1]
+  uint64_t* weightBar = barBase + GROUPS * 4;
+  const int warpId = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int kProducerWarp = GROUPS * kGroupWarps;
 
   // Programmatic dependent launch: the next launch on the stream (the next frame's gather) may place its CTAs as soon
-  // as ours retire, and run its prologue -- which touches only constant data: weights, job list, sampling records --
-  // under our tail.  Everything an earlier kernel may have written (the source planes, the scheduler counters) is
-  // only touched after griddepcontrol.wait below.
+  // as ours retire, and run its prologue -- which touches only constant data: weights, job list -- under our tail.
+  // Everything an earlier kernel may have written or may still read (the planes, the scheduler counters) is only
+  // touched after griddepcontrol.wait below.
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (threadIdx.x == 0) {
-    for (int g = 0; g < GROUPS; ++g)
-      for (int i = 0; i < 3; ++i) mbarInit(barBase + g * 8 + i, 1);
+    for (int g = 0; g < GROUPS; ++g) {
+      mbarInit(barBase + g * 4 + 0, 1);
+      mbarInit(barBase + g * 4 + 1, 1);
+      mbarInit(barBase + g * 4 + 2, kGroupWarps);
+      mbarInit(barBase + g * 4 + 3, kGroupWarps);
+    }
     mbarInit(weightBar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    // the weight image (host-permuted, both copies) in four bulk copies
-    mbarExpectTx(weightBar, kWeights);
-    constexpr int kChunk = kWeights / 4;
-    for (int i = 0; i < 4; ++i)
-      bulkCopyToShared(wsmem + i * kChunk, reinterpret_cast<const unsigned char*>(p.weightImage) + i * kChunk, kChunk, weightBar);
   }
+  if (threadIdx.x < kMaxFramePlanes * (int)(sizeof(PlaneView) / 4))
+    reinterpret_cast<uint32_t*>(planes)[threadIdx.x] = reinterpret_cast<const uint32_t*>(p.plane)[threadIdx.x];
   __syncthreads();
 
-  const int worker = blockIdx.x * GROUPS + group, numWorkers = gridDim.x * GROUPS;
-  // Software pipeline, two deep, so that no load is waited for in the iteration that issues it (a warp executes in
-  // order: a header load followed by the record loads that need its fields would stall the whole job on the header):
-  //   iteration n:  issue header(n+2) | issue records(n+1) from header(n+1), already in registers | compute job n
-  auto loadHeader = [&](int i) { return i < jobs.numTiles ? jobs.tiles[i] : GatherJob{0, 0, 0, 0}; };
-  // The header fetched two jobs ahead must not be waited for where it is issued.  The compiler keeps warp-uniform
-  // values in uniform registers and converts a loaded header the moment it arrives; so the load is opaque (asm: four
-  // ordinary registers), and the header becomes uniform -- through a warp reduction whose result the compiler knows
-  // to be uniform -- only at the end of the job, when it has long arrived.  An index past the list reads its last
-  // entry; validity is tracked by the index itself.
-  auto issueHeaderLoad = [&](int i, int (&raw)[4]) {
-    const GatherJob* src = jobs.tiles + min(i, jobs.numTiles - 1);
-    asm volatile("ld.global.nc.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(raw[0]), "=r"(raw[1]), "=r"(raw[2]), "=r"(raw[3]) : "l"(src));
-  };
-  auto uniformHeader = [&](const int (&raw)[4]) {
-    return GatherJob{(int)__reduce_or_sync(0xffffffffu, (unsigned)raw[0]), (int)__reduce_or_sync(0xffffffffu, (unsigned)raw[1]),
-                     (int)__reduce_or_sync(0xffffffffu, (unsigned)raw[2]), (int)__reduce_or_sync(0xffffffffu, (unsigned)raw[3])};
-  };
-  // The plane of a job, field by field through selects on kernel-parameter operands: an indexed load from the
-  // parameter bank instead would put its latency in front of every job's record loads.
-  static_assert(kMaxFramePlanes == 3, "planeOf selects among three planes");
-  const PlaneView &pa = p.plane[0], &pb = p.plane[1], &pc = p.plane[2];
-#define T360_PICK(pl, f) ((pl) == 0 ? pa.f : ((pl) == 1 ? pb.f : pc.f))
-  auto planeOf = [&](const GatherJob& job) {
-    const int pl = job.outY >> kJobPlaneShift;
-    return PlaneView{T360_PICK(pl, src), T360_PICK(pl, dst), T360_PICK(pl, samples), nullptr, T360_PICK(pl, srcW), T360_PICK(pl, srcH),
-                     T360_PICK(pl, srcPitch), T360_PICK(pl, dstW), T360_PICK(pl, dstH), T360_PICK(pl, dstPitch), T360_PICK(pl, tilesPerRow), 0};
-  };
-  auto kindOf = [](const GatherJob& job) { return (job.outY >> kJobKindShift) & kJobKindMask; };
-  // compact records: one 128-bit load per thread (+ one 32-bit column header in a share job); general jobs fetch their
-  // full records when they run (few jobs, latency-bound anyway)
-  auto loadRecords = [&](int i, const GatherJob& job, uint4& rec, uint32_t& header) {
-    rec = make_uint4(0, 0, 0, 0);
-    header = 0;
-    const int kind = kindOf(job);
-    if (i >= jobs.numTiles || kind == kJobGeneral) return;
-    const int pl = job.outY >> kJobPlaneShift;
-    const uint4* base = T360_PICK(pl, records) + (unsigned)job.recordOffset;
-    if (kind == kJobShare) {
-      base += warp * (kShareJobRecordBytes / kGroupWarps / 16);
-      rec = loadRecords128(base + lane);
-      header = loadRecords32(reinterpret_cast<const uint32_t*>(base + 32) + lane);
-    } else {
-      rec = loadRecords128(base + warp * 32 + lane);
+  if (warpId >= kProducerWarp) {
+    // =================================== producers: one warp per group ==============================================
+    const int g = warpId - kProducerWarp;
+    if (g == 0 && lane == 0) {  // the weight image (host-permuted, both copies) in four bulk copies
+      mbarExpectTx(weightBar, L::kWeights);
+      constexpr int kChunk = L::kWeights / 4;
+      for (int i = 0; i < 4; ++i)
+        bulkCopyToShared(wsmem + i * kChunk, reinterpret_cast<const unsigned char*>(p.weightImage) + i * kChunk, kChunk, weightBar);
     }
-  };
-  // Dynamic scheduling: the first four jobs of a group are static (worker + k * numWorkers), every further one is
-  // claimed from a global counter by the group's thread 0 and handed to the other threads through a double-buffered
-  // shared slot across the end-of-job barrier.  The value the atomic returns is not touched in the iteration that
-  // issues it -- a warp executes in order and would sit out the round trip while the rest of the group waits for it at
-  // the barrier -- but one iteration later (in an asm statement, so that the compiler cannot hoist the use).
-  int* claimSlot = reinterpret_cast<int*>(bars + 3);
-  const int claimBase = 4 * numWorkers;
-  int claimedRaw = worker - numWorkers;  // thread 0; claimBase + claimedRaw = the group's fourth static job
-  int i0 = worker, i1 = i0 + numWorkers, i2 = i1 + numWorkers;
-  GatherJob job = loadHeader(i0), jobNext = loadHeader(i1);
-  uint4 rec;
-  uint32_t header;
-  loadRecords(i0, job, rec, header);
-  // q0 / q1: single-buffer boxes (class 0, share) / double-buffer boxes (class 1, seam) this group has consumed;
-  // issued0: single-buffer boxes it has requested.  A single-buffer job with sequence number q lives in stage q & 1 and
-  // completes phase (q >> 1) & 1 of that stage's barrier.
-  uint32_t q0 = 0, q1 = 0, issued0 = 0;
+    // Jobs are claimed kClaimBatch at a time: the first batch of a producer is static, every further one comes from the
+    // global counter.  Lane i holds the header of job i of the batch; the next batch (claim + header loads) is in
+    // flight while the current one is handed out, so neither the atomic nor the loads are waited for, and the records
+    // and source window of its jobs are requested into L2 a batch ahead of the copies into shared memory.
+    const int producer = blockIdx.x * GROUPS + g, dynamicBase = gridDim.x * GROUPS * kClaimBatch;
+    auto loadBatch = [&](int base) {
+      int4 h = make_int4(0, kJobExit << kJobKindShift, 0, 0);
+      if (lane < kClaimBatch && base + lane < jobs.numTiles) h = __ldg(reinterpret_cast<const int4*>(jobs.tiles) + base + lane);
+      return h;
+    };
+    auto prefetchBatch = [&](const int4& h) {
+      const int kind = (h.y >> kJobKindShift) & kJobKindMask;
+      if (kind != kJobShare && kind != kJobClass0 && kind != kJobClass1) return;
+      const int pl = h.y >> kJobPlaneShift;
+      const uint32_t recBytes = kind == kJobShare ? shareJobRecordBytes(K) : kTileJobRecordBytes;
+      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(planes[pl].records + (unsigned)h.w), "r"(recBytes) : "memory");
+      asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];"
+                   ::"l"(reinterpret_cast<uint64_t>(&maps.map[pl][boxClassOf(kind)])), "r"(h.z & 0xffff), "r"(h.z >> 16) : "memory");
+    };
+    int4 batch = loadBatch(producer * kClaimBatch);
+    asm volatile("griddepcontrol.wait;" ::: "memory");  // earlier kernels on the stream are complete and visible from here on
+    int claimed = 0;
+    if (lane == 0) claimed = atomicAdd(jobs.claimCounter, kClaimBatch);
+    claimed = __shfl_sync(0xffffffffu, claimed, 0);
+    int4 batchNext = loadBatch(dynamicBase + claimed);
+    prefetchBatch(batch);
+    prefetchBatch(batchNext);
+    unsigned char* groupBase = smem + L::kWeights + g * L::kGroupBytes;
+    uint64_t* full = barBase + g * 4;
+    uint64_t* empty = full + 2;
+    int pos = 0;
+    uint32_t n = 0;  // stages handed to the group so far: stage = n & 1, use count = n >> 1
+    for (;;) {
+      if (pos == kClaimBatch) {  // next batch; start claiming the one after
+        batch = batchNext;
+        pos = 0;
+        if (lane == 0) claimed = atomicAdd(jobs.claimCounter, kClaimBatch);
+        claimed = __shfl_sync(0xffffffffu, claimed, 0);
+        batchNext = loadBatch(dynamicBase + claimed);
+        prefetchBatch(batchNext);
+      }
+      int4 h;
+      h.x = __shfl_sync(0xffffffffu, batch.x, pos); h.y = __shfl_sync(0xffffffffu, batch.y, pos);
+      h.z = __shfl_sync(0xffffffffu, batch.z, pos); h.w = __shfl_sync(0xffffffffu, batch.w, pos);
+      ++pos;
+      const int kind = (h.y >> kJobKindShift) & kJobKindMask;
+      const bool twoStages = kind == kJobClass1;  // its box spans both stage buffers: both must be free
+      mbarWait(empty + (n & 1), ((n >> 1) & 1) ^ 1);
+      if (twoStages) mbarWait(empty + ((n + 1) & 1), (((n + 1) >> 1) & 1) ^ 1);
+      if (lane == 0) {
+        const uint32_t st = n & 1;
+        unsigned char* rec = groupBase + 2 * kStage + st * kRec;
+        *reinterpret_cast<int4*>(rec) = h;
+        if (kind == kJobShare || kind == kJobClass0 || kind == kJobClass1) {
+          const int pl = h.y >> kJobPlaneShift;
+          const uint32_t boxBytes = kind == kJobShare ? kBoxShare : (kind == kJobClass0 ? kBox0 : kBox1);
+          const uint32_t recBytes = kind == kJobShare ? shareJobRecordBytes(K) : kTileJobRecordBytes;
+          mbarExpectTx(full + st, boxBytes + recBytes);
+          // class-1 boxes start at the first stage buffer whatever the stage (both are free)
+          tmaLoadBox(groupBase + (twoStages ? 0 : st * kStage), &maps.map[pl][boxClassOf(kind)], h.z & 0xffff, h.z >> 16, full + st);
+          bulkCopyToShared(rec + 128, planes[pl].records + (unsigned)h.w, recBytes, full + st);
+        } else {
+          mbarArrive(full + st);  // general job / end of list: the header is all there is
+        }
+        if (twoStages) {  // the second stage of the pair is taken too: a no-op job stands for it
+          unsigned char* rec2 = groupBase + 2 * kStage + (st ^ 1) * kRec;
+          *reinterpret_cast<int4*>(rec2) = make_int4(0, kJobNop << kJobKindShift, 0, 0);
+          mbarArrive(full + (st ^ 1));
+        }
+      }
+      __syncwarp();
+      n += twoStages ? 2u : 1u;
+      if (kind == kJobExit) break;
+    }
+    // the producer that finishes last re-arms the scheduler for the next launch (claimCounter[0] = claims, [1] = finished)
+    if (lane == 0 && atomicAdd(jobs.claimCounter + 1, 1) == (int)(gridDim.x * GROUPS) - 1) {
+      jobs.claimCounter[0] = 0;
+      jobs.claimCounter[1] = 0;
+      __threadfence();
+    }
+    return;
+  }
+
+  // ===================================== consumers ===================================================================
+  const int group = warpId / kGroupWarps, warp = warpId % kGroupWarps;
+  unsigned char* groupBase = smem + L::kWeights + group * L::kGroupBytes;
+  const uint32_t boxAddr = smemAddr(groupBase), recAddr = smemAddr(groupBase + 2 * kStage);
+  uint64_t* full = barBase + group * 4;
+  uint64_t* empty = full + 2;
   const uint32_t wAddr = smemAddr(wsmem);
   mbarWait(weightBar, 0);
-  asm volatile("griddepcontrol.wait;" ::: "memory");  // earlier kernels on the stream are complete and visible from here on
-  auto pipelined = [](int kind) { return kind == kJobClass0 || kind == kJobShare; };
-  auto requestBox = [&](const GatherJob& j) {  // thread 0 of the group only
-    const uint32_t st = issued0 & 1;
-    const bool share = kindOf(j) == kJobShare;
-    mbarExpectTx(&bars[st], share ? kBoxShare : kBox0);
-    tmaLoadBox(stage0 + st * kStage, &maps.map[j.outY >> kJobPlaneShift][share ? 2 : 0], j.boxXY & 0xffff, j.boxXY >> 16, &bars[st]);
-  };
-  for (uint32_t it = 0; i0 < jobs.numTiles; ++it) {
-    const int next = i1;
-    if (t == 0) {
-      int claimed;
-      asm volatile("add.s32 %0, %1, %2;" : "=r"(claimed) : "r"(claimedRaw), "r"(claimBase));
-      claimSlot[it & 1] = claimed;
-      claimedRaw = atomicAdd(jobs.claimCounter, 1);
-    }
-    int headerAfterNext[4];
-    issueHeaderLoad(i2, headerAfterNext);
-    uint4 recNext;
-    uint32_t headerNext;
-    loadRecords(next, jobNext, recNext, headerNext);
-    const int kind = kindOf(job), outY = job.outY & kJobRowMask;
-    const PlaneView pv = planeOf(job);
-    const bool nextPipelined = next < jobs.numTiles && pipelined(kindOf(jobNext));
-    if (pipelined(kind)) {
-      if (issued0 == q0) {  // not prefetched (first job, or it follows a job that needed both stages)
-        if (t == 0) requestBox(job);
-        ++issued0;
-      }
-      if (nextPipelined) {  // the other stage was released by the barrier that ended the previous job
-        if (t == 0) requestBox(jobNext);
-        ++issued0;
-      }
-      const uint32_t st = q0 & 1;
-      mbarWait(&bars[st], (q0 >> 1) & 1);
-      const uint32_t stageAddr = smemAddr(stage0 + st * kStage);
-      if (kind == kJobShare) {
-        if constexpr (K >= 4) computeShareJob<K, stageBoxW(K, 2), VS>(pv, stageAddr, job.outX, outY, rec, header, wAddr, warp);
-      } else {
-        computeTileJob<K, stageBoxW(K, 0), VS>(pv, stageAddr, job.outX, outY, rec, wAddr, warp);
-      }
-      ++q0;
-    } else if (kind == kJobClass1) {
-      if (t == 0) {  // no single-buffer box is in flight here: the larger box may span both stage buffers
-        mbarExpectTx(&bars[2], kBox1);
-        tmaLoadBox(stage0, &maps.map[job.outY >> kJobPlaneShift][1], job.boxXY & 0xffff, job.boxXY >> 16, &bars[2]);
-      }
-      mbarWait(&bars[2], q1 & 1);
-      computeTileJob<K, stageBoxW(K, 1), VS>(pv, smemAddr(stage0), job.outX, outY, rec, wAddr, warp);
-      ++q1;
-    } else if (kind == kJobSeam) {
-      // two complementary class-0 boxes (zero-filled outside the plane), one per stage buffer, OR-ed into the first
-      const int boxX = job.boxXY & 0xffff, boxY = job.boxXY >> 16;
-      if (t == 0) {
-        mbarExpectTx(&bars[2], 2 * kBox0);
-        const CUtensorMap* m = &maps.map[job.outY >> kJobPlaneShift][0];
-        tmaLoadBox(stage0, m, boxX, boxY, &bars[2]);
-        tmaLoadBox(stage0 + kStage, m, boxX - pv.srcW, boxY, &bars[2]);
-      }
-      mbarWait(&bars[2], q1 & 1);
-      {
-        uint4* a = reinterpret_cast<uint4*>(stage0);
-        const uint4* b = reinterpret_cast<const uint4*>(stage0 + kStage);
-        for (int i = t; i < (int)(kBox0 / 16); i += kGroupThreads) {
-          uint4 x = a[i];
-          const uint4 y = b[i];
-          x.x |= y.x; x.y |= y.y; x.z |= y.z; x.w |= y.w;
-          a[i] = x;
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // these writes precede later TMA writes to the stage
-      }
-      groupBarrier(group);
-      computeTileJob<K, stageBoxW(K, 0), VS>(pv, smemAddr(stage0), job.outX, outY, rec, wAddr, warp);
-      ++q1;
-    } else {
-      if (nextPipelined && issued0 == q0) {  // both stages are idle during a general job: start the next box now
-        if (t == 0) requestBox(jobNext);
-        ++issued0;
-      }
-      SrcView sv;
-      sv.bytes = pv.src;
-      sv.misalign = (int)(reinterpret_cast<uintptr_t>(pv.src) & 3);
-      sv.words = reinterpret_cast<const uint32_t*>(pv.src - sv.misalign);
-      sv.w = pv.srcW; sv.h = pv.srcH; sv.pitch = pv.srcPitch;
-      const int y0 = outY + warp * kRowsPerThread;
-      if (job.outX + lane < pv.dstW) {
-        // full records, tile-major over tiles of 32 x gatherTileH(K) pixels
-        const int2* segment = pv.samples + ((size_t)(y0 / gatherTileH(K)) * pv.tilesPerRow + job.outX / kGatherTileW) * gatherTileH(K) * kGatherTileW +
-                              (y0 % gatherTileH(K)) * kGatherTileW + lane;
+  asm volatile("griddepcontrol.wait;" ::: "memory");  // the planes may still be in use by earlier kernels until here
+  for (uint32_t n = 0;; ++n) {
+    const uint32_t st = n & 1;
+    mbarWait(full + st, (n >> 1) & 1);
+    const uint32_t rec = recAddr + st * kRec;
+    const uint4 h = ldsVec(rec);
+    const int kind = ((int)h.y >> kJobKindShift) & kJobKindMask;
+    if (kind == kJobExit) break;
+    const int outX = (int)h.x, outY = (int)h.y & kJobRowMask;
+    const PlaneView& pv = planes[(int)h.y >> kJobPlaneShift];
+    if (kind == kJobShare) {
+      if constexpr (K >= 4) {
+        const uint32_t mine = rec + 128 + warp * shareWarpRecordBytes(K);
+        uint4 r[shareRows(K) / 8];
 #pragma unroll
-        for (int j = 0; j < kRowsPerThread; ++j) {
-          if (y0 + j >= pv.dstH) break;
-          const int2 full = loadPlan(segment + j * kGatherTileW);
-          const int v = gatherPixel<K, false, VS>(sv, wsmem, recordCol0(full.x), full.y);
-          pv.dst[(size_t)(y0 + j) * pv.dstPitch + job.outX + recordColumn(full.x)] = (uint8_t)v;
-        }
+        for (int b = 0; b < shareRows(K) / 8; ++b) r[b] = ldsVec(mine + b * 512 + lane * 16);
+        const uint32_t header = ldsWord(mine + shareRows(K) / 8 * 512 + lane * 4);
+        uint8_t* dst = pv.dst + (size_t)(outY + (warp >> 1) * shareRows(K)) * pv.dstPitch + (outX + (warp & 1) * 32 + (int)(header >> kRecordColumnShift));
+        computeShareJob<K, stageBoxW(K, 2), VS, shareRows(K)>(dst, pv.dstPitch, boxAddr + st * kStage, r, header, wAddr);
       }
+    } else if (kind == kJobClass0) {
+      computeTileJob<K, stageBoxW(K, 0), VS>(pv, boxAddr + st * kStage, outX, outY, ldsVec(rec + 128 + warp * 512 + lane * 16), wAddr, warp);
+    } else if (kind == kJobClass1) {
+      computeTileJob<K, stageBoxW(K, 1), VS>(pv, boxAddr, outX, outY, ldsVec(rec + 128 + warp * 512 + lane * 16), wAddr, warp);
+    } else if (kind == kJobGeneral) {
+      computeGeneralJob<K, VS>(pv, outX, outY, wsmem, wAddr, lane, warp);
     }
-    groupBarrier(group);  // everyone is done with this job's stage before it is refilled (and sees the claimed index)
-    i0 = i1; i1 = i2; i2 = claimSlot[it & 1];
-    job = jobNext;
-    jobNext = uniformHeader(headerAfterNext);
-    // (asm: the copies stay here, ahead of the next job's loads, whose scoreboards they would otherwise share)
-    asm volatile("mov.b32 %0, %1;" : "=r"(rec.x) : "r"(recNext.x));
-    asm volatile("mov.b32 %0, %1;" : "=r"(rec.y) : "r"(recNext.y));
-    asm volatile("mov.b32 %0, %1;" : "=r"(rec.z) : "r"(recNext.z));
-    asm volatile("mov.b32 %0, %1;" : "=r"(rec.w) : "r"(recNext.w));
-    asm volatile("mov.b32 %0, %1;" : "=r"(header) : "r"(headerNext));
-  }
-#undef T360_PICK
-  // the group that finishes last re-arms the scheduler for the next launch (claimCounter[0] = claims, [1] = finished groups)
-  if (t == 0 && atomicAdd(jobs.claimCounter + 1, 1) == numWorkers - 1) {
-    jobs.claimCounter[0] = 0;
-    jobs.claimCounter[1] = 0;
-    __threadfence();
+    __syncwarp();
+    if (lane == 0) mbarArrive(empty + st);  // this warp is done with the stage (its shared-memory reads are complete)
   }
 }
 
@@ -439,11 +489,11 @@ template <int K, int COPIES, int GROUPS>
 cudaError_t launchFrameK(const FrameGatherParams& p, const StagedParams& jobs, const FrameTensorMaps& maps, int numSMs,
                          cudaStream_t stream) {
   static DeviceLaunchCfg cfgs;
-  constexpr int threads = GROUPS * kGroupThreads, smemBytes = frameSmemBytes<K, COPIES, GROUPS>();
+  constexpr int threads = GROUPS * (kGroupWarps + 1) * 32, smemBytes = FrameLayout<K, COPIES, GROUPS>::kTotal;
   LaunchCfg cfg;
   cudaError_t err = prepare<gatherFrameKernel<K, COPIES, GROUPS>>(cfgs, threads, smemBytes, cfg);
   if (err != cudaSuccess) return err;
-  const int grid = std::min(numSMs * cfg.perSM, (jobs.numTiles + GROUPS - 1) / GROUPS);  // persistent: one CTA per SM
+  const int grid = std::min(numSMs * cfg.perSM, (jobs.numTiles + GROUPS * kClaimBatch - 1) / (GROUPS * kClaimBatch));  // persistent: one CTA per SM
   cudaLaunchConfig_t lc{};
   lc.gridDim = dim3(grid);
   lc.blockDim = dim3(threads);
@@ -470,9 +520,9 @@ cudaError_t launchGatherFrame(const FrameGatherParams& p, const StagedParams& jo
   for (int i = p.numPlanes; i < kMaxFramePlanes; ++i)  // unused entries: valid descriptors that no job refers to
     for (int c = 0; c < kNumBoxClasses; ++c) maps.map[i][c] = maps.map[0][c];
   switch (p.kernelSize) {
-    case 2: return launchFrameK<2, weightCopies(2), kGatherGroups>(p, jobs, maps, numSMs, stream);
-    case 4: return launchFrameK<4, weightCopies(4), kGatherGroups>(p, jobs, maps, numSMs, stream);
-    case 8: return launchFrameK<8, weightCopies(8), kGatherGroups>(p, jobs, maps, numSMs, stream);
+    case 2: return launchFrameK<2, weightCopies(2), gatherGroups(2)>(p, jobs, maps, numSMs, stream);
+    case 4: return launchFrameK<4, weightCopies(4), gatherGroups(4)>(p, jobs, maps, numSMs, stream);
+    case 8: return launchFrameK<8, weightCopies(8), gatherGroups(8)>(p, jobs, maps, numSMs, stream);
     default: return cudaErrorInvalidValue;
   }
 }

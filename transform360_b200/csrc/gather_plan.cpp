@@ -123,17 +123,17 @@ Extent extentOf(const HostPlan& h, int x0, int y0, int x1, int y1) {
   return e;
 }
 
-// A 64 x 32 block qualifies as a share job when every column keeps its first source column down the 32 rows, steps
-// 0-2 source rows per output row, and the windows of the whole block fit one 192-byte-wide box inside the plane.
+// A 64 x shareH block qualifies as a share job when every column keeps its first source column down the rows, steps
+// 1 or 2 source rows per output row, and the windows of the whole block fit one 192-byte-wide box inside the plane.
 bool shareBlock(const HostPlan& h, int x0, int y0, TileClass& out) {
-  const int k = h.kernelSize;
+  const int k = h.kernelSize, kShareH = shareH(k);
   if (k < 4 || x0 + kShareW > h.mapW || y0 + kShareH > h.mapH) return false;
   for (int y = y0 + 1; y < y0 + kShareH; ++y) {
     const SamplePoint* a = &h.samples[static_cast<size_t>(y - 1) * h.mapW + x0];
     const SamplePoint* b = a + h.mapW;
     for (int x = 0; x < kShareW; ++x) {
       const int d = (b[x].rowPhase >> 10) - (a[x].rowPhase >> 10);
-      if (b[x].col0 != a[x].col0 || d < 0 || d > 2) return false;
+      if (b[x].col0 != a[x].col0 || d < 1 || d > 2) return false;
     }
   }
   const Extent e = extentOf(h, x0, y0, x0 + kShareW, y0 + kShareH);
@@ -147,7 +147,7 @@ bool shareBlock(const HostPlan& h, int x0, int y0, TileClass& out) {
   return true;
 }
 
-void classifyTile(const HostPlan& h, int x0, int y0, bool seamPossible, TileClass& out) {
+void classifyTile(const HostPlan& h, int x0, int y0, TileClass& out) {
   const int k = h.kernelSize;
   const int x1 = std::min(h.mapW, x0 + kGatherTileW), y1 = std::min(h.mapH, y0 + kFrameTileH);
   const Extent e = extentOf(h, x0, y0, x1, y1);
@@ -162,26 +162,6 @@ void classifyTile(const HostPlan& h, int x0, int y0, bool seamPossible, TileClas
         return;
       }
   }
-  // windows that cross the left/right border only (BORDER_WRAP): do they fit a class-0 box that wraps around it?
-  if (seamPossible && e.minR >= 0 && e.maxR + k <= h.inH && e.maxR + k - e.minR <= stageBoxH(k, 0)) {
-    const int W = h.inW, half = W / 2;  // columns rotated by half a plane: the border is in the middle of the range
-    int lo = INT32_MAX, hi = INT32_MIN;
-    for (int y = y0; y < y1; ++y)
-      for (int x = x0; x < x1; ++x) {
-        int cw = h.samples[static_cast<size_t>(y) * h.mapW + x].col0 % W;
-        if (cw < 0) cw += W;
-        const int rot = cw + half >= W ? cw + half - W : cw + half;
-        lo = std::min(lo, rot); hi = std::max(hi, rot);
-      }
-    const int first = lo - half < 0 ? lo - half + W : lo - half;  // leftmost first column, in plane coordinates
-    const int bx = first & ~15;
-    if (hi - lo + (first - bx) + k <= stageBoxW(k, 0) && bx + stageBoxW(k, 0) > W) {
-      out.kind = kJobSeam;
-      out.boxX = bx;
-      out.boxY = e.minR;
-      return;
-    }
-  }
   out.kind = kJobGeneral;
   out.boxX = out.boxY = 0;
 }
@@ -190,20 +170,20 @@ inline uint32_t slotField(int k, int phase, int copy) { return static_cast<uint3
 
 // compact records of a share job (kernels.cuh)
 void writeShareRecords(const HostPlan& h, const GatherJob& job, uint32_t* out) {
-  const int k = h.kernelSize, copies = weightCopies(k);
+  const int k = h.kernelSize, copies = weightCopies(k), kShareRows = shareRows(k), kShareH = shareH(k);
   const int x0 = job.outX, y0 = job.outY & kJobRowMask, boxX = job.boxXY & 0xffff, boxY = job.boxXY >> 16;
   const int pitch = stageBoxW(k, 2);
   for (int wx = 0; wx < kShareW / 32; ++wx) {
-    // the bank group of a pixel's weights depends on fracX only, which a column keeps (up to rounding jitter of the
-    // map): one lane order and one copy choice per column, found on the block's first row
-    int slot[32], laneOf[32], copyOf[32];
-    const SamplePoint* first = &h.samples[static_cast<size_t>(y0) * h.mapW + x0 + wx * 32];
-    for (int i = 0; i < 32; ++i) slot[i] = weightSlotOf(k, first[i].rowPhase & 1023);
-    dealLanes(k, copies, 32, slot, laneOf, copyOf);
     for (int wy = 0; wy < kShareH / kShareRows; ++wy) {
+      // the bank group of a pixel's weights depends on fracX only, which a column keeps (up to rounding jitter of the
+      // map): one lane order and one copy choice per column and warp, found on the warp's first row
+      int slot[32], laneOf[32], copyOf[32];
+      const SamplePoint* first = &h.samples[static_cast<size_t>(y0 + wy * kShareRows) * h.mapW + x0 + wx * 32];
+      for (int i = 0; i < 32; ++i) slot[i] = weightSlotOf(k, first[i].rowPhase & 1023);
+      dealLanes(k, copies, 32, slot, laneOf, copyOf);
       const int w = wy * (kShareW / 32) + wx;
-      uint32_t* words = out + static_cast<size_t>(w) * (kShareJobRecordBytes / kGroupWarps / 4);
-      uint32_t* headers = words + 32 * 4;
+      uint32_t* words = out + static_cast<size_t>(w) * (shareWarpRecordBytes(k) / 4);
+      uint32_t* headers = words + kShareRows / 8 * 32 * 4;
       for (int c = 0; c < 32; ++c) {
         const int lane = laneOf[c], x = x0 + wx * 32 + c, ya = y0 + wy * kShareRows;
         const SamplePoint* col = &h.samples[static_cast<size_t>(ya) * h.mapW + x];
@@ -211,9 +191,9 @@ void writeShareRecords(const HostPlan& h, const GatherJob& job, uint32_t* out) {
         headers[lane] = static_cast<uint32_t>(off) | (static_cast<uint32_t>(c) << kRecordColumnShift);
         for (int j = 0; j < kShareRows; ++j) {
           const SamplePoint& sp = col[static_cast<size_t>(j) * h.mapW];
-          const int d = j == 0 ? 0 : (sp.rowPhase >> 10) - (col[static_cast<size_t>(j - 1) * h.mapW].rowPhase >> 10);
-          const uint32_t rec = slotField(k, sp.rowPhase & 1023, copyOf[c]) | static_cast<uint32_t>(d);
-          uint32_t& word = words[lane * 4 + (j >> 1)];
+          const int d = j == 0 ? 1 : (sp.rowPhase >> 10) - (col[static_cast<size_t>(j - 1) * h.mapW].rowPhase >> 10);
+          const uint32_t rec = slotField(k, sp.rowPhase & 1023, copyOf[c]) | static_cast<uint32_t>(d - 1);  // bit 0: a second row
+          uint32_t& word = words[(j >> 3) * 32 * 4 + lane * 4 + ((j >> 1) & 3)];
           word = (j & 1) ? (word | (rec << 16)) : rec;
         }
       }
@@ -241,12 +221,7 @@ void writeTileRecords(const HostPlan& h, const GatherJob& job, uint32_t* out) {
     dealLanes(k, copies, n, slot, laneOf, copyOf);
     for (int c = n; c < 32; ++c) words[c * 4 + j] = static_cast<uint32_t>(c) << 16;  // right of the plane: skipped (x >= dstW)
     for (int c = 0; c < n; ++c) {
-      int col0 = row[c].col0;
-      if (kind == kJobSeam) {  // first column relative to the unwrapped box (boxX <= col0 < boxX + box width)
-        int cw = col0 % h.inW;
-        if (cw < 0) cw += h.inW;
-        col0 = boxX + (cw - boxX + h.inW) % h.inW;
-      }
+      const int col0 = row[c].col0;
       const int off = ((row[c].rowPhase >> 10) - boxY) * pitch + (col0 - boxX);
       words[laneOf[c] * 4 + j] = static_cast<uint32_t>(off) | (static_cast<uint32_t>(c) << 16) |
                                  (slotField(k, row[c].rowPhase & 1023, copyOf[c]) << 17);
@@ -316,6 +291,22 @@ int dealLanes(int k, int copies, int n, const int* slot, int* laneOf, int* copyO
   return wavefronts;
 }
 
+void spreadGeneralJobs(std::vector<GatherJob>& jobs) {
+  std::vector<GatherJob> general, staged;
+  for (const GatherJob& j : jobs)
+    (((j.outY >> kJobKindShift) & kJobKindMask) == kJobGeneral ? general : staged).push_back(j);
+  if (general.empty() || staged.empty()) return;
+  const size_t span = staged.size() * 3 / 4 + 1;  // the tail of the launch stays fine-grained staged work
+  jobs.clear();
+  size_t g = 0;
+  for (size_t i = 0; i < staged.size(); ++i) {
+    // general job number g goes in front of staged job number g * span / general.size()
+    while (g < general.size() && g * span / general.size() <= i) jobs.push_back(general[g++]);
+    jobs.push_back(staged[i]);
+  }
+  while (g < general.size()) jobs.push_back(general[g++]);
+}
+
 std::vector<uint8_t> buildWeightImage(int k, const int16_t* table) {
   const int copies = weightCopies(k), vs = weightVectorStride(k, copies);
   std::vector<uint8_t> img(static_cast<size_t>(weightImageBytes(k, copies)), 0);
@@ -347,22 +338,22 @@ void buildGatherPlan(const HostPlan& h, bool stageTiles, GatherPlan& g) {
 
   // ---- cut the plane into jobs: 64 x 32 share blocks where the geometry allows, 32 x 32 tiles elsewhere
   const int tilesX = g.tilesPerRow, tilesY = (h.mapH + kFrameTileH - 1) / kFrameTileH;
-  // seam tiles need whole 16-byte columns on both sides of the border and a plane much wider than the box
-  const bool seamPossible = h.inW % 16 == 0 && h.inW >= 4 * stageBoxW(k, 0);
   std::vector<TileClass> cls(static_cast<size_t>(tilesX) * tilesY);
-  parallelRanges(tilesY, static_cast<size_t>(h.mapW) * kFrameTileH, [&](int tyBegin, int tyEnd) {
-    for (int ty = tyBegin; ty < tyEnd; ++ty)
+  const int blockRows = shareH(k) / kFrameTileH;  // tile rows a share block spans
+  parallelRanges((tilesY + blockRows - 1) / blockRows, static_cast<size_t>(h.mapW) * shareH(k), [&](int byBegin, int byEnd) {
+    for (int by = byBegin; by < byEnd; ++by)
       for (int tx = 0; tx < tilesX; tx += 2) {
-        TileClass* c = &cls[static_cast<size_t>(ty) * tilesX + tx];
-        if (shareBlock(h, tx * 32, ty * kFrameTileH, c[0])) continue;  // c[1] stays -1: covered
-        classifyTile(h, tx * 32, ty * kFrameTileH, seamPossible, c[0]);
-        if (tx + 1 < tilesX) classifyTile(h, (tx + 1) * 32, ty * kFrameTileH, seamPossible, c[1]);
+        TileClass* c = &cls[static_cast<size_t>(by) * blockRows * tilesX + tx];
+        if (shareBlock(h, tx * 32, by * shareH(k), c[0])) continue;  // the other tiles of the block stay -1: covered
+        for (int ty = by * blockRows; ty < std::min(tilesY, (by + 1) * blockRows); ++ty)
+          for (int t = tx; t < std::min(tilesX, tx + 2); ++t)
+            classifyTile(h, t * 32, ty * kFrameTileH, cls[static_cast<size_t>(ty) * tilesX + t]);
       }
   });
   // launch order: general tiles (latency-bound: they run while every group of the SM is busy), seam, class 1 (both
   // need the two stage buffers), then the share jobs and finally the small class-0 tiles through the double-buffered
   // TMA pipeline, which leaves a short, fine-grained tail
-  const int order[5] = {kJobGeneral, kJobSeam, kJobClass1, kJobShare, kJobClass0};
+  const int order[4] = {kJobGeneral, kJobClass1, kJobShare, kJobClass0};
   size_t offset = 0;  // bytes
   for (int kind : order)
     for (int ty = 0; ty < tilesY; ++ty)
@@ -372,12 +363,11 @@ void buildGatherPlan(const HostPlan& h, bool stageTiles, GatherPlan& g) {
         GatherJob job{tx * 32, ty * kFrameTileH | (kind << kJobKindShift), c.boxX | (c.boxY << 16), 0};
         if (kind != kJobGeneral) {
           job.recordOffset = static_cast<int>(offset / 16);
-          offset += kind == kJobShare ? kShareJobRecordBytes : kTileJobRecordBytes;
+          offset += kind == kJobShare ? shareJobRecordBytes(k) : kTileJobRecordBytes;
         }
         g.jobs.push_back(job);
         switch (kind) {
           case kJobGeneral: ++g.numGeneral; break;
-          case kJobSeam: ++g.numSeam; break;
           case kJobShare: ++g.numShare; break;
           default: ++g.numStaged[kind]; break;
         }

@@ -21,34 +21,32 @@ struct GatherParams {
 };
 
 // ---- the persistent frame gather (gatherFrameKernel) -------------------------------------------------------------
-// A CTA holds kGatherGroups independent GROUPS of 256 threads (8 warps); every group runs its own job pipeline
-// (claim -> header -> records -> TMA box -> compute) on its own pair of stage buffers, synchronised with a named
-// barrier, while all groups share ONE copy of the weight tables in shared memory.  One CTA per SM.
+// One CTA per SM: gatherGroups(k) GROUPS of 8 consumer warps + 1 producer warp each, all sharing one copy of the weight
+// tables in shared memory.  A producer claims jobs from the frame's job list (an atomic counter, four jobs at a time),
+// and for every job fills one stage of its group's two-stage ring: the job header (st.shared), the job's
+// compact sampling records (cp.async.bulk) and its source window (ONE cp.async.bulk.tensor.2d box from the
+// pitch-linear plane), all signalled through the stage's "full" mbarrier.  The consumer warps wait for "full", compute,
+// and each arrives on the stage's "empty" mbarrier: no global load, no claim, no CTA-wide barrier on the consumer side.
 //
 // A JOB is a block of output pixels of one image plane:
-//   kJobShare    64 x 32 pixels on which every output column keeps its source column down the rows and consecutive
-//                rows start 0, 1 or 2 source rows apart (the four equatorial cube faces, equirect -> equirect ...).
-//                A warp owns 32 columns x 8 rows, a thread one column: it slides ONE K-row register window down its
-//                column, fetching only the 0-2 new rows per pixel.  Source window: one 192 x boxH TMA box.
-//   kJobClass0   32 x 32 pixels, any geometry whose windows fit a 208 x boxH box: a thread computes 4 pixels, each
-//   kJobClass1   from its own window.  Class 1: a 240 x boxH1 box that takes both stage buffers.
-//   kJobSeam     like class 0, but the windows cross the left/right plane border (BORDER_WRAP at the +-180 degree
-//                meridian): two class-0 boxes, at boxX and boxX - srcW, zero-filled outside the plane, OR-ed together.
-//   kJobGeneral  32 x 32 pixels read through L1 with full border handling (pole caps, anything that fits no box).
 struct GatherJob {
   int outX, outY;    // outY carries the job kind (kJobKindShift) and the image plane (kJobPlaneShift)
   int boxXY;         // boxX | boxY << 16 (boxX % 16 == 0)
   int recordOffset;  // of the job's compact records, in 16-byte units from the plane's record buffer
 };
 using StagedTile = GatherJob;
-constexpr int kJobClass0 = 0, kJobClass1 = 1, kJobGeneral = 2, kJobSeam = 3, kJobShare = 4;
+constexpr int kJobClass0 = 0, kJobClass1 = 1, kJobGeneral = 2, kJobShare = 4, kJobNop = 5, kJobExit = 6;
 constexpr int kJobKindShift = 24, kJobRowMask = (1 << kJobKindShift) - 1;
 constexpr int kJobPlaneShift = 28, kJobKindMask = (1 << (kJobPlaneShift - kJobKindShift)) - 1;
 
 constexpr int kGroupThreads = 256, kGroupWarps = kGroupThreads / 32;
-constexpr int kGatherGroups = 3;  // job pipelines per CTA (768 threads, one CTA per SM)
+// consumer groups per CTA (+ one producer warp): as many as the rings fit beside the weight tables in 227 KB
+__host__ __device__ constexpr int gatherGroups(int k) { return k == 8 ? 2 : 3; }
+constexpr int kClaimBatch = 4;  // jobs a producer warp claims with one atomic
 constexpr int kGatherTileW = 32, kFrameTileH = 32;  // generic jobs: 32 x 32, four rows per thread
-constexpr int kShareW = 64, kShareH = 32, kShareRows = 8;  // share jobs: 2 x 4 warps of 32 columns x 8 rows
+constexpr int kShareW = 64;  // share jobs: 2 x 4 warps of 32 columns x shareRows(k) rows
+__host__ __device__ constexpr int shareRows(int /*k*/) { return 8; }
+__host__ __device__ constexpr int shareH(int k) { return 4 * shareRows(k); }
 // Staging boxes (bytes x rows).  The shared-memory row pitch is the box width (TMA writes dense rows).  192 B = 48 words
 // puts consecutive rows 16 banks apart: the 32 adjacent pixels of a share-job warp span <= 13 words of 1-2 source rows,
 // so their window loads are conflict-free (1.10 wavefronts per load in the bank model, 1.57 at 96 B).  Polar tiles
@@ -88,17 +86,24 @@ __host__ __device__ constexpr int weightBankGroups(int k) { return k == 2 ? 16 :
 __host__ __device__ constexpr int weightLanesPerPass(int k) { return k == 2 ? 16 : 8; }
 
 // Compact sampling records of the staged jobs (32-bit words, one buffer per plan, GatherJob::recordOffset):
-//   share job    per warp w (columns 32 * (w & 1) .., rows 8 * (w >> 1) ..): 32 x uint4, then 32 x uint32, by lane.
-//                uint32 = header of the lane's column: off | column << 27, off = (row0 - boxY) * 192 + (col0 - boxX) of
-//                the column's first pixel; uint4 = 8 x 16-bit pixel records, row j in half j & 1 of word j >> 1:
-//                slotField | d, d = source rows between this pixel's window and the previous one's (0 for the first).
-//                2.5 bytes per pixel.
+//   share job    per warp w (columns 32 * (w & 1) .., rows R * (w >> 1) .., R = shareRows(k)): R / 8 blocks of 32 x uint4,
+//                then 32 x uint32, by lane.  uint32 = header of the lane's column: off | column << 27,
+//                off = (row0 - boxY) * 192 + (col0 - boxX) of the column's first pixel; uint4 number b = 8 x 16-bit pixel
+//                records of rows 8b .., row j in half j & 1 of word (j >> 1) & 3: slotField | (d - 1), d = 1 or 2 source
+//                rows between this pixel's window and the previous one's (bit 0 is clear in a column's first record).
+//                2.25 (R = 16) or 2.5 bytes per pixel.
 //   other jobs   per warp w (rows 4 * w ..): 32 x uint4 by lane, word j = pixel of row 4 * w + j:
 //                off (15 bits) | column << 16 (5 bits) | slotField << 17.  4 bytes per pixel.  Inside a 32-pixel row the
 //                pixels are dealt to lanes (and copies) per row; pixels outside the plane carry a column / row that
 //                fails the bounds check.
 // General jobs read the full records below.
-constexpr int kShareJobRecordBytes = kGroupWarps * (32 * 16 + 32 * 4), kTileJobRecordBytes = kGroupWarps * 32 * 16;
+__host__ __device__ constexpr int shareWarpRecordBytes(int k) { return shareRows(k) / 8 * 32 * 16 + 32 * 4; }
+__host__ __device__ constexpr int shareJobRecordBytes(int k) { return kGroupWarps * shareWarpRecordBytes(k); }
+constexpr int kTileJobRecordBytes = kGroupWarps * 32 * 16;
+// one stage of a ring: the header (padded to 128 bytes) and the records of a job
+__host__ __device__ constexpr int stageRecordBytes(int k) {
+  return 128 + (shareJobRecordBytes(k) > kTileJobRecordBytes ? shareJobRecordBytes(k) : kTileJobRecordBytes);
+}
 constexpr int kRecordColumnShift = 27;
 
 // The persistent gather kernel takes the jobs of up to three image planes (Y, U, V of one frame) in ONE launch:

@@ -497,8 +497,10 @@ class VideoFrameTransform {
       for (int c = 0; c < 2; ++c) d.numStaged[c] = g.numStaged[c];
       d.numJobs = static_cast<int>(g.jobs.size());
       if (!g.jobs.empty()) {
-        d.gatherJobs.reserve(g.jobs.size());
-        CU(cudaMemcpy(d.gatherJobs.ptr, g.jobs.data(), g.jobs.size() * sizeof(GatherJob), cudaMemcpyHostToDevice));
+        std::vector<GatherJob> launchOrder = g.jobs;  // (hostJobs stay sorted by kind: gatherFrame() merges the planes)
+        t360::spreadGeneralJobs(launchOrder);
+        d.gatherJobs.reserve(launchOrder.size());
+        CU(cudaMemcpy(d.gatherJobs.ptr, launchOrder.data(), launchOrder.size() * sizeof(GatherJob), cudaMemcpyHostToDevice));
       }
       if (!g.compact.empty()) {
         d.records.reserve(g.compact.size());
@@ -763,13 +765,14 @@ class VideoFrameTransform {
     FrameJobList& f = frameJobs_;
     if (f.generation != planGeneration_ || f.numPlanes != numPlanes) {
       std::vector<GatherJob> merged;
-      for (int kind : {t360::kJobGeneral, t360::kJobSeam, t360::kJobClass1, t360::kJobShare, t360::kJobClass0})
+      for (int kind : {t360::kJobGeneral, t360::kJobClass1, t360::kJobShare, t360::kJobClass0})
         for (int p = 0; p < numPlanes; ++p)
           for (GatherJob t : work[p].plan->hostJobs) {
             if (((t.outY >> t360::kJobKindShift) & t360::kJobKindMask) != kind) continue;
             t.outY |= p << t360::kJobPlaneShift;
             merged.push_back(t);
           }
+      t360::spreadGeneralJobs(merged);
       CU(cudaStreamSynchronize(s));  // a previous frame may still be reading the old list
       f.tiles.reserve(merged.size());
       CU(cudaMemcpy(f.tiles.ptr, merged.data(), merged.size() * sizeof(GatherJob), cudaMemcpyHostToDevice));
