@@ -15,20 +15,21 @@ import transform360_b200 as t360
 from tests.golden.cases import FULL, SMALL, plane_dims
 
 KIND_SHIFT, PLANE_SHIFT, ROW_MASK = 24, 28, (1 << 24) - 1
-CLASS0, CLASS1, GENERAL, SEAM, SHARE = 0, 1, 2, 3, 4
-ORDER = {GENERAL: 0, CLASS1: 2, SHARE: 3, CLASS0: 4}
+CLASS0, CLASS1, GENERAL, SHARE_STAY, SHARE, SEAM = 0, 1, 2, 3, 4, 7
+SKIP = 0x8000
+ORDER = {GENERAL: 0, SEAM: 1, CLASS1: 2, SHARE_STAY: 3, SHARE: 4, CLASS0: 5}
 SLOT_MASK = 0x7FF0
 INTERP = {2: t360.LINEAR, 4: t360.CUBIC, 8: t360.LANCZOS4}
 
 
 def box_w(kind):
-    return 192 if kind == SHARE else (240 if kind == CLASS1 else 208)
+    return 192 if kind in (SHARE, SHARE_STAY) else (240 if kind == CLASS1 else 208)
 
 
 def box_h(k, kind):
     if k == 8:
-        return 80 if kind == SHARE else (128 if kind == CLASS1 else 72)
-    return 72 if kind == SHARE else (96 if kind == CLASS1 else 64)
+        return 80 if kind in (SHARE, SHARE_STAY) else (128 if kind == CLASS1 else 72)
+    return 72 if kind in (SHARE, SHARE_STAY) else (96 if kind == CLASS1 else 64)
 
 
 def share_rows(k):
@@ -123,8 +124,9 @@ def test_gather_plan_invariants(group, name, plane):
         return
     cnt = g["counts"]
     kinds = (jobs[:, 1] >> KIND_SHIFT) & 15
-    assert list(kinds) == sorted(kinds, key=lambda v: ORDER[int(v)]), "launch order: general, class 1, share, class 0"
-    assert (np.bincount(kinds, minlength=5) == [cnt["class0"], cnt["class1"], cnt["general"], 0, cnt["share"]]).all() and cnt["seam"] == 0
+    assert list(kinds) == sorted(kinds, key=lambda v: ORDER[int(v)]), "launch order: general, seam, class 1, share (with stays), share, class 0"
+    by_kind = np.bincount(kinds, minlength=8)
+    assert (by_kind[:3] == [cnt["class0"], cnt["class1"], cnt["general"]]).all() and by_kind[3] + by_kind[4] == cnt["share"] and by_kind[7] == cnt["seam"]
     assert ((jobs[:, 1] >> PLANE_SHIFT) == 0).all()
     if k < 4:
         assert cnt["share"] == 0
@@ -135,14 +137,15 @@ def test_gather_plan_invariants(group, name, plane):
     for ox, oy, boxxy, rec_off in jobs:
         kind, y0 = (oy >> KIND_SHIFT) & 15, oy & ROW_MASK
         bx, by = boxxy & 0xFFFF, boxxy >> 16
-        assert ox % 32 == 0 and y0 % 32 == 0
+        quad, ox = (ox & 7) - 1, ox & ~7  # 16 x 16 quadrant of the tile this job covers (-1: all of it)
+        assert ox % 32 == 0 and y0 % 32 == 0 and quad < 4 and (quad < 0 or kind == CLASS0)
         if kind == GENERAL:
             assert boxxy == 0 and rec_off == 0  # taps through L1 from the full records: nothing for the host to promise
             produced[y0:y0 + 32, ox:ox + 32] += 1
             continue
         pitch, bh = box_w(kind), box_h(k, kind)
         assert bx % 16 == 0 and rec_off == next_offset, "records are laid out in launch order, 16-byte units"
-        if kind == SHARE:
+        if kind in (SHARE, SHARE_STAY):
             R = share_rows(k)
             sh, nwords = 4 * R, R // 8 * 128 + 32  # job height; 32-bit words per warp
             assert ox % 64 == 0 and y0 % sh == 0 and ox + 64 <= mw and y0 + sh <= mh
@@ -155,9 +158,15 @@ def test_gather_plan_invariants(group, name, plane):
                 col, off = hdr >> 27, hdr & 0x7FFF
                 assert ((hdr & ((1 << 27) - 1)) == off).all() and (np.sort(col) == np.arange(32)).all()
                 rec = np.stack([px[j >> 3, :, (j >> 1) & 3] >> (16 * (j & 1)) & 0xFFFF for j in range(R)], axis=1)  # [lane][row]
-                d, field = (rec & 1) + 1, rec & SLOT_MASK  # bit 0: the window moves two source rows instead of one
-                d[:, 0] -= 1
-                assert ((rec & ~(SLOT_MASK | 1)) == 0).all() and (d[:, 0] == 0).all(), "the first record of a column carries no step"
+                field = rec & SLOT_MASK
+                if kind == SHARE:  # bit 0: the window moves two source rows instead of one
+                    d = (rec & 1) + 1
+                    d[:, 0] -= 1
+                    assert ((rec & ~(SLOT_MASK | 1)) == 0).all()
+                else:              # bits 0-1: it moves 0, 1 or 2 rows
+                    d = rec & 3
+                    assert ((rec & ~(SLOT_MASK | 3)) == 0).all() and (d <= 2).all() and (d == 0).any()
+                assert (d[:, 0] == 0).all(), "the first record of a column carries no step"
                 row0 = by + off[:, None] // pitch + np.cumsum(d, axis=1)
                 col0 = bx + off % pitch
                 want = s[y0 + wy * R:y0 + wy * R + R, ox + wx * 32:ox + wx * 32 + 32]  # [row][column]
@@ -171,31 +180,38 @@ def test_gather_plan_invariants(group, name, plane):
                 assert (col0 >= 0).all() and (col0 + k <= iw).all() and (row0 >= 0).all() and (row0 + k <= ih).all()
             produced[y0:y0 + sh, ox:ox + 64] += 1
             continue
-        # 32 x 32 jobs: class 0, class 1
-        words = compact[rec_off * 4:rec_off * 4 + 8 * 128].reshape(8, 32, 4).astype(np.int64)  # [warp][lane][row in warp]
+        # 32 x 32 jobs: class 0 (also one quadrant of a tile), class 1, seam.  Warp w, word j = one pixel of the 8 x 4
+        # patch at rows 4w .., columns 8j ..
+        words = compact[rec_off * 4:rec_off * 4 + 8 * 128].reshape(8, 32, 4).astype(np.int64)  # [warp][lane][step]
         next_offset += 8 * 128 // 4
-        w = words.transpose(0, 2, 1).reshape(32, 32)  # [row in tile][lane]
-        off, col, field = w & 0x7FFF, (w >> 16) & 31, (w >> 17) & SLOT_MASK
-        assert ((w >> 15) & 1 == 0).all()
-        hh, ww = min(32, mh - y0), min(32, mw - ox)
-        assert (np.sort(col, axis=1) == np.arange(32)).all(), "a row holds every column once (also the skipped ones)"
-        order = np.argsort(col, axis=1)
-        off, field = np.take_along_axis(off, order, axis=1)[:hh, :ww], np.take_along_axis(field, order, axis=1)[:hh, :ww]
-        want = s[y0:y0 + hh, ox:ox + ww]
-        row0, col0 = by + off // pitch, bx + off % pitch
+        off, pos, field, skip = words & 0x7FFF, (words >> 16) & 31, (words >> 17) & SLOT_MASK, (words & SKIP) != 0
+        assert (np.sort(pos, axis=1) == np.arange(32)[None, :, None]).all(), "a patch holds every position once (also the skipped ones)"
+        x = ox + 8 * np.arange(4)[None, None, :] + (pos & 7)
+        y = y0 + 4 * np.arange(8)[:, None, None] + (pos >> 3)
+        live = (x < mw) & (y < mh)
+        if quad >= 0:
+            live &= (x >= ox + 16 * (quad & 1)) & (x < ox + 16 * (quad & 1) + 16) & (y >= y0 + 16 * (quad >> 1)) & (y < y0 + 16 * (quad >> 1) + 16)
+        assert (skip == ~live).all(), "exactly the pixels outside the plane / the quadrant are skipped"
+        xs, ys, offs, fields = x[live], y[live], off[live], field[live]
+        want = s[ys, xs]
+        row0, col0 = by + offs // pitch, bx + offs % pitch
         assert (row0 == want[..., 1] >> 10).all()
-        wimg.check(field.ravel(), (want[..., 1] & 1023).ravel())
-        assert (off % pitch + k <= pitch).all() and (off // pitch + k <= bh).all() and (row0 >= 0).all() and (row0 + k <= ih).all()
-        assert (col0 == want[..., 0]).all() and (col0 >= 0).all() and (col0 + k <= iw).all(), "a staged tile never needs BORDER_WRAP"
-        produced[y0:y0 + hh, ox:ox + ww] += 1
+        wimg.check(fields, want[..., 1] & 1023)
+        assert (offs % pitch + k <= pitch).all() and (offs // pitch + k <= bh).all() and (row0 >= 0).all() and (row0 + k <= ih).all()
+        if kind == SEAM:
+            assert iw % 16 == 0 and bx < iw < bx + pitch, "the box of a seam tile wraps around the border"
+            assert (col0 % iw == want[..., 0] % iw).all()
+        else:
+            assert (col0 == want[..., 0]).all() and (col0 >= 0).all() and (col0 + k <= iw).all(), "a staged tile never needs BORDER_WRAP"
+        np.add.at(produced, (ys, xs), 1)
     assert (produced == 1).all(), "every output pixel belongs to exactly one job"
     assert compact is None or next_offset * 4 == compact.size
 
 
 def test_job_counts_of_the_headline_plan():
     """cfg2 (8K equirect -> 3840x2560 cubemap, bicubic): the numbers DESIGN.md quotes."""
-    for plane, want in ((0, dict(class0=3120, class1=416, seam=0, general=360, share=2852)),
-                        (1, dict(class0=848, class1=88, seam=0, general=128, share=668))):
+    for plane, want in ((0, dict(class0=4760, class1=0, seam=112, general=120, share=3120)),
+                        (1, dict(class0=1176, class1=0, seam=56, general=32, share=760))):
         _, hp, _, _ = _plan(FULL["cfg2"], plane)
         assert hp.gather_plan()["counts"] == want
 
@@ -206,7 +222,7 @@ def test_weight_bank_balance_of_the_headline_plan():
     _, hp, _, _ = _plan(FULL["cfg2"], 0)
     g = hp.gather_plan()
     jobs, compact = g["jobs"], g["compact"]
-    share = jobs[((jobs[:, 1] >> KIND_SHIFT) & 15) == SHARE][::16]
+    share = jobs[np.isin((jobs[:, 1] >> KIND_SHIFT) & 15, (SHARE, SHARE_STAY))][::16]
     R = share_rows(4)
     nwords = R // 8 * 128 + 32
     total = n = 0

@@ -37,24 +37,29 @@ def needs_build() -> bool:
     return any(d.stat().st_mtime > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> Path:
-    if not force and not needs_build():
+def build(force: bool = False, verbose: bool = False, defines: tuple = (), out: Path | None = None) -> Path:
+    """defines / out: experiment variants (e.g. defines=("T360_STAGES=3",), out=lib/libTransform360_s3.so), loaded
+    with T360B200_LIB=<path>."""
+    out = out or LIB
+    if not force and not defines and not needs_build():
         return LIB
     LIB_DIR.mkdir(exist_ok=True)
     # host code: -ffp-contract=off keeps the planner's float sequence identical to the reference's build
     host_flags = "-fPIC,-fvisibility=hidden,-ffp-contract=off,-fno-fast-math,-Wall"
     cmd = [nvcc_path(), *ARCH, "-O3", "-lineinfo", "-std=c++17", "--shared", "-Xcompiler", host_flags,
            "-Xptxas", "-v" if verbose else "-warn-spills", "-I", str(ROOT / "include"), "-I", str(CSRC),
-           "-o", str(LIB)] + [str(CSRC / s) for s in SOURCES]
+           *[f"-D{d}" for d in defines], "-o", str(out)] + [str(CSRC / s) for s in SOURCES]
     env = dict(os.environ)
     r = subprocess.run(cmd, capture_output=True, text=True, env=env)
     if verbose or r.returncode != 0:
         sys.stderr.write(" ".join(cmd) + "\n" + r.stdout + r.stderr)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed building libTransform360.so")
-    return LIB
+    return out
 
 
 if __name__ == "__main__":
-    p = build(force="--force" in sys.argv, verbose="--verbose" in sys.argv)
+    defs = tuple(a[2:] for a in sys.argv[1:] if a.startswith("-D"))
+    outs = [a.split("=", 1)[1] for a in sys.argv[1:] if a.startswith("--out=")]
+    p = build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, defines=defs, out=Path(outs[0]) if outs else None)
     print(p)

@@ -158,7 +158,7 @@ __device__ __forceinline__ uint32_t packBytes(int hi, int lo) {  // sat_u8(hi) <
   return r;
 }
 
-template <int K, int PITCH, int VS, int ROWS>
+template <int K, int PITCH, int VS, int ROWS, bool ZERO>
 __device__ __forceinline__ void computeShareJob(uint8_t* dst, int dstPitch, uint32_t stageAddr, const uint4 (&rec)[ROWS / 8],
                                                 uint32_t header, uint32_t wAddr) {
   static_assert(PITCH % 4 == 0 && (K == 4 || K == 8) && ROWS % 8 == 0, "");
@@ -172,7 +172,7 @@ __device__ __forceinline__ void computeShareJob(uint8_t* dst, int dstPitch, uint
     const uint4& block = rec[j >> 3];
     const uint32_t word = ((j >> 1) & 3) == 0 ? block.x : (((j >> 1) & 3) == 1 ? block.y : (((j >> 1) & 3) == 2 ? block.z : block.w));
     const uint32_t r = (j & 1) ? word >> 16 : word;
-    if constexpr (j > 0) {
+    if constexpr (j > 0 && !ZERO) {
       const bool two = (r & 1u) != 0;
       // the previous window starts at base + (j - 1) * PITCH; this one 1 (+ 1) rows below
       const RowBytes<K> below = loadRow<K, (j - 1 + K) * PITCH>(base, sh);
@@ -187,6 +187,24 @@ __device__ __forceinline__ void computeShareJob(uint8_t* dst, int dstPitch, uint
       W[K - 1] = below2;
       if (two) base += PITCH;
     }
+    if constexpr (j > 0 && ZERO) {
+      // the variant for blocks in which a window may also stay where it is (d = 0, 1 or 2 in bits 0-1 of the record): no
+      // static part in the addresses, three-way selects
+      const uint32_t d = r & 3u;
+      RowBytes<K> below = W[K - 1], below2 = W[K - 1];
+      if (d != 0) below = loadRow<K, K * PITCH>(base, sh);
+      if (d == 2) below2 = loadRow<K, (K + 1) * PITCH>(base, sh);
+#pragma unroll
+      for (int q = 0; q + 2 < K; ++q)
+#pragma unroll
+        for (int i = 0; i < (K == 8 ? 2 : 1); ++i) W[q].b[i] = d == 0 ? W[q].b[i] : (d == 1 ? W[q + 1].b[i] : W[q + 2].b[i]);
+#pragma unroll
+      for (int i = 0; i < (K == 8 ? 2 : 1); ++i) {
+        W[K - 2].b[i] = d == 0 ? W[K - 2].b[i] : (d == 1 ? W[K - 1].b[i] : below.b[i]);
+        W[K - 1].b[i] = d == 0 ? W[K - 1].b[i] : (d == 1 ? below.b[i] : below2.b[i]);
+      }
+      base += d * PITCH;
+    }
     const int acc = foldRows<K, VS>(W, wAddr + (r & kSlotFieldMask)) >> 15;
     if constexpr (j & 1) {
       const uint32_t pair = packBytes(acc, accPrev);
@@ -198,26 +216,26 @@ __device__ __forceinline__ void computeShareJob(uint8_t* dst, int dstPitch, uint
   });
 }
 
-// ---- 32 x 32 staged job: a window per pixel, four pixels per thread ----------------------------------------------------
+// ---- 32 x 32 staged job: a window per pixel, four pixels per thread (one of each 8 x 4 patch of the warp's rows) --------
 template <int K, int PITCH, int VS>
 __device__ __forceinline__ void computeTileJob(const PlaneView& pv, uint32_t stageAddr, int outX, int outY, const uint4& rec,
                                                uint32_t wAddr, int warp) {
   static_assert(PITCH % 4 == 0, "");
-  const int y0 = outY + warp * kRowsPerThread;
+  const int y0 = outY + warp * kTilePatchH;
   const int dstPitch = pv.dstPitch, dstW = pv.dstW, dstH = pv.dstH;
   uint8_t* const dstRow = pv.dst + (size_t)y0 * dstPitch + outX;
   const uint32_t words[4] = {rec.x, rec.y, rec.z, rec.w};
-  staticFor<kRowsPerThread>([&](auto J) {
+  staticFor<kRowsPerPatchStep>([&](auto J) {
     constexpr int j = decltype(J)::value;
     const uint32_t w = words[j];
-    const int col = (int)(w >> 16) & 31;
-    if (outX + col < dstW && y0 + j < dstH) {
+    const int col = kTilePatchW * j + ((int)(w >> 16) & (kTilePatchW - 1)), row = (int)(w >> 19) & (kTilePatchH - 1);
+    if (!(w & kRecordSkip) && outX + col < dstW && y0 + row < dstH) {
       const uint32_t rowAddr = stageAddr + (w & 0x7ffcu);
       const int sh = (int)(w << 3);
       RowBytes<K> W[K];
       staticFor<K>([&](auto R) { W[decltype(R)::value] = loadRow<K, decltype(R)::value * PITCH>(rowAddr, sh); });
       const int acc = foldRows<K, VS>(W, wAddr + slotOffset<K>((w >> 17) & kSlotFieldMask));
-      dstRow[(size_t)j * dstPitch + col] = (uint8_t)biasedToByte(acc);
+      dstRow[(size_t)row * dstPitch + col] = (uint8_t)biasedToByte(acc);
     }
   });
 }
@@ -305,15 +323,17 @@ __device__ __forceinline__ uint32_t ldsWord(uint32_t addr) {
   return v;
 }
 
-// shared-memory layout: weights | per group {box 0, box 1, records 0, records 1} | planes | barriers
+// shared-memory layout: weights | per group {boxes of all stages, records of all stages} | planes | barriers
 template <int K, int COPIES, int GROUPS>
 struct FrameLayout {
+  static constexpr int kStages = gatherStages(K);
   static constexpr int kWeights = weightImageBytes(K, COPIES);
   static constexpr int kStage = stageBytesOf(K), kRec = stageRecordBytes(K);
-  static constexpr int kGroupBytes = 2 * kStage + 2 * kRec;
+  static constexpr int kGroupBytes = kStages * (kStage + kRec);
   static constexpr int kPlanes = kWeights + GROUPS * kGroupBytes;
-  static constexpr int kBars = kPlanes + 256;  // per group: full[2], empty[2]; then the weight barrier
-  static constexpr int kTotal = kBars + GROUPS * 32 + 16;
+  static constexpr int kBars = kPlanes + 256;  // per group: full[kStages], empty[kStages]; then the weight barrier
+  static constexpr int kTotal = kBars + GROUPS * kStages * 16 + 16;
+  static_assert(kTotal <= 232448, "227 KB of shared memory per CTA");
   static_assert(sizeof(PlaneView) * kMaxFramePlanes <= 256, "");
   static_assert(kStage % 128 == 0 && kRec % 128 == 0 && kWeights % 128 == 0, "TMA / bulk-copy destinations");
 };
@@ -322,15 +342,15 @@ template <int K, int COPIES, int GROUPS>
 __global__ void __launch_bounds__(GROUPS * (kGroupWarps + 1) * 32, 1)
 gatherFrameKernel(const __grid_constant__ FrameGatherParams p, StagedParams jobs, const __grid_constant__ FrameTensorMaps maps) {
   using L = FrameLayout<K, COPIES, GROUPS>;
-  constexpr int VS = weightVectorStride(K, COPIES), kStage = L::kStage, kRec = L::kRec;
+  constexpr int VS = weightVectorStride(K, COPIES), kStage = L::kStage, kRec = L::kRec, S = L::kStages;
   constexpr uint32_t kBox0 = stageBoxW(K, 0) * stageBoxH(K, 0), kBox1 = stageBoxW(K, 1) * stageBoxH(K, 1),
                      kBoxShare = stageBoxW(K, 2) * stageBoxH(K, 2);
   static_assert(kBox1 + 64 <= 2 * kStage && kBox0 + 64 <= kStage && kBoxShare + 64 <= kStage, "boxes must fit their stage buffers");
   extern __shared__ __align__(128) unsigned char smem[];
   unsigned char* wsmem = smem;
   PlaneView* planes = reinterpret_cast<PlaneView*>(smem + L::kPlanes);
-  uint64_t* barBase = reinterpret_cast<uint64_t*>(smem + L::kBars);  // group g: full[0], full[1], empty[0], empty[1]
-  uint64_t* weightBar = barBase + GROUPS * 4;
+  uint64_t* barBase = reinterpret_cast<uint64_t*>(smem + L::kBars);  // group g: full[S], empty[S]
+  uint64_t* weightBar = barBase + GROUPS * 2 * S;
   const int warpId = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int kProducerWarp = GROUPS * kGroupWarps;
 
@@ -340,12 +360,11 @@ gatherFrameKernel(const __grid_constant__ FrameGatherParams p, StagedParams jobs
   // touched after griddepcontrol.wait below.
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (threadIdx.x == 0) {
-    for (int g = 0; g < GROUPS; ++g) {
-      mbarInit(barBase + g * 4 + 0, 1);
-      mbarInit(barBase + g * 4 + 1, 1);
-      mbarInit(barBase + g * 4 + 2, kGroupWarps);
-      mbarInit(barBase + g * 4 + 3, kGroupWarps);
-    }
+    for (int g = 0; g < GROUPS; ++g)
+      for (int st = 0; st < S; ++st) {
+        mbarInit(barBase + g * 2 * S + st, 1);
+        mbarInit(barBase + g * 2 * S + S + st, kGroupWarps);
+      }
     mbarInit(weightBar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -362,11 +381,11 @@ gatherFrameKernel(const __grid_constant__ FrameGatherParams p, StagedParams jobs
       for (int i = 0; i < 4; ++i)
         bulkCopyToShared(wsmem + i * kChunk, reinterpret_cast<const unsigned char*>(p.weightImage) + i * kChunk, kChunk, weightBar);
     }
-    // Jobs are claimed kClaimBatch at a time: the first batch of a producer is static, every further one comes from the
-    // global counter.  Lane i holds the header of job i of the batch; the next batch (claim + header loads) is in
-    // flight while the current one is handed out, so neither the atomic nor the loads are waited for, and the records
-    // and source window of its jobs are requested into L2 a batch ahead of the copies into shared memory.
-    const int producer = blockIdx.x * GROUPS + g, dynamicBase = gridDim.x * GROUPS * kClaimBatch;
+    // Jobs are claimed kClaimBatch at a time: the first two batches of a producer are static, every further one comes
+    // from the global counter.  Lane i holds the header of job i of the batch.  The claim runs two batches ahead and the
+    // header loads one, so neither the atomic nor the loads are waited for, and the records and source window of a
+    // batch's jobs are requested into L2 a batch ahead of the copies into shared memory.
+    const int producer = blockIdx.x * GROUPS + g, dynamicBase = gridDim.x * GROUPS * 2 * kClaimBatch;
     auto loadBatch = [&](int base) {
       int4 h = make_int4(0, kJobExit << kJobKindShift, 0, 0);
       if (lane < kClaimBatch && base + lane < jobs.numTiles) h = __ldg(reinterpret_cast<const int4*>(jobs.tiles) + base + lane);
@@ -374,33 +393,37 @@ gatherFrameKernel(const __grid_constant__ FrameGatherParams p, StagedParams jobs
     };
     auto prefetchBatch = [&](const int4& h) {
       const int kind = (h.y >> kJobKindShift) & kJobKindMask;
-      if (kind != kJobShare && kind != kJobClass0 && kind != kJobClass1) return;
+      if (kind != kJobShare && kind != kJobShareStay && kind != kJobClass0 && kind != kJobClass1 && kind != kJobSeam) return;
       const int pl = h.y >> kJobPlaneShift;
-      const uint32_t recBytes = kind == kJobShare ? shareJobRecordBytes(K) : kTileJobRecordBytes;
+      const uint32_t recBytes = boxClassOf(kind) == 2 ? shareJobRecordBytes(K) : kTileJobRecordBytes;
       asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(planes[pl].records + (unsigned)h.w), "r"(recBytes) : "memory");
       asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];"
                    ::"l"(reinterpret_cast<uint64_t>(&maps.map[pl][boxClassOf(kind)])), "r"(h.z & 0xffff), "r"(h.z >> 16) : "memory");
     };
-    int4 batch = loadBatch(producer * kClaimBatch);
+    // (the first TWO batches are static, so that the first job is not held up by the round trip of an atomic)
+    int4 batch = loadBatch(producer * 2 * kClaimBatch);
+    int4 batchNext = loadBatch((producer * 2 + 1) * kClaimBatch);
     asm volatile("griddepcontrol.wait;" ::: "memory");  // earlier kernels on the stream are complete and visible from here on
-    int claimed = 0;
+    int claimed = 0;  // lane 0: the claim for the batch after next, issued one batch before it is looked at
     if (lane == 0) claimed = atomicAdd(jobs.claimCounter, kClaimBatch);
-    claimed = __shfl_sync(0xffffffffu, claimed, 0);
-    int4 batchNext = loadBatch(dynamicBase + claimed);
     prefetchBatch(batch);
     prefetchBatch(batchNext);
     unsigned char* groupBase = smem + L::kWeights + g * L::kGroupBytes;
-    uint64_t* full = barBase + g * 4;
-    uint64_t* empty = full + 2;
+    uint64_t* full = barBase + g * 2 * S;
+    uint64_t* empty = full + S;
     int pos = 0;
-    uint32_t n = 0;  // stages handed to the group so far: stage = n & 1, use count = n >> 1
+    uint32_t st = 0, phase = 0;  // the stage the next job goes to, and the parity of its use count
+    auto advance = [&]() { if (++st == S) { st = 0; phase ^= 1; } };
+    auto postEmptyJob = [&](int kind) {  // header only (lane 0)
+      *reinterpret_cast<int4*>(groupBase + S * kStage + st * kRec) = make_int4(0, kind << kJobKindShift, 0, 0);
+      mbarArrive(full + st);
+    };
     for (;;) {
       if (pos == kClaimBatch) {  // next batch; start claiming the one after
         batch = batchNext;
         pos = 0;
+        batchNext = loadBatch(dynamicBase + __shfl_sync(0xffffffffu, claimed, 0));
         if (lane == 0) claimed = atomicAdd(jobs.claimCounter, kClaimBatch);
-        claimed = __shfl_sync(0xffffffffu, claimed, 0);
-        batchNext = loadBatch(dynamicBase + claimed);
         prefetchBatch(batchNext);
       }
       int4 h;
@@ -408,32 +431,41 @@ gatherFrameKernel(const __grid_constant__ FrameGatherParams p, StagedParams jobs
       h.z = __shfl_sync(0xffffffffu, batch.z, pos); h.w = __shfl_sync(0xffffffffu, batch.w, pos);
       ++pos;
       const int kind = (h.y >> kJobKindShift) & kJobKindMask;
-      const bool twoStages = kind == kJobClass1;  // its box spans both stage buffers: both must be free
-      mbarWait(empty + (n & 1), ((n >> 1) & 1) ^ 1);
-      if (twoStages) mbarWait(empty + ((n + 1) & 1), (((n + 1) >> 1) & 1) ^ 1);
+      mbarWait(empty + st, phase ^ 1);
+      const bool twoStages = kind == kJobClass1 || kind == kJobSeam;
+      if (twoStages) {
+        // its box(es) span two stage buffers: they must be adjacent (not the last and the first) and both free; no-op
+        // jobs stand for the stages that carry no job of their own
+        if (st == S - 1) {
+          if (lane == 0) postEmptyJob(kJobNop);
+          advance();
+          mbarWait(empty + st, phase ^ 1);
+        }
+        mbarWait(empty + st + 1, phase ^ 1);  // (st + 1 < S: the same round of the ring)
+      }
       if (lane == 0) {
-        const uint32_t st = n & 1;
-        unsigned char* rec = groupBase + 2 * kStage + st * kRec;
+        unsigned char* rec = groupBase + S * kStage + st * kRec;
         *reinterpret_cast<int4*>(rec) = h;
-        if (kind == kJobShare || kind == kJobClass0 || kind == kJobClass1) {
+        if (kind == kJobShare || kind == kJobShareStay || kind == kJobClass0 || kind == kJobClass1 || kind == kJobSeam) {
           const int pl = h.y >> kJobPlaneShift;
-          const uint32_t boxBytes = kind == kJobShare ? kBoxShare : (kind == kJobClass0 ? kBox0 : kBox1);
-          const uint32_t recBytes = kind == kJobShare ? shareJobRecordBytes(K) : kTileJobRecordBytes;
+          const bool share = boxClassOf(kind) == 2;
+          const uint32_t boxBytes = share ? kBoxShare : (kind == kJobClass1 ? kBox1 : (kind == kJobSeam ? 2 * kBox0 : kBox0));
+          const uint32_t recBytes = share ? shareJobRecordBytes(K) : kTileJobRecordBytes;
           mbarExpectTx(full + st, boxBytes + recBytes);
-          // class-1 boxes start at the first stage buffer whatever the stage (both are free)
-          tmaLoadBox(groupBase + (twoStages ? 0 : st * kStage), &maps.map[pl][boxClassOf(kind)], h.z & 0xffff, h.z >> 16, full + st);
+          tmaLoadBox(groupBase + st * kStage, &maps.map[pl][boxClassOf(kind)], h.z & 0xffff, h.z >> 16, full + st);
+          if (kind == kJobSeam)  // the part of the window beyond the right border, from the left of the plane
+            tmaLoadBox(groupBase + (st + 1) * kStage, &maps.map[pl][0], (h.z & 0xffff) - planes[pl].srcW, h.z >> 16, full + st);
           bulkCopyToShared(rec + 128, planes[pl].records + (unsigned)h.w, recBytes, full + st);
         } else {
           mbarArrive(full + st);  // general job / end of list: the header is all there is
         }
-        if (twoStages) {  // the second stage of the pair is taken too: a no-op job stands for it
-          unsigned char* rec2 = groupBase + 2 * kStage + (st ^ 1) * kRec;
-          *reinterpret_cast<int4*>(rec2) = make_int4(0, kJobNop << kJobKindShift, 0, 0);
-          mbarArrive(full + (st ^ 1));
-        }
+      }
+      advance();
+      if (twoStages) {
+        if (lane == 0) postEmptyJob(kJobNop);
+        advance();
       }
       __syncwarp();
-      n += twoStages ? 2u : 1u;
       if (kind == kJobExit) break;
     }
     // the producer that finishes last re-arms the scheduler for the next launch (claimCounter[0] = claims, [1] = finished)
@@ -448,22 +480,26 @@ gatherFrameKernel(const __grid_constant__ FrameGatherParams p, StagedParams jobs
   // ===================================== consumers ===================================================================
   const int group = warpId / kGroupWarps, warp = warpId % kGroupWarps;
   unsigned char* groupBase = smem + L::kWeights + group * L::kGroupBytes;
-  const uint32_t boxAddr = smemAddr(groupBase), recAddr = smemAddr(groupBase + 2 * kStage);
-  uint64_t* full = barBase + group * 4;
-  uint64_t* empty = full + 2;
+  const uint32_t boxAddr = smemAddr(groupBase), recAddr = smemAddr(groupBase + S * kStage);
+  uint64_t* full = barBase + group * 2 * S;
+  uint64_t* empty = full + S;
   const uint32_t wAddr = smemAddr(wsmem);
   mbarWait(weightBar, 0);
   asm volatile("griddepcontrol.wait;" ::: "memory");  // the planes may still be in use by earlier kernels until here
-  for (uint32_t n = 0;; ++n) {
-    const uint32_t st = n & 1;
-    mbarWait(full + st, (n >> 1) & 1);
+  auto now = []() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; };
+  unsigned long long* trace = jobs.trace && warp == 0 && lane == 0 ? jobs.trace + (size_t)(blockIdx.x * GROUPS + group) * kTraceJobsPerGroup * 4 : nullptr;
+  uint32_t traced = 0;
+  for (uint32_t st = 0, phase = 0;;) {
+    const unsigned long long t0 = trace ? now() : 0;
+    mbarWait(full + st, phase);
+    const unsigned long long t1 = trace ? now() : 0;
     const uint32_t rec = recAddr + st * kRec;
     const uint4 h = ldsVec(rec);
     const int kind = ((int)h.y >> kJobKindShift) & kJobKindMask;
     if (kind == kJobExit) break;
-    const int outX = (int)h.x, outY = (int)h.y & kJobRowMask;
+    const int outX = (int)h.x & ~kJobQuadMask, outY = (int)h.y & kJobRowMask;
     const PlaneView& pv = planes[(int)h.y >> kJobPlaneShift];
-    if (kind == kJobShare) {
+    if (kind == kJobShare || kind == kJobShareStay) {
       if constexpr (K >= 4) {
         const uint32_t mine = rec + 128 + warp * shareWarpRecordBytes(K);
         uint4 r[shareRows(K) / 8];
@@ -471,17 +507,39 @@ gatherFrameKernel(const __grid_constant__ FrameGatherParams p, StagedParams jobs
         for (int b = 0; b < shareRows(K) / 8; ++b) r[b] = ldsVec(mine + b * 512 + lane * 16);
         const uint32_t header = ldsWord(mine + shareRows(K) / 8 * 512 + lane * 4);
         uint8_t* dst = pv.dst + (size_t)(outY + (warp >> 1) * shareRows(K)) * pv.dstPitch + (outX + (warp & 1) * 32 + (int)(header >> kRecordColumnShift));
-        computeShareJob<K, stageBoxW(K, 2), VS, shareRows(K)>(dst, pv.dstPitch, boxAddr + st * kStage, r, header, wAddr);
+        if (kind == kJobShare) computeShareJob<K, stageBoxW(K, 2), VS, shareRows(K), false>(dst, pv.dstPitch, boxAddr + st * kStage, r, header, wAddr);
+        else computeShareJob<K, stageBoxW(K, 2), VS, shareRows(K), true>(dst, pv.dstPitch, boxAddr + st * kStage, r, header, wAddr);
       }
     } else if (kind == kJobClass0) {
       computeTileJob<K, stageBoxW(K, 0), VS>(pv, boxAddr + st * kStage, outX, outY, ldsVec(rec + 128 + warp * 512 + lane * 16), wAddr, warp);
     } else if (kind == kJobClass1) {
-      computeTileJob<K, stageBoxW(K, 1), VS>(pv, boxAddr, outX, outY, ldsVec(rec + 128 + warp * 512 + lane * 16), wAddr, warp);
+      computeTileJob<K, stageBoxW(K, 1), VS>(pv, boxAddr + st * kStage, outX, outY, ldsVec(rec + 128 + warp * 512 + lane * 16), wAddr, warp);
+    } else if (kind == kJobSeam) {
+      // two complementary class-0 boxes (zero-filled outside the plane) in this stage and the next: OR the second into
+      // the first -- all warps of the group, then everybody waits for everybody
+      {
+        uint4* a = reinterpret_cast<uint4*>(groupBase + st * kStage);
+        const uint4* b = reinterpret_cast<const uint4*>(groupBase + (st + 1) * kStage);
+        for (int i = warp * 32 + lane; i < (int)(kBox0 / 16); i += kGroupThreads) {
+          uint4 x = a[i];
+          const uint4 y = b[i];
+          x.x |= y.x; x.y |= y.y; x.z |= y.z; x.w |= y.w;
+          a[i] = x;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // these writes precede later TMA writes to the stage
+      }
+      groupBarrier(group);
+      computeTileJob<K, stageBoxW(K, 0), VS>(pv, boxAddr + st * kStage, outX, outY, ldsVec(rec + 128 + warp * 512 + lane * 16), wAddr, warp);
     } else if (kind == kJobGeneral) {
       computeGeneralJob<K, VS>(pv, outX, outY, wsmem, wAddr, lane, warp);
     }
     __syncwarp();
     if (lane == 0) mbarArrive(empty + st);  // this warp is done with the stage (its shared-memory reads are complete)
+    if (trace && traced < kTraceJobsPerGroup) {
+      trace[traced * 4 + 0] = t0; trace[traced * 4 + 1] = t1; trace[traced * 4 + 2] = now(); trace[traced * 4 + 3] = kind;
+      ++traced;
+    }
+    if (++st == S) { st = 0; phase ^= 1; }
   }
 }
 
@@ -493,7 +551,7 @@ cudaError_t launchFrameK(const FrameGatherParams& p, const StagedParams& jobs, c
   LaunchCfg cfg;
   cudaError_t err = prepare<gatherFrameKernel<K, COPIES, GROUPS>>(cfgs, threads, smemBytes, cfg);
   if (err != cudaSuccess) return err;
-  const int grid = std::min(numSMs * cfg.perSM, (jobs.numTiles + GROUPS * kClaimBatch - 1) / (GROUPS * kClaimBatch));  // persistent: one CTA per SM
+  const int grid = std::min(numSMs * cfg.perSM, (jobs.numTiles + GROUPS * 2 * kClaimBatch - 1) / (GROUPS * 2 * kClaimBatch));  // persistent: one CTA per SM
   cudaLaunchConfig_t lc{};
   lc.gridDim = dim3(grid);
   lc.blockDim = dim3(threads);

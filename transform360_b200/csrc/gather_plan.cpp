@@ -104,6 +104,8 @@ struct TileClass {
   int kind = -1;  // kJob*; -1: covered by the share job that starts at the tile to its left (or at this tile)
   int boxX = 0, boxY = 0;
   bool shareStart = false;
+  bool quads = false;  // four class-0 jobs, one per 16 x 16 quadrant, each with its own box
+  int quadBoxX[4] = {}, quadBoxY[4] = {};
 };
 
 // Bounding box of the source windows of a block of output pixels.
@@ -124,43 +126,91 @@ Extent extentOf(const HostPlan& h, int x0, int y0, int x1, int y1) {
 }
 
 // A 64 x shareH block qualifies as a share job when every column keeps its first source column down the rows, steps
-// 1 or 2 source rows per output row, and the windows of the whole block fit one 192-byte-wide box inside the plane.
+// 1 or 2 source rows per output row (0 - 2: kJobShareStay), and the windows of the whole block fit one 192-byte-wide
+// box inside the plane.
 bool shareBlock(const HostPlan& h, int x0, int y0, TileClass& out) {
   const int k = h.kernelSize, kShareH = shareH(k);
   if (k < 4 || x0 + kShareW > h.mapW || y0 + kShareH > h.mapH) return false;
+  bool stays = false;
   for (int y = y0 + 1; y < y0 + kShareH; ++y) {
     const SamplePoint* a = &h.samples[static_cast<size_t>(y - 1) * h.mapW + x0];
     const SamplePoint* b = a + h.mapW;
     for (int x = 0; x < kShareW; ++x) {
       const int d = (b[x].rowPhase >> 10) - (a[x].rowPhase >> 10);
-      if (b[x].col0 != a[x].col0 || d < 1 || d > 2) return false;
+      if (b[x].col0 != a[x].col0 || d < 0 || d > 2) return false;
+      stays = stays || d == 0;
     }
   }
   const Extent e = extentOf(h, x0, y0, x0 + kShareW, y0 + kShareH);
   if (e.minC < 0 || e.minR < 0 || e.maxC + k > h.inW || e.maxR + k > h.inH) return false;
   const int boxX = e.minC & ~15;
   if (e.maxC + k - boxX > stageBoxW(k, 2) || e.maxR + k - e.minR > stageBoxH(k, 2)) return false;
-  out.kind = kJobShare;
+  out.kind = stays ? kJobShareStay : kJobShare;
   out.boxX = boxX;
   out.boxY = e.minR;
   out.shareStart = true;
   return true;
 }
 
-void classifyTile(const HostPlan& h, int x0, int y0, TileClass& out) {
+// class of the box that holds the windows of the pixel block [x0, x1) x [y0, y1): 0, 1 or -1
+int boxClassFor(const HostPlan& h, int x0, int y0, int x1, int y1, int maxClass, int* boxX, int* boxY) {
+  const int k = h.kernelSize;
+  const Extent e = extentOf(h, x0, y0, x1, y1);
+  if (e.minC < 0 || e.minR < 0 || e.maxC + k > h.inW || e.maxR + k > h.inH) return -1;
+  *boxX = e.minC & ~15;
+  *boxY = e.minR;
+  for (int cls = 0; cls <= maxClass; ++cls)
+    if (e.maxC + k - *boxX <= stageBoxW(k, cls) && e.maxR + k - e.minR <= stageBoxH(k, cls)) return cls;
+  return -1;
+}
+
+void classifyTile(const HostPlan& h, int x0, int y0, bool seamPossible, TileClass& out) {
   const int k = h.kernelSize;
   const int x1 = std::min(h.mapW, x0 + kGatherTileW), y1 = std::min(h.mapH, y0 + kFrameTileH);
+  const int cls = boxClassFor(h, x0, y0, x1, y1, 1, &out.boxX, &out.boxY);
+  if (cls == 0) {
+    out.kind = kJobClass0;
+    return;
+  }
+  // The ring around a pole cap: the tile's windows span hundreds of columns, those of a 16 x 16 quadrant fit a class-0
+  // box.  Also preferred to a class-1 job, whose box takes both stage buffers of a group and so cannot be loaded while
+  // the group computes (measured: 2.0 us of waiting per class-1 job against 0.15 us per class-0 job).
+  if (x1 - x0 == kGatherTileW && y1 - y0 == kFrameTileH) {
+    bool all = true;
+    for (int q = 0; q < 4 && all; ++q) {
+      const int qx = x0 + 16 * (q & 1), qy = y0 + 16 * (q >> 1);
+      all = boxClassFor(h, qx, qy, qx + 16, qy + 16, 0, &out.quadBoxX[q], &out.quadBoxY[q]) == 0;
+    }
+    if (all) {
+      out.kind = kJobClass0;
+      out.quads = true;
+      return;
+    }
+  }
+  if (cls == 1) {
+    out.kind = kJobClass1;
+    return;
+  }
+  // windows that cross the left/right border only (BORDER_WRAP): do they fit a class-0 box that wraps around it?
   const Extent e = extentOf(h, x0, y0, x1, y1);
-  const bool inPlane = e.minC >= 0 && e.minR >= 0 && e.maxC + k <= h.inW && e.maxR + k <= h.inH;
-  if (inPlane) {
-    const int boxX = e.minC & ~15;
-    for (int cls = 0; cls < 2; ++cls)
-      if (e.maxC + k - boxX <= stageBoxW(k, cls) && e.maxR + k - e.minR <= stageBoxH(k, cls)) {
-        out.kind = cls == 0 ? kJobClass0 : kJobClass1;
-        out.boxX = boxX;
-        out.boxY = e.minR;
-        return;
+  if (seamPossible && e.minR >= 0 && e.maxR + k <= h.inH && e.maxR + k - e.minR <= stageBoxH(k, 0)) {
+    const int W = h.inW, half = W / 2;  // columns rotated by half a plane: the border is in the middle of the range
+    int lo = INT32_MAX, hi = INT32_MIN;
+    for (int y = y0; y < y1; ++y)
+      for (int x = x0; x < x1; ++x) {
+        int cw = h.samples[static_cast<size_t>(y) * h.mapW + x].col0 % W;
+        if (cw < 0) cw += W;
+        const int rot = cw + half >= W ? cw + half - W : cw + half;
+        lo = std::min(lo, rot); hi = std::max(hi, rot);
       }
+    const int first = lo - half < 0 ? lo - half + W : lo - half;  // leftmost first column, in plane coordinates
+    const int bx = first & ~15;
+    if (hi - lo + (first - bx) + k <= stageBoxW(k, 0) && bx + stageBoxW(k, 0) > W) {
+      out.kind = kJobSeam;
+      out.boxX = bx;
+      out.boxY = e.minR;
+      return;
+    }
   }
   out.kind = kJobGeneral;
   out.boxX = out.boxY = 0;
@@ -173,6 +223,7 @@ void writeShareRecords(const HostPlan& h, const GatherJob& job, uint32_t* out) {
   const int k = h.kernelSize, copies = weightCopies(k), kShareRows = shareRows(k), kShareH = shareH(k);
   const int x0 = job.outX, y0 = job.outY & kJobRowMask, boxX = job.boxXY & 0xffff, boxY = job.boxXY >> 16;
   const int pitch = stageBoxW(k, 2);
+  const bool stay = ((job.outY >> kJobKindShift) & kJobKindMask) == kJobShareStay;
   for (int wx = 0; wx < kShareW / 32; ++wx) {
     for (int wy = 0; wy < kShareH / kShareRows; ++wy) {
       // the bank group of a pixel's weights depends on fracX only, which a column keeps (up to rounding jitter of the
@@ -191,8 +242,9 @@ void writeShareRecords(const HostPlan& h, const GatherJob& job, uint32_t* out) {
         headers[lane] = static_cast<uint32_t>(off) | (static_cast<uint32_t>(c) << kRecordColumnShift);
         for (int j = 0; j < kShareRows; ++j) {
           const SamplePoint& sp = col[static_cast<size_t>(j) * h.mapW];
-          const int d = j == 0 ? 1 : (sp.rowPhase >> 10) - (col[static_cast<size_t>(j - 1) * h.mapW].rowPhase >> 10);
-          const uint32_t rec = slotField(k, sp.rowPhase & 1023, copyOf[c]) | static_cast<uint32_t>(d - 1);  // bit 0: a second row
+          const int first = stay ? 0 : 1;
+          const int d = j == 0 ? first : (sp.rowPhase >> 10) - (col[static_cast<size_t>(j - 1) * h.mapW].rowPhase >> 10);
+          const uint32_t rec = slotField(k, sp.rowPhase & 1023, copyOf[c]) | static_cast<uint32_t>(d - first);  // kJobShare: bit 0 = a second row
           uint32_t& word = words[(j >> 3) * 32 * 4 + lane * 4 + ((j >> 1) & 3)];
           word = (j & 1) ? (word | (rec << 16)) : rec;
         }
@@ -201,32 +253,50 @@ void writeShareRecords(const HostPlan& h, const GatherJob& job, uint32_t* out) {
   }
 }
 
-// compact records of a 32 x 32 job (class 0, class 1, seam)
+// compact records of a 32 x 32 job (class 0, class 1): warp w takes rows 4w .. 4w+3 in four steps of one 8 x 4 patch
+// each (a compact patch keeps the 32 source windows of a step close together: 1.6 shared-memory wavefronts per window
+// load in the bank model where a 32 x 1 row segment costs 2.2 on the polar faces)
 void writeTileRecords(const HostPlan& h, const GatherJob& job, uint32_t* out) {
   const int k = h.kernelSize, copies = weightCopies(k);
   const int kind = (job.outY >> kJobKindShift) & kJobKindMask;
-  const int x0 = job.outX, y0 = job.outY & kJobRowMask, boxX = job.boxXY & 0xffff, boxY = job.boxXY >> 16;
+  const int x0 = job.outX & ~kJobQuadMask, y0 = job.outY & kJobRowMask, boxX = job.boxXY & 0xffff, boxY = job.boxXY >> 16;
   const int pitch = stageBoxW(k, boxClassOf(kind));
-  const int n = std::min(32, h.mapW - x0);
-  for (int yy = 0; yy < kFrameTileH; ++yy) {
-    const int y = y0 + yy, w = yy / 4, j = yy % 4;
-    uint32_t* words = out + static_cast<size_t>(w) * 32 * 4;
-    if (y >= h.mapH) {  // below the plane: the kernel skips the row (y >= dstH)
-      for (int lane = 0; lane < 32; ++lane) words[lane * 4 + j] = static_cast<uint32_t>(lane) << 16;
-      continue;
+  // the live rectangle: the whole tile, or one quadrant
+  const int quad = (job.outX & kJobQuadMask) - 1;
+  const int lx0 = quad < 0 ? x0 : x0 + 16 * (quad & 1), ly0 = quad < 0 ? y0 : y0 + 16 * (quad >> 1);
+  const int lx1 = quad < 0 ? x0 + kGatherTileW : lx0 + 16, ly1 = quad < 0 ? y0 + kFrameTileH : ly0 + 16;
+  for (int w = 0; w < kGroupWarps; ++w)
+    for (int j = 0; j < kRowsPerPatchStep; ++j) {
+      uint32_t* words = out + static_cast<size_t>(w) * 32 * 4;
+      // the pixels of the patch that exist, in position order; the others keep a position that fails the bounds check
+      int slot[32], laneOf[32], copyOf[32], posOf[32], n = 0;
+      bool present[32] = {};
+      for (int pos = 0; pos < 32; ++pos) {
+        const int x = x0 + kTilePatchW * j + (pos & (kTilePatchW - 1)), y = y0 + kTilePatchH * w + pos / kTilePatchW;
+        if (x >= h.mapW || y >= h.mapH || x < lx0 || x >= lx1 || y < ly0 || y >= ly1) continue;
+        present[pos] = true;
+        posOf[n] = pos;
+        slot[n++] = weightSlotOf(k, h.samples[static_cast<size_t>(y) * h.mapW + x].rowPhase & 1023);
+      }
+      dealLanes(k, copies, n, slot, laneOf, copyOf);  // n < 32: identity order
+      int lane = n;
+      for (int pos = 0; pos < 32; ++pos)
+        if (!present[pos]) words[(lane++) * 4 + j] = (static_cast<uint32_t>(pos) << 16) | kRecordSkip;
+      for (int i = 0; i < n; ++i) {
+        const int pos = posOf[i];
+        const int x = x0 + kTilePatchW * j + (pos & (kTilePatchW - 1)), y = y0 + kTilePatchH * w + pos / kTilePatchW;
+        const SamplePoint& sp = h.samples[static_cast<size_t>(y) * h.mapW + x];
+        int col0 = sp.col0;
+        if (kind == kJobSeam) {  // first column relative to the unwrapped box (boxX <= col0 < boxX + box width)
+          int cw = col0 % h.inW;
+          if (cw < 0) cw += h.inW;
+          col0 = boxX + (cw - boxX + h.inW) % h.inW;
+        }
+        const int off = ((sp.rowPhase >> 10) - boxY) * pitch + (col0 - boxX);
+        words[laneOf[i] * 4 + j] = static_cast<uint32_t>(off) | (static_cast<uint32_t>(pos) << 16) |
+                                   (slotField(k, sp.rowPhase & 1023, copyOf[i]) << 17);
+      }
     }
-    const SamplePoint* row = &h.samples[static_cast<size_t>(y) * h.mapW + x0];
-    int slot[32], laneOf[32], copyOf[32];
-    for (int i = 0; i < n; ++i) slot[i] = weightSlotOf(k, row[i].rowPhase & 1023);
-    dealLanes(k, copies, n, slot, laneOf, copyOf);
-    for (int c = n; c < 32; ++c) words[c * 4 + j] = static_cast<uint32_t>(c) << 16;  // right of the plane: skipped (x >= dstW)
-    for (int c = 0; c < n; ++c) {
-      const int col0 = row[c].col0;
-      const int off = ((row[c].rowPhase >> 10) - boxY) * pitch + (col0 - boxX);
-      words[laneOf[c] * 4 + j] = static_cast<uint32_t>(off) | (static_cast<uint32_t>(c) << 16) |
-                                 (slotField(k, row[c].rowPhase & 1023, copyOf[c]) << 17);
-    }
-  }
 }
 
 }  // namespace
@@ -338,6 +408,8 @@ void buildGatherPlan(const HostPlan& h, bool stageTiles, GatherPlan& g) {
 
   // ---- cut the plane into jobs: 64 x 32 share blocks where the geometry allows, 32 x 32 tiles elsewhere
   const int tilesX = g.tilesPerRow, tilesY = (h.mapH + kFrameTileH - 1) / kFrameTileH;
+  // seam tiles need whole 16-byte columns on both sides of the border and a plane much wider than the box
+  const bool seamPossible = h.inW % 16 == 0 && h.inW >= 4 * stageBoxW(k, 0);
   std::vector<TileClass> cls(static_cast<size_t>(tilesX) * tilesY);
   const int blockRows = shareH(k) / kFrameTileH;  // tile rows a share block spans
   parallelRanges((tilesY + blockRows - 1) / blockRows, static_cast<size_t>(h.mapW) * shareH(k), [&](int byBegin, int byEnd) {
@@ -347,29 +419,36 @@ void buildGatherPlan(const HostPlan& h, bool stageTiles, GatherPlan& g) {
         if (shareBlock(h, tx * 32, by * shareH(k), c[0])) continue;  // the other tiles of the block stay -1: covered
         for (int ty = by * blockRows; ty < std::min(tilesY, (by + 1) * blockRows); ++ty)
           for (int t = tx; t < std::min(tilesX, tx + 2); ++t)
-            classifyTile(h, t * 32, ty * kFrameTileH, cls[static_cast<size_t>(ty) * tilesX + t]);
+            classifyTile(h, t * 32, ty * kFrameTileH, seamPossible, cls[static_cast<size_t>(ty) * tilesX + t]);
       }
   });
   // launch order: general tiles (latency-bound: they run while every group of the SM is busy), seam, class 1 (both
   // need the two stage buffers), then the share jobs and finally the small class-0 tiles through the double-buffered
   // TMA pipeline, which leaves a short, fine-grained tail
-  const int order[4] = {kJobGeneral, kJobClass1, kJobShare, kJobClass0};
+  const int order[6] = {kJobGeneral, kJobSeam, kJobClass1, kJobShareStay, kJobShare, kJobClass0};
   size_t offset = 0;  // bytes
   for (int kind : order)
     for (int ty = 0; ty < tilesY; ++ty)
       for (int tx = 0; tx < tilesX; ++tx) {
         const TileClass& c = cls[static_cast<size_t>(ty) * tilesX + tx];
         if (c.kind != kind) continue;
-        GatherJob job{tx * 32, ty * kFrameTileH | (kind << kJobKindShift), c.boxX | (c.boxY << 16), 0};
-        if (kind != kJobGeneral) {
-          job.recordOffset = static_cast<int>(offset / 16);
-          offset += kind == kJobShare ? shareJobRecordBytes(k) : kTileJobRecordBytes;
+        for (int q = 0; q < (c.quads ? 4 : 1); ++q) {
+          GatherJob job{tx * 32, ty * kFrameTileH | (kind << kJobKindShift), c.boxX | (c.boxY << 16), 0};
+          if (c.quads) {
+            job.outX |= q + 1;
+            job.boxXY = c.quadBoxX[q] | (c.quadBoxY[q] << 16);
+          }
+          if (kind != kJobGeneral) {
+            job.recordOffset = static_cast<int>(offset / 16);
+            offset += boxClassOf(kind) == 2 ? shareJobRecordBytes(k) : kTileJobRecordBytes;
+          }
+          g.jobs.push_back(job);
         }
-        g.jobs.push_back(job);
         switch (kind) {
           case kJobGeneral: ++g.numGeneral; break;
-          case kJobShare: ++g.numShare; break;
-          default: ++g.numStaged[kind]; break;
+          case kJobSeam: ++g.numSeam; break;
+          case kJobShare: case kJobShareStay: ++g.numShare; break;
+          default: g.numStaged[kind] += c.quads ? 4 : 1; break;
         }
       }
   g.compact.assign(offset / 4, 0u);
@@ -379,7 +458,7 @@ void buildGatherPlan(const HostPlan& h, bool stageTiles, GatherPlan& g) {
       const int kind = (job.outY >> kJobKindShift) & kJobKindMask;
       if (kind == kJobGeneral) continue;
       uint32_t* out = g.compact.data() + static_cast<size_t>(job.recordOffset) * 4;
-      if (kind == kJobShare) writeShareRecords(h, job, out);
+      if (boxClassOf(kind) == 2) writeShareRecords(h, job, out);
       else writeTileRecords(h, job, out);
     }
   });

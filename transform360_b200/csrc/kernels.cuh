@@ -5,6 +5,10 @@
 
 #include <cstdint>
 
+#ifndef T360_STAGES
+#define T360_STAGES 2
+#endif
+
 namespace t360 {
 
 // One gather launch: dst[y][x] = interpolate(src, samples[y][x]) for a whole plane.
@@ -22,7 +26,7 @@ struct GatherParams {
 
 // ---- the persistent frame gather (gatherFrameKernel) -------------------------------------------------------------
 // One CTA per SM: gatherGroups(k) GROUPS of 8 consumer warps + 1 producer warp each, all sharing one copy of the weight
-// tables in shared memory.  A producer claims jobs from the frame's job list (an atomic counter, four jobs at a time),
+// tables in shared memory.  A producer claims jobs from the frame's job list (an atomic counter, one job at a time: 55.8 us per cfg2 frame against 58.5 / 63.2 with batches of 2 / 4, whose last batches leave groups idle at the end),
 // and for every job fills one stage of its group's two-stage ring: the job header (st.shared), the job's
 // compact sampling records (cp.async.bulk) and its source window (ONE cp.async.bulk.tensor.2d box from the
 // pitch-linear plane), all signalled through the stage's "full" mbarrier.  The consumer warps wait for "full", compute,
@@ -35,15 +39,25 @@ struct GatherJob {
   int recordOffset;  // of the job's compact records, in 16-byte units from the plane's record buffer
 };
 using StagedTile = GatherJob;
-constexpr int kJobClass0 = 0, kJobClass1 = 1, kJobGeneral = 2, kJobShare = 4, kJobNop = 5, kJobExit = 6;
+constexpr int kJobClass0 = 0, kJobClass1 = 1, kJobGeneral = 2, kJobShareStay = 3, kJobShare = 4, kJobNop = 5, kJobExit = 6, kJobSeam = 7;
+// A 32 x 32 job may cover one 16 x 16 quadrant of its tile only (a tile whose windows fit no box as a whole, but whose
+// quadrants do: the ring around a pole cap): outX carries 1 + the quadrant in its low bits (0: the whole tile), and the
+// records of the pixels outside the quadrant have kRecordSkip set.
+constexpr int kJobQuadMask = 7;
+constexpr uint32_t kRecordSkip = 0x8000u;
 constexpr int kJobKindShift = 24, kJobRowMask = (1 << kJobKindShift) - 1;
 constexpr int kJobPlaneShift = 28, kJobKindMask = (1 << (kJobPlaneShift - kJobKindShift)) - 1;
 
 constexpr int kGroupThreads = 256, kGroupWarps = kGroupThreads / 32;
 // consumer groups per CTA (+ one producer warp): as many as the rings fit beside the weight tables in 227 KB
 __host__ __device__ constexpr int gatherGroups(int k) { return k == 8 ? 2 : 3; }
-constexpr int kClaimBatch = 4;  // jobs a producer warp claims with one atomic
-constexpr int kGatherTileW = 32, kFrameTileH = 32;  // generic jobs: 32 x 32, four rows per thread
+#ifndef T360_CLAIM_BATCH
+#define T360_CLAIM_BATCH 1
+#endif
+constexpr int kClaimBatch = T360_CLAIM_BATCH;  // jobs a producer warp claims with one atomic
+constexpr int kGatherTileW = 32, kFrameTileH = 32;  // generic jobs: 32 x 32, four pixels per thread
+// a warp of a 32 x 32 job takes its 32 x 4 pixels in four steps of one 8 x 4 patch each
+constexpr int kTilePatchW = 8, kTilePatchH = 4, kRowsPerPatchStep = 4;
 constexpr int kShareW = 64;  // share jobs: 2 x 4 warps of 32 columns x shareRows(k) rows
 __host__ __device__ constexpr int shareRows(int /*k*/) { return 8; }
 __host__ __device__ constexpr int shareH(int k) { return 4 * shareRows(k); }
@@ -52,13 +66,24 @@ __host__ __device__ constexpr int shareH(int k) { return 4 * shareRows(k); }
 // so their window loads are conflict-free (1.10 wavefronts per load in the bank model, 1.57 at 96 B).  Polar tiles
 // (a warp's pixels drift over many rows) are worst at 192 B (2.9) and want a pitch that is 4 * odd words: 208 B (2.3).
 constexpr int kNumBoxClasses = 3;  // tensor map index: 0 = class 0 / seam, 1 = class 1, 2 = share
-__host__ __device__ constexpr int boxClassOf(int kind) { return kind == kJobShare ? 2 : (kind == kJobClass1 ? 1 : 0); }
+__host__ __device__ constexpr int boxClassOf(int kind) { return (kind == kJobShare || kind == kJobShareStay) ? 2 : (kind == kJobClass1 ? 1 : 0); }
 __host__ __device__ constexpr int stageBoxW(int /*k*/, int cls) { return cls == 2 ? 192 : (cls == 0 ? 208 : 240); }
 __host__ __device__ constexpr int stageBoxH(int k, int cls) {
+#if T360_STAGES == 3
+  return k == 8 ? (cls == 2 ? 80 : (cls == 0 ? 72 : 128)) : (cls == 2 ? 68 : (cls == 0 ? 63 : 96));
+#else
   return k == 8 ? (cls == 2 ? 80 : (cls == 0 ? 72 : 128)) : (cls == 2 ? 72 : (cls == 0 ? 64 : 96));
+#endif
 }
+// Stages of a group's ring (a stage = one box + one record buffer).  Three fit beside the cubic tables if the boxes lose
+// a few rows, but measured slower (64.9 vs 58.1 us per cfg2 frame): they leave the SM only ~3 KB of L1 for the general
+// jobs and the job headers.
+__host__ __device__ constexpr int gatherStages(int k) { return (T360_STAGES == 3 && k != 8) ? 3 : 2; }
 // one stage buffer (TMA destinations need 128-byte alignment; the tail absorbs the over-read of a window's last word)
-__host__ __device__ constexpr int stageBytesOf(int k) { return (stageBoxW(k, 2) * stageBoxH(k, 2) + 64 + 127) & ~127; }
+__host__ __device__ constexpr int stageBytesOf(int k) {
+  const int a = stageBoxW(k, 2) * stageBoxH(k, 2), b = stageBoxW(k, 0) * stageBoxH(k, 0);
+  return ((a > b ? a : b) + 64 + 127) & ~127;
+}
 
 // Weight tables in shared memory.  Phase a = (fracY << 5) | fracX lives in SLOT weightSlotOf(k, a); the K*K int16
 // weights of a slot are K*K/8 16-byte vectors (k >= 4), vector v of copy c at byte
@@ -90,12 +115,13 @@ __host__ __device__ constexpr int weightLanesPerPass(int k) { return k == 2 ? 16
 //                then 32 x uint32, by lane.  uint32 = header of the lane's column: off | column << 27,
 //                off = (row0 - boxY) * 192 + (col0 - boxX) of the column's first pixel; uint4 number b = 8 x 16-bit pixel
 //                records of rows 8b .., row j in half j & 1 of word (j >> 1) & 3: slotField | (d - 1), d = 1 or 2 source
-//                rows between this pixel's window and the previous one's (bit 0 is clear in a column's first record).
+//                rows between this pixel's window and the previous one's (bit 0 is clear in a column's first record);
+//                kJobShareStay: slotField | d, d = 0, 1 or 2 (0 in the first record).
 //                2.25 (R = 16) or 2.5 bytes per pixel.
-//   other jobs   per warp w (rows 4 * w ..): 32 x uint4 by lane, word j = pixel of row 4 * w + j:
-//                off (15 bits) | column << 16 (5 bits) | slotField << 17.  4 bytes per pixel.  Inside a 32-pixel row the
-//                pixels are dealt to lanes (and copies) per row; pixels outside the plane carry a column / row that
-//                fails the bounds check.
+//   other jobs   per warp w (rows 4 * w .. 4 * w + 3): 32 x uint4 by lane, word j = one pixel of the 8 x 4 patch at columns
+//                8 * j ..: off (15 bits) | position << 16 (5 bits: column in patch | row in patch << 3) | slotField << 17.
+//                4 bytes per pixel.  The pixels of a patch are dealt to lanes (and copies) per patch; pixels outside the
+//                plane carry a position that fails the bounds check.
 // General jobs read the full records below.
 __host__ __device__ constexpr int shareWarpRecordBytes(int k) { return shareRows(k) / 8 * 32 * 16 + 32 * 4; }
 __host__ __device__ constexpr int shareJobRecordBytes(int k) { return kGroupWarps * shareWarpRecordBytes(k); }
@@ -138,7 +164,11 @@ struct StagedParams {
   const GatherJob* tiles;  // device list
   int numTiles;
   int* claimCounter;        // two device ints, zero before the first launch (the kernel re-arms them): job scheduler
+  // optional timeline for tuning (T360B200_debugTrace): per consumer group and job four 64-bit words
+  // {wait start, data ready, done (ns, %globaltimer), kind}, kTraceJobsPerGroup jobs per group; nullptr = off
+  unsigned long long* trace;
 };
+constexpr int kTraceJobsPerGroup = 64;
 
 // One tile of the segmented low-pass: output rectangle and the taps to use.
 struct BlurJob {

@@ -197,6 +197,7 @@ class VideoFrameTransform {
         if (l.done) cudaEventDestroy(l.done);
       }
       frameJobs_.tiles.release();
+      trace_.release();
       frameJobs_.claimCounter.release();
       if (frameFork_) cudaEventDestroy(frameFork_);
       if (stream_) cudaStreamDestroy(stream_);
@@ -374,6 +375,15 @@ class VideoFrameTransform {
       cudaGetLastError();
     }
     return false;
+  }
+
+  // tuning aid: a timeline of the consumer groups of the last frame gather (see StagedParams::trace)
+  void enableTrace(bool on) { traceEnabled_ = on; }
+  size_t readTrace(unsigned long long* out, size_t maxWords) {
+    if (!trace_.ptr) return 0;
+    const size_t n = std::min(maxWords, trace_.count);
+    if (cudaMemcpy(out, trace_.ptr, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
+    return n;
   }
 
   bool synchronize() {
@@ -750,7 +760,7 @@ class VideoFrameTransform {
       fp.weightImage = reinterpret_cast<const uint4*>(weightImages_[plan.kernelSize].ptr);
       fp.kernelSize = plan.kernelSize;
       fp.numPlanes = 1;
-      t360::StagedParams jobs{plan.gatherJobs.ptr, plan.numJobs, lane.claimCounter.ptr};
+      t360::StagedParams jobs{plan.gatherJobs.ptr, plan.numJobs, lane.claimCounter.ptr, nullptr};
       CU(t360::launchGatherFrame(fp, jobs, w.maps, numSMs_, s));
     } else {
       const t360::PlaneView& v = w.view;
@@ -765,7 +775,7 @@ class VideoFrameTransform {
     FrameJobList& f = frameJobs_;
     if (f.generation != planGeneration_ || f.numPlanes != numPlanes) {
       std::vector<GatherJob> merged;
-      for (int kind : {t360::kJobGeneral, t360::kJobClass1, t360::kJobShare, t360::kJobClass0})
+      for (int kind : {t360::kJobGeneral, t360::kJobSeam, t360::kJobClass1, t360::kJobShareStay, t360::kJobShare, t360::kJobClass0})
         for (int p = 0; p < numPlanes; ++p)
           for (GatherJob t : work[p].plan->hostJobs) {
             if (((t.outY >> t360::kJobKindShift) & t360::kJobKindMask) != kind) continue;
@@ -790,7 +800,11 @@ class VideoFrameTransform {
     fp.weightImage = reinterpret_cast<const uint4*>(weightImages_[work[0].plan->kernelSize].ptr);
     fp.kernelSize = work[0].plan->kernelSize;
     fp.numPlanes = numPlanes;
-    t360::StagedParams jobs{f.tiles.ptr, f.numTiles, f.claimCounter.ptr};
+    if (traceEnabled_) {
+      trace_.reserve(static_cast<size_t>(numSMs_) * t360::gatherGroups(work[0].plan->kernelSize) * t360::kTraceJobsPerGroup * 4);
+      CU(cudaMemsetAsync(trace_.ptr, 0, trace_.bytes(), s));
+    }
+    t360::StagedParams jobs{f.tiles.ptr, f.numTiles, f.claimCounter.ptr, traceEnabled_ ? trace_.ptr : nullptr};
     CU(t360::launchGatherFrame(fp, jobs, maps, numSMs_, s));
   }
 
@@ -815,6 +829,8 @@ class VideoFrameTransform {
   bool pinHostPlanes_ = false;
   PlaneLane lanes_[kPlaneLanes];
   FrameJobList frameJobs_;
+  DeviceBuffer<unsigned long long> trace_;
+  bool traceEnabled_ = false;
   unsigned long long planGeneration_ = 0;
   cudaEvent_t frameFork_ = nullptr;
   cudaStream_t stream_ = nullptr;
@@ -947,6 +963,10 @@ T360_API int T360B200_lowPassPlaneAsync(VideoFrameTransform* t, const uint8_t* d
   }
 }
 T360_API void T360B200_setPinHostPlanes(VideoFrameTransform* t, int enable) { if (t) t->setPinHostPlanes(enable != 0); }
+T360_API void T360B200_debugTrace(VideoFrameTransform* t, int enable) { if (t) t->enableTrace(enable != 0); }
+T360_API unsigned long long T360B200_debugTraceRead(VideoFrameTransform* t, unsigned long long* out, unsigned long long maxWords) {
+  return t && out ? t->readTrace(out, maxWords) : 0;
+}
 T360_API int T360B200_synchronize(VideoFrameTransform* t) { return t ? t->synchronize() : 0; }
 T360_API void* T360B200_stream(VideoFrameTransform* t) { return t ? t->stream() : nullptr; }
 T360_API unsigned long long T360B200_kernelLaunchCount(void) { return t360::kernelLaunchCount(); }

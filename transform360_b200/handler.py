@@ -70,7 +70,7 @@ def load(path: os.PathLike | None = None):
     global _lib
     if _lib is not None and path is None:
         return _lib
-    p = Path(path) if path else LIB_PATH
+    p = Path(path) if path else Path(os.environ.get("T360B200_LIB") or LIB_PATH)  # T360B200_LIB: experiment builds
     if not p.exists():
         raise FileNotFoundError(f"{p} not found: build it with `python -m transform360_b200.build` (needs nvcc); "
                                 "transform360_b200 has no CPU fallback")
@@ -110,6 +110,10 @@ def load(path: os.PathLike | None = None):
     L.T360B200_lowPassPlaneAsync.argtypes = [vp, vp, vp] + [ci] * 5 + [vp]
     L.T360B200_setPinHostPlanes.restype = None
     L.T360B200_setPinHostPlanes.argtypes = [vp, ci]
+    L.T360B200_debugTrace.restype = None
+    L.T360B200_debugTrace.argtypes = [vp, ci]
+    L.T360B200_debugTraceRead.restype = C.c_ulonglong
+    L.T360B200_debugTraceRead.argtypes = [vp, vp, C.c_ulonglong]
     L.T360B200_synchronize.restype = ci
     L.T360B200_synchronize.argtypes = [vp]
     L.T360B200_stream.restype = vp
@@ -133,7 +137,7 @@ EXPORTED_SYMBOLS = [
     "T360B200_hostPlanGather", "T360B200_weightImage",
     "T360B200_remapTable", "T360B200_transformFramePlaneAsync", "T360B200_transformFrameAsync",
     "T360B200_lowPassPlaneAsync",
-    "T360B200_setPinHostPlanes", "T360B200_synchronize", "T360B200_stream", "T360B200_kernelLaunchCount", "T360B200_planDeviceBytes",
+    "T360B200_setPinHostPlanes", "T360B200_debugTrace", "T360B200_debugTraceRead", "T360B200_synchronize", "T360B200_stream", "T360B200_kernelLaunchCount", "T360B200_planDeviceBytes",
     "T360B200_planTileCounts", "T360B200_deviceCount", "T360B200_version",
 ]
 
@@ -217,6 +221,15 @@ class VideoFrameTransform:
 
     def set_pin_host_planes(self, enable: bool) -> None:
         self._lib.T360B200_setPinHostPlanes(self._h, 1 if enable else 0)
+
+    def debug_trace(self, enable: bool) -> None:
+        self._lib.T360B200_debugTrace(self._h, 1 if enable else 0)
+
+    def read_trace(self, max_groups: int = 148 * 3) -> np.ndarray:
+        """[groups][64 jobs][wait start, ready, done (ns), kind] of the last whole-frame gather (after a synchronize)."""
+        buf = np.zeros(max_groups * 64 * 4, np.uint64)
+        n = int(self._lib.T360B200_debugTraceRead(self._h, buf.ctypes.data, buf.size))
+        return buf[:n].reshape(-1, 64, 4)
 
     def synchronize(self) -> bool:
         return bool(self._lib.T360B200_synchronize(self._h))
