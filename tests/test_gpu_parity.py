@@ -416,3 +416,132 @@ def test_frame_bytes_do_not_depend_on_the_gpu(torch_cuda):
     assert shared, "test must compare at least one frame processed on both GPUs"
     for k in shared:
         assert res[0][k] == res[1][k], f"frame {k} differs between GPUs"
+
+
+# ---- round 2: the paths the bench times, at the sizes it times them -----------------------------------------------
+@pytest.mark.parametrize("name", ["cfg2", "cfg3", "cfg4"])
+def test_full_size_frames_through_the_frame_entry_point(name, golden, torch_cuda):
+    """What bench.py's device-resident leg runs: T360B200_transformFrameAsync on BASELINE configs[1..3] at full size,
+    ALL THREE planes, six frames back to back (programmatic dependent launch, self re-arming scheduler); the first and
+    the last frame completely, and every luma plane of cfg2, against the oracle; frame 0 luma also against the
+    reference's recorded SHA."""
+    torch = torch_cuda
+    from transform360_b200.stream import FrameTransformer, StreamSpec
+    case = FULL[name]
+    ctx, octx = _ctxs(case)
+    spec = StreamSpec(case["inp"][0], case["inp"][1], case["out"][0], case["out"][1])
+    ft = FrameTransformer(ctx, spec)
+    pitch = lambda w: (w + 255) // 256 * 256
+    frames = 6
+    plans = {idx: co.OraclePlan(octx, *spec.plane_dims(p)[:4]) for p, idx in ((0, 0), (1, 1))}
+    st = torch.cuda.Stream()
+    d_in, d_out, srcs = [], [], []
+    for f in range(frames):
+        planes = [co.noise_plane(*spec.plane_dims(p)[:2], plane=p, frame=f) for p in range(3)]
+        srcs.append(planes)
+        d_in.append([_pitched(torch, planes[p], pitch(spec.plane_dims(p)[0])) for p in range(3)])
+        d_out.append([torch.zeros((spec.plane_dims(p)[3], pitch(spec.plane_dims(p)[2])), dtype=torch.uint8, device="cuda") for p in range(3)])
+    dims = [spec.plane_dims(p)[:4] for p in range(3)]
+    torch.cuda.synchronize()
+    for f in range(frames):
+        call = ft.vft.make_frame_call([(t.data_ptr(), t.stride(0)) for t in d_in[f]], [(t.data_ptr(), t.stride(0)) for t in d_out[f]], dims)
+        assert call(st.cuda_stream)
+    st.synchronize()
+    for f in range(frames):
+        for p in range(3):
+            iw, ih, ow, oh, idx = spec.plane_dims(p)
+            got = d_out[f][p][:, :ow].cpu().numpy()
+            if f in (0, frames - 1) or (p == 0 and name == "cfg2"):  # (the oracle takes seconds per 8K plane)
+                want = co.transform_plane(octx, plans[idx], srcs[f][p], ow, oh, map_index=idx)
+                assert np.array_equal(got, want), f"{name} frame {f} plane {p}: {(got != want).sum()} px differ"
+            if f == 0 and p == 0:
+                assert rh.sha16(got) == golden["full"][name]["planes"]["0"]["out_sha"]
+    ft.close()
+
+
+def test_random_contexts_product_vs_oracle(torch_cuda):
+    """Seeded sweep over the whole option space (all layouts both ways, stereo, rotation, off-centre, scale factors, every
+    interpolator, low-pass on and off, odd sizes), small planes, product through the C-ABI against the oracle on the GPU."""
+    from tests.test_host_plan import _random_context
+    rng = np.random.default_rng(2024)
+    checked = refused = 0
+    for i in range(220):
+        ov = _random_context(rng)
+        iw, ih = int(rng.integers(100, 400)) * 2, int(rng.integers(60, 200)) * 2
+        ow, oh = int(rng.integers(30, 160)) * 2 + int(rng.random() < 0.3), int(rng.integers(24, 120)) * 2 + int(rng.random() < 0.3)
+        plane = int(rng.integers(0, 3))
+        idx = 1 if plane else 0
+        ctx, octx = t360.make_context(**ov), rh.default_context(**ov)
+        try:
+            plan = co.OraclePlan(octx, iw, ih, ow, oh)
+        except Exception:
+            plan = None
+        with t360.VideoFrameTransform(ctx) as vft:
+            ok = vft.generateMapForPlane(iw, ih, ow, oh, idx)
+            if plan is None or not ok:
+                assert plan is None and not ok, f"case {i}: product and oracle disagree on whether the plan exists ({ov})"
+                refused += 1
+                continue
+            src = co.noise_plane(iw, ih, plane=plane, frame=i)
+            fill = _prefill(ctx)
+            out = np.full((oh, ow), fill, np.uint8)
+            vft.transform_plane(src, ow, oh, idx, image_plane=plane, out=out)
+        want = co.transform_plane(octx, plan, src, ow, oh, map_index=idx, prefill=fill)
+        assert np.array_equal(out, want), f"case {i}: {(out != want).sum()} px differ ({ov}, {iw}x{ih} -> {ow}x{oh}, plane {plane})"
+        checked += 1
+    assert checked >= 200, (checked, refused)
+
+
+@pytest.mark.parametrize("name", ["cube_cubic", "cube_linear", "cube_lanczos", "rotated", "eac_mono_cubic", "cube_to_equirect", "cube_cubic_odd"])
+def test_streamed_host_path_on_small_planes(name, torch_cuda, monkeypatch):
+    """Large host planes are streamed through the device in row bands (chunked H2D || gather waves || D2H of finished
+    rectangles).  T360B200_PIPELINE_MIN_BYTES=0 sends small planes down that path too: same bytes as the oracle."""
+    monkeypatch.setenv("T360B200_PIPELINE_MIN_BYTES", "0")
+    case = SMALL[name]
+    ctx, octx = _ctxs(case)
+    with t360.VideoFrameTransform(ctx) as vft:
+        for idx in (0, 1):
+            iw, ih, ow, oh, _ = plane_dims(case, idx)
+            assert vft.generateMapForPlane(iw, ih, ow, oh, idx)
+        for plane in (0, 1, 2):
+            iw, ih, ow, oh, idx = plane_dims(case, plane)
+            plan = co.OraclePlan(octx, iw, ih, ow, oh)
+            for frame in (0, 1):
+                src = co.noise_plane(iw, ih, plane=plane, frame=frame, pitch=iw + 5)
+                out = np.full((oh, ow + 3), 0x5A, np.uint8)
+                assert vft.transformFramePlane(src.ctypes.data, out.ctypes.data, iw, ih, src.strides[0], ow, oh, out.strides[0], idx, plane)
+                want = co.transform_plane(octx, plan, np.ascontiguousarray(src[:, :iw]), ow, oh, map_index=idx)
+                assert np.array_equal(out[:, :ow], want), f"{name} plane {plane} frame {frame}: {(out[:, :ow] != want).sum()} px differ"
+                assert (out[:, ow:] == 0x5A).all()
+
+
+def test_concurrent_calls_on_different_planes(torch_cuda):
+    """The reference object is safe for concurrent transformFramePlane calls on different planes after init
+    (VideoFrameTransform.h:150-159: read-only maps); three host threads, one plane each, several frames."""
+    import threading
+    case = SMALL["lp_tiles"]
+    ctx, octx = _ctxs(case)
+    with t360.VideoFrameTransform(ctx) as vft:
+        for idx in (0, 1):
+            iw, ih, ow, oh, _ = plane_dims(case, idx)
+            assert vft.generateMapForPlane(iw, ih, ow, oh, idx)
+        results, errors = {}, []
+
+        def work(plane):
+            try:
+                iw, ih, ow, oh, idx = plane_dims(case, plane)
+                for frame in range(6):
+                    src = co.noise_plane(iw, ih, plane=plane, frame=frame)
+                    results[(plane, frame)] = (src, vft.transform_plane(src, ow, oh, idx, image_plane=plane))
+            except Exception as e:  # noqa: BLE001
+                errors.append(repr(e))
+        threads = [threading.Thread(target=work, args=(p,)) for p in range(3)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        assert not errors, errors
+    for (plane, frame), (src, got) in results.items():
+        iw, ih, ow, oh, idx = plane_dims(case, plane)
+        want = co.transform_plane(octx, co.OraclePlan(octx, iw, ih, ow, oh), src, ow, oh, map_index=idx)
+        assert np.array_equal(got, want), f"plane {plane} frame {frame}"

@@ -7,12 +7,29 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parents[1]
 
 
+USES_ORACLE = re.compile(r"(import|from|include|CDLL|dlopen).*\boracle\b")
+
+
+def _touches_oracle(line: str) -> bool:
+    return bool(USES_ORACLE.search(line)) or "t360o_" in line or "libt360" in line
+
+
+def test_the_guard_itself_fires():
+    """Positive controls: the pattern must catch what it is there to catch (round 1 shipped it with a doubled backslash,
+    which matched nothing)."""
+    for bad in ("from oracle import c_oracle", "import oracle.ref_harness as rh", '#include "../../oracle/t360_oracle.h"',
+                'ctypes.CDLL("oracle/libt360oracle.so")', "x = t360o_remap(1)"):
+        assert _touches_oracle(bad), bad
+    for fine in ("# the oracle checks this in tests/", "coracle = 1", "from .handler import load"):
+        assert not _touches_oracle(fine), fine
+
+
 def test_product_sources_never_mention_the_oracle():
     offenders = []
     for f in (ROOT / "transform360_b200").rglob("*"):
         if f.is_file() and f.suffix in {".py", ".cpp", ".cu", ".cuh", ".h"}:
             for i, line in enumerate(f.read_text(errors="ignore").splitlines(), 1):
-                if re.search(r"(import|from|include|CDLL|dlopen).*\\boracle\\b", line) or "t360o_" in line or "libt360" in line:
+                if _touches_oracle(line):
                     offenders.append(f"{f.relative_to(ROOT)}:{i}: {line.strip()}")
     assert not offenders, "\n".join(offenders)
 

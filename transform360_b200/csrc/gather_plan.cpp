@@ -452,9 +452,16 @@ void buildGatherPlan(const HostPlan& h, bool stageTiles, GatherPlan& g) {
         }
       }
   g.compact.assign(offset / 4, 0u);
+  g.jobNeedRows.assign(g.jobs.size(), h.inH);
   parallelRanges(static_cast<int>(g.jobs.size()), 2048, [&](int begin, int end) {
     for (int i = begin; i < end; ++i) {
       const GatherJob& job = g.jobs[i];
+      {  // the source rows the job reads: what a caller that streams the plane in must have delivered before it runs
+        int rect[4];
+        jobOutputRect(job, k, rect);
+        const Extent e = extentOf(h, rect[0], rect[1], std::min(rect[2], h.mapW), std::min(rect[3], h.mapH));
+        if (e.minR >= 0 && e.maxR + k <= h.inH) g.jobNeedRows[i] = e.maxR + k;
+      }
       const int kind = (job.outY >> kJobKindShift) & kJobKindMask;
       if (kind == kJobGeneral) continue;
       uint32_t* out = g.compact.data() + static_cast<size_t>(job.recordOffset) * 4;

@@ -16,6 +16,7 @@ struct GatherPlan {
   std::vector<int2> records;                     // full records: tile-major, lane-ordered (kernels.cuh)
   std::vector<GatherJob> jobs;                   // general, seam, class 1, share, class 0 (empty: the plan is not staged)
   std::vector<uint32_t> compact;                 // compact records of the staged jobs (GatherJob::recordOffset)
+  std::vector<int> jobNeedRows;                  // per job: source rows [0, n) it reads (inH if a window wraps vertically)
   int numStaged[2] = {}, numSeam = 0, numGeneral = 0, numShare = 0;
   int totalStaged() const { return numSeam + numShare + numStaged[0] + numStaged[1]; }
 };
@@ -23,6 +24,17 @@ struct GatherPlan {
 // stageTiles: cut the plane into jobs for the persistent kernel (kernel size >= 2 and BORDER_WRAP); otherwise only the
 // full records are produced (nearest neighbour, barrel layouts: whole-plane general kernels).
 void buildGatherPlan(const HostPlan& h, bool stageTiles, GatherPlan& g);
+
+// The output rectangle of a job {x0, y0, x1, y1} (clipped to the plane by the caller).
+inline void jobOutputRect(const GatherJob& job, int k, int rect[4]) {
+  const int kind = (job.outY >> kJobKindShift) & kJobKindMask, quad = (job.outX & kJobQuadMask) - 1;
+  rect[0] = job.outX & ~kJobQuadMask;
+  rect[1] = job.outY & kJobRowMask;
+  if (quad >= 0) { rect[0] += 16 * (quad & 1); rect[1] += 16 * (quad >> 1); }
+  const bool share = kind == kJobShare || kind == kJobShareStay;
+  rect[2] = rect[0] + (quad >= 0 ? 16 : (share ? kShareW : kGatherTileW));
+  rect[3] = rect[1] + (quad >= 0 ? 16 : (share ? shareH(k) : kFrameTileH));
+}
 
 // Launch order of a job list that is sorted by kind (general, class 1, share, class 0): the general jobs -- latency-bound
 // reads through L1 that leave the shared-memory pipe idle -- are spread evenly over the first three quarters of the

@@ -84,6 +84,7 @@ struct DevicePlan {
   // gather jobs: share blocks and tiles whose source windows fit a TMA staging box, and the rest
   DeviceBuffer<GatherJob> gatherJobs;  // every job of the plane, sorted by kind (general, seam, class 1, share, class 0)
   std::vector<GatherJob> hostJobs;     // the same list on the host: merged per frame by gatherFrame()
+  std::vector<int> jobNeedRows;        // per host job: the source rows [0, n) it reads (streaming host planes in)
   int numJobs = 0, numStaged[2] = {}, numSeam = 0, numShare = 0, numFallback = 0;
   int totalStaged() const { return numSeam + numShare + numStaged[0] + numStaged[1]; }
   // low-pass: register-resident strip jobs grouped by vertical half-size 1..3, and the rest (large vertical kernels)
@@ -166,6 +167,19 @@ struct FrameJobList {
   DeviceBuffer<int> claimCounter;
 };
 
+// How the synchronous host-pointer call streams a large plane through the GPU: the input arrives in `chunks` row bands;
+// wave c = the gather jobs that only read rows delivered by chunks 0..c; rects[c] = the output rectangles that are
+// complete after wave c (copied back while later chunks are still on their way: PCIe carries both directions at once).
+struct WavePlan {
+  struct Rect { int x, y, w, h; };
+  int chunks = 0;
+  const void* plan = nullptr;  // the DevicePlan it was made for
+  unsigned long long generation = ~0ull;
+  std::vector<int> chunkRowEnd, waveStart;
+  DeviceBuffer<GatherJob> jobs;  // wave-major
+  std::vector<std::vector<Rect>> rects;
+};
+
 constexpr int kPitchAlign = 256;
 inline int alignedPitch(int w) { return (w + kPitchAlign - 1) / kPitchAlign * kPitchAlign; }
 
@@ -177,6 +191,7 @@ class VideoFrameTransform {
     std::memcpy(&ctx_, ctx, sizeof(ctx_));
     const char* e = std::getenv("T360B200_PIN_HOST_PLANES");
     pinHostPlanes_ = e && *e && *e != '0';
+    if (const char* m = std::getenv("T360B200_PIPELINE_MIN_BYTES")) pipelineMinBytes_ = std::atoll(m);  // tests: 0 = always
   }
   void setPinHostPlanes(bool on) { pinHostPlanes_ = on; }
 
@@ -200,6 +215,11 @@ class VideoFrameTransform {
       trace_.release();
       frameJobs_.claimCounter.release();
       if (frameFork_) cudaEventDestroy(frameFork_);
+      for (cudaEvent_t e : chunkIn_) cudaEventDestroy(e);
+      for (cudaEvent_t e : waveDone_) cudaEventDestroy(e);
+      for (WavePlan& w : wavePlans_) w.jobs.release();
+      if (copyIn_) cudaStreamDestroy(copyIn_);
+      if (copyOut_) cudaStreamDestroy(copyOut_);
       if (stream_) cudaStreamDestroy(stream_);
     }
   }
@@ -235,6 +255,14 @@ class VideoFrameTransform {
       const bool inOnDevice = isDevicePointer(in), outOnDevice = isDevicePointer(out);
       const DevicePlan* plan = findPlan(planIndex, imagePlaneIndex);
       if (!plan) return false;
+      if (plan->kernelSize == 0) {  // reference cpp:780-784: message, output untouched, true
+        std::printf("Could not find interpolation algorithm for plane %d", imagePlaneIndex);
+        return true;
+      }
+      // (the reference object may be called from several threads on different planes; here such calls take turns)
+      std::lock_guard<std::mutex> hostLock(hostCallMu_);
+      if (!inOnDevice && !outOnDevice && pipelineEligible(*plan, inW, inH, outW, outH))
+        return transformHostPlanePipelined(*plan, in, out, inW, inH, inPitch, outW, outH, outPitch, planIndex, imagePlaneIndex);
       const uint8_t* dIn = in;
       uint8_t* dOut = out;
       int dInPitch = inPitch, dOutPitch = outPitch;
@@ -272,6 +300,130 @@ class VideoFrameTransform {
       std::printf("Could not transform the plane %d. Error: %s\n", imagePlaneIndex, ex.what());
     }
     return false;
+  }
+
+  // ---- streaming a large host plane through the device -------------------------------------------------------
+  bool pipelineEligible(const DevicePlan& plan, int inW, int inH, int outW, int outH) const {
+    return plan.totalStaged() > 0 && !plan.transparent && !plan.lowPass && !plan.resizeNeeded && inW == plan.inW && inH == plan.inH &&
+           outW == plan.outW && outH == plan.outH && static_cast<long long>(inW) * inH >= pipelineMinBytes_ && inH >= 64;
+  }
+
+  WavePlan& wavePlanFor(const DevicePlan& plan, int planIndex, int chunks) {
+    WavePlan& w = wavePlans_[planIndex ? 1 : 0];
+    if (w.plan == &plan && w.chunks == chunks && w.generation == planGeneration_) return w;
+    w.chunks = chunks;
+    w.plan = &plan;
+    w.generation = planGeneration_;
+    const int rowsPer = ((plan.inH + chunks - 1) / chunks + 7) & ~7;
+    w.chunkRowEnd.assign(chunks, plan.inH);
+    for (int c = 0; c < chunks; ++c) w.chunkRowEnd[c] = std::min(plan.inH, (c + 1) * rowsPer);
+    auto waveOf = [&](int needRows) {
+      int c = 0;
+      while (c + 1 < chunks && w.chunkRowEnd[c] < needRows) ++c;
+      return c;
+    };
+    std::vector<std::vector<GatherJob>> byWave(chunks);
+    // which output rectangles are complete after which wave: 32-row bands x column blocks that no job straddles
+    int blocks = 1;
+    for (int nb : {4, 3, 2})
+      if (plan.mapW % (nb * t360::kShareW) == 0) { blocks = nb; break; }
+    const int blockW = plan.mapW / blocks, bands = (plan.mapH + 31) / 32;
+    std::vector<int> complete(static_cast<size_t>(bands) * blocks, 0);
+    for (size_t i = 0; i < plan.hostJobs.size(); ++i) {
+      const int c = waveOf(plan.jobNeedRows[i]);
+      byWave[c].push_back(plan.hostJobs[i]);
+      int rect[4];
+      t360::jobOutputRect(plan.hostJobs[i], plan.kernelSize, rect);
+      for (int band = rect[1] / 32; band <= (std::min(rect[3], plan.mapH) - 1) / 32; ++band) {
+        int& slot = complete[static_cast<size_t>(band) * blocks + rect[0] / blockW];
+        slot = std::max(slot, c);
+      }
+    }
+    std::vector<GatherJob> all;
+    w.waveStart.assign(chunks + 1, 0);
+    for (int c = 0; c < chunks; ++c) {
+      t360::spreadGeneralJobs(byWave[c]);
+      w.waveStart[c] = static_cast<int>(all.size());
+      all.insert(all.end(), byWave[c].begin(), byWave[c].end());
+    }
+    w.waveStart[chunks] = static_cast<int>(all.size());
+    w.jobs.reserve(all.size());
+    CU(cudaMemcpy(w.jobs.ptr, all.data(), all.size() * sizeof(GatherJob), cudaMemcpyHostToDevice));
+    w.rects.assign(chunks, {});
+    for (int b = 0; b < blocks; ++b)
+      for (int band = 0; band < bands;) {  // vertically adjacent bands of a block that complete together: one copy
+        const int c = complete[static_cast<size_t>(band) * blocks + b];
+        int end = band + 1;
+        while (end < bands && complete[static_cast<size_t>(end) * blocks + b] == c) ++end;
+        w.rects[c].push_back(WavePlan::Rect{b * blockW, band * 32, blockW, std::min(plan.mapH, end * 32) - band * 32});
+        band = end;
+      }
+    return w;
+  }
+
+  // reference transformFramePlane for large host planes (same result as the plain path): chunked H2D || gather || D2H
+  bool transformHostPlanePipelined(const DevicePlan& plan, uint8_t* in, uint8_t* out, int inW, int inH, int inPitch, int outW, int outH,
+                                   int outPitch, int planIndex, int imagePlaneIndex) {
+    const long long bytes = static_cast<long long>(inW) * inH;
+    const int chunks = static_cast<int>(std::min<long long>(8, std::max<long long>(2, bytes / (3ll << 20))));
+    WavePlan& w = wavePlanFor(plan, planIndex, chunks);
+    if (!copyIn_) {
+      CU(cudaStreamCreateWithFlags(&copyIn_, cudaStreamNonBlocking));
+      CU(cudaStreamCreateWithFlags(&copyOut_, cudaStreamNonBlocking));
+    }
+    while (static_cast<int>(chunkIn_.size()) < chunks) {
+      cudaEvent_t a = nullptr, b = nullptr;
+      CU(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+      chunkIn_.push_back(a);
+      CU(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+      waveDone_.push_back(b);
+    }
+    pinIfRecurring(in, static_cast<size_t>(inPitch) * (inH - 1) + inW);
+    pinIfRecurring(out, static_cast<size_t>(outPitch) * (outH - 1) + outW);
+    const int dInPitch = alignedPitch(inW), dOutPitch = alignedPitch(outW);
+    stagingIn_.reserve(static_cast<size_t>(dInPitch) * inH + 64);
+    stagingOut_.reserve(static_cast<size_t>(dOutPitch) * outH + 64);
+    GatherWork work;
+    if (!prepareGather(plan, stagingIn_.ptr, stagingOut_.ptr, inW, inH, dInPitch, outW, outH, dOutPitch, stream_, imagePlaneIndex, lanes_[0], work))
+      return false;
+    if (!work.staged) {  // the plane cannot be described to the TMA unit after all: plain path
+      CU(cudaMemcpy2DAsync(stagingIn_.ptr, dInPitch, in, inPitch, inW, inH, cudaMemcpyHostToDevice, stream_));
+      gatherPlane(work, lanes_[0], stream_);
+      CU(cudaMemcpy2DAsync(out, outPitch, stagingOut_.ptr, dOutPitch, outW, outH, cudaMemcpyDeviceToHost, stream_));
+      CU(cudaStreamSynchronize(stream_));
+      return true;
+    }
+    armScheduler(lanes_[0].claimCounter, stream_);
+    t360::FrameGatherParams fp{};
+    fp.plane[0] = work.view;
+    fp.weightImage = reinterpret_cast<const uint4*>(weightImages_[plan.kernelSize].ptr);
+    fp.kernelSize = plan.kernelSize;
+    fp.numPlanes = 1;
+    bool copiedOut = false;
+    for (int c = 0; c < chunks; ++c) {
+      const int r0 = c ? w.chunkRowEnd[c - 1] : 0, r1 = w.chunkRowEnd[c];
+      if (r1 > r0)
+        CU(cudaMemcpy2DAsync(stagingIn_.ptr + static_cast<size_t>(r0) * dInPitch, dInPitch, in + static_cast<size_t>(r0) * inPitch, inPitch, inW,
+                             r1 - r0, cudaMemcpyHostToDevice, copyIn_));
+      CU(cudaEventRecord(chunkIn_[c], copyIn_));
+      CU(cudaStreamWaitEvent(stream_, chunkIn_[c], 0));
+      const int n = w.waveStart[c + 1] - w.waveStart[c];
+      if (n > 0) {
+        t360::StagedParams jobs{w.jobs.ptr + w.waveStart[c], n, lanes_[0].claimCounter.ptr, nullptr};
+        CU(t360::launchGatherFrame(fp, jobs, work.maps, numSMs_, stream_));
+      }
+      if (!w.rects[c].empty()) {
+        CU(cudaEventRecord(waveDone_[c], stream_));
+        CU(cudaStreamWaitEvent(copyOut_, waveDone_[c], 0));
+        for (const WavePlan::Rect& r : w.rects[c])
+          CU(cudaMemcpy2DAsync(out + static_cast<size_t>(r.y) * outPitch + r.x, outPitch, stagingOut_.ptr + static_cast<size_t>(r.y) * dOutPitch + r.x,
+                               dOutPitch, r.w, r.h, cudaMemcpyDeviceToHost, copyOut_));
+        copiedOut = true;
+      }
+    }
+    CU(cudaStreamSynchronize(stream_));
+    if (copiedOut) CU(cudaStreamSynchronize(copyOut_));
+    return true;
   }
 
   // device to device, asynchronous
@@ -517,6 +669,7 @@ class VideoFrameTransform {
         CU(cudaMemcpy(d.records.ptr, g.compact.data(), g.compact.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
       }
       d.hostJobs = std::move(g.jobs);
+      d.jobNeedRows = std::move(g.jobNeedRows);
     }
     d.lowPass = ctx_.enable_low_pass_filter != 0;
     if (d.lowPass) buildBlurJobs(h, d);
@@ -823,6 +976,11 @@ class VideoFrameTransform {
   DeviceBuffer<int16_t> weights_[9];       // OpenCV's tables [1024][k][k] (general kernels), by kernel size
   DeviceBuffer<uint8_t> weightImages_[9];  // their shared-memory images for the frame kernel
   DeviceBuffer<uint8_t> stagingIn_, stagingOut_;
+  std::mutex hostCallMu_;  // the synchronous host-pointer path shares the staging planes and the streams: one call at a time
+  cudaStream_t copyIn_ = nullptr, copyOut_ = nullptr;
+  std::vector<cudaEvent_t> chunkIn_, waveDone_;
+  WavePlan wavePlans_[2];  // plan index 0 / 1
+  long long pipelineMinBytes_ = 6ll << 20;
   // opt-in page-locking of recurring pageable caller planes (ffmpeg recycles its frame pool): see pinIfRecurring()
   struct HostRange { uintptr_t base; size_t bytes; int seen; bool pinned; };
   std::vector<HostRange> hostRanges_;
