@@ -177,7 +177,7 @@ def run_reference_arm(args, cfg, rank):
         "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
         "config": {"workload": f"{args.config}: {cfg['desc']}", "engine": "reference CPU path on host cores"},
         "cpu_baseline": {"value": round(v, 2), "unit": "Mpx/s", "cores": cores, "kind": kind, "sample": sample,
-                         "best_ms_per_step": round(1e3 * min(times), 3)},
+                         "best_ms_per_step": round(1e3 * min(times), 3), "median_ms_per_step": round(1e3 * statistics.median(times), 3)},
         "e2e": {"value": round(v, 2), "unit": "Mpx/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -185,6 +185,175 @@ def run_reference_arm(args, cfg, rank):
 
 
 # ------------------------------------------------------------------------------------------------------
+class DeviceFrames:
+    """Synthetic frames of one config resident in HBM: a ring of input frames larger than L2 and two output frames."""
+
+    def __init__(self, spec, dev, rank, world, synth):
+        self.spec = spec
+        frame_bytes = spec.input_pixels_per_frame()
+        self.ring = max(4, -(-200_000_000 // frame_bytes))
+        pitch = lambda w: (w + 255) // 256 * 256
+        self.d_in, self.d_out = [], []
+        for f in range(self.ring):
+            gframe = rank + f * world  # global frame index handled by this rank (round-robin sharding)
+            self.d_in.append([synth.noise_plane_torch(*spec.plane_dims(p)[:2], plane=p, frame=gframe, device=dev, pitch=pitch(spec.plane_dims(p)[0]))
+                              for p in range(3)])
+        import torch
+        for f in range(2):
+            self.d_out.append([torch.zeros((spec.plane_dims(p)[3], pitch(spec.plane_dims(p)[2])), dtype=torch.uint8, device=dev) for p in range(3)])
+        self.in_args = [[(t.data_ptr(), t.stride(0)) for t in fr] for fr in self.d_in]
+        self.out_args = [[(t.data_ptr(), t.stride(0)) for t in fr] for fr in self.d_out]
+
+
+def measure_config(name, cfg, ctx, spec, K, warmup, dev, rank, world, barrier, want_e2e, e2e_steps):
+    """Device-resident leg, roofline leg (the frame gather kernel alone: isolated launches and a back-to-back stream) and,
+    optionally, the end-to-end leg of one config.  Returns a dict of raw measurements (this rank's; times are reduced
+    with MAX over ranks by the caller where the contract asks for it)."""
+    import torch
+    import transform360_b200 as t360
+    from transform360_b200 import synth
+    from transform360_b200.stream import FrameTransformer
+    t_plan = time.perf_counter()
+    ft = FrameTransformer(ctx, spec)
+    plan_seconds = time.perf_counter() - t_plan
+    fr = DeviceFrames(spec, dev, rank, world, synth)
+    ring = fr.ring
+    tstream = torch.cuda.Stream(device=dev)  # a real (non-default) stream: the events below bracket the library's kernels
+    stream = tstream.cuda_stream
+    assert stream != 0
+    calls = [[ft.frame_call(fr.in_args[i], fr.out_args[o]) for o in range(2)] for i in range(ring)]
+
+    def run(call_table, n, first=0):
+        for i in range(first, first + n):
+            if not call_table[i % ring][i % 2](stream):
+                raise RuntimeError("T360B200_transformFrameAsync failed")
+
+    torch.cuda.synchronize()  # the ring was filled on torch's default stream
+    run(calls, warmup)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = t360.kernel_launch_count()
+    e0.record(tstream)
+    run(calls, K)
+    e1.record(tstream)
+    barrier()
+    out = {"ms_total": e0.elapsed_time(e1), "launches": t360.kernel_launch_count() - launches0, "ring": ring,
+           "plan_seconds": plan_seconds, "tiles": [list(ft.vft.plan_tile_counts(0)), list(ft.vft.plan_tile_counts(1))]}
+
+    # ---- the dominant kernel alone: with the low-pass enabled a frame call also launches the blur kernels, so the gather
+    # is timed through a second transform with the same geometry and the low-pass switched off (same jobs, same records)
+    ft_gather = ft
+    if cfg["ov"].get("enable_low_pass_filter"):
+        ft_gather = FrameTransformer(t360.make_context(**dict(cfg["ov"], enable_low_pass_filter=0)), spec)
+    gcalls = [[ft_gather.frame_call(fr.in_args[i], fr.out_args[o]) for o in range(2)] for i in range(ring)]
+    run(gcalls, 3)
+    barrier()
+    Kl = min(K, 200)
+    gl0 = t360.kernel_launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(Kl)]
+    for i in range(Kl):
+        ev[i][0].record(tstream)
+        run(gcalls, 1, i)
+        ev[i][1].record(tstream)
+    barrier()
+    out["gather_launches_per_call"] = (t360.kernel_launch_count() - gl0) / Kl
+    out["gather_ms"] = [a.elapsed_time(b) for a, b in ev]
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record(tstream)
+    run(gcalls, Kl)
+    g1.record(tstream)
+    barrier()
+    out["gather_streamed_ms"] = g0.elapsed_time(g1) / Kl
+
+    # ---- a frame every rank has in common (global frame 0), for the cross-rank identity check
+    common = [synth.noise_plane_torch(*spec.plane_dims(p)[:2], plane=p, frame=0, device=dev, pitch=fr.d_in[0][p].stride(0)) for p in range(3)]
+    torch.cuda.synchronize()
+    if not ft.frame_call([(t.data_ptr(), t.stride(0)) for t in common], fr.out_args[0])(stream):
+        raise RuntimeError("T360B200_transformFrameAsync failed")
+    torch.cuda.synchronize()
+    import hashlib
+    hsh = hashlib.sha256()
+    for p in range(3):
+        hsh.update(fr.d_out[0][p][:, :spec.plane_dims(p)[2]].contiguous().cpu().numpy().tobytes())
+    out["common_frame_sha"] = hsh.hexdigest()[:16]
+
+    # ---- end to end through the reference-facing C-ABI with pinned host planes ------------------------------------
+    if want_e2e:
+        Ke = e2e_steps
+        h_ring = 2
+        h_in = [[torch.empty((spec.plane_dims(p)[1], spec.plane_dims(p)[0]), dtype=torch.uint8).pin_memory() for p in range(3)]
+                for _ in range(h_ring)]
+        for f in range(h_ring):
+            for p in range(3):
+                h_in[f][p].copy_(fr.d_in[f][p][:, :spec.plane_dims(p)[0]].cpu())
+        h_out = [[torch.empty((spec.plane_dims(p)[3], spec.plane_dims(p)[2]), dtype=torch.uint8).pin_memory() for p in range(3)]
+                 for _ in range(h_ring)]
+        hin_args = [[(t.data_ptr(), t.stride(0)) for t in f] for f in h_in]
+        hout_args = [[(t.data_ptr(), t.stride(0)) for t in f] for f in h_out]
+        lib_stream = torch.cuda.ExternalStream(ft.vft.stream, device=dev)
+        for i in range(3):
+            ft.transform_frame_host(hin_args[i % h_ring], hout_args[i % h_ring])
+        barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        per_step = []
+        w0 = time.perf_counter()
+        s0.record(lib_stream)
+        for i in range(Ke):
+            t0 = time.perf_counter()
+            ft.transform_frame_host(hin_args[i % h_ring], hout_args[i % h_ring])  # synchronous: output complete on return
+            per_step.append((time.perf_counter() - t0) * 1e3)
+        s1.record(lib_stream)
+        barrier()
+        wall_ms = (time.perf_counter() - w0) * 1e3
+        ms_e2e = s0.elapsed_time(s1)
+        if ms_e2e <= 0:
+            ms_e2e = wall_ms
+        # sanity: the host path and the device path produce the same bytes for the same frame
+        ft.transform_frame_host(hin_args[0], hout_args[0])
+        run(calls, 1, 0)
+        torch.cuda.synchronize()
+        same = all(torch.equal(h_out[0][p], fr.d_out[0][p][:, :spec.plane_dims(p)[2]].cpu()) for p in range(3))
+        out["e2e"] = {"ms_total": ms_e2e, "wall_ms": wall_ms, "steps": Ke, "median_ms": statistics.median(per_step), "best_ms": min(per_step),
+                      "matches_device_leg": bool(same)}
+    ft.close()
+    if ft_gather is not ft:
+        ft_gather.close()
+    del fr
+    torch.cuda.empty_cache()
+    return out
+
+
+def kernel_size_of(cfg):
+    return {1: 2, 2: 4, 4: 8}.get(cfg["ov"]["interpolation_alg"], 0)
+
+
+def roofline_of(name, cfg, spec, m, ms_per_step):
+    peak, peak_src = measured_hbm_peak()
+    in_px, out_px = spec.input_pixels_per_frame(), spec.output_pixels_per_frame()
+    gather_bytes = in_px + out_px  # every input byte read once, every output byte written once (SURVEY.md 8d)
+    avg = statistics.mean(m["gather_ms"])
+    achieved = gather_bytes / (avg * 1e-3) / 1e9
+    traffic = None
+    tp = ROOT / "profiles" / "traffic.json"
+    if tp.exists():
+        try:
+            traffic = json.loads(tp.read_text()).get(name, {}).get("frame_gather_dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    k = kernel_size_of(cfg)
+    return {"bound": "hbm", "kernel": f"gatherFrameKernel<{k}> (Y+U+V jobs of one frame, one persistent warp-specialised launch)",
+            "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
+            "traffic": traffic, "algorithmic_bytes_per_launch": gather_bytes, "avg_launch_ms": round(avg, 5),
+            "median_launch_ms": round(statistics.median(m["gather_ms"]), 5),
+            "streamed_launch_ms": round(m["gather_streamed_ms"], 5),
+            "frac_streamed": round(gather_bytes / (m["gather_streamed_ms"] * 1e-3) / 1e9 / peak, 4),
+            "share_of_step": round(m["gather_streamed_ms"] / ms_per_step, 3),
+            "launches_per_timed_call": m["gather_launches_per_call"],
+            "read_only_frac": round(in_px / (avg * 1e-3) / 1e9 / peak, 4), "peak_source": peak_src,
+            "timing": f"{len(m['gather_ms'])} launches each bracketed by CUDA events on the launch stream (avg/median_launch_ms, frac), and the "
+                      f"same launches back to back between two events (streamed_launch_ms, frac_streamed, share_of_step); inputs from the >L2 ring"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -195,7 +364,9 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the host-pointer leg (default min(steps, 100))")
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
+    ap.add_argument("--skip-other-configs", action="store_true", help="do not add the short cfg3 / cfg4 legs (N=1 only)")
     ap.add_argument("--cpu-steps", type=int, default=12)
+    ap.add_argument("--no-numa-bind", action="store_true")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
     rank = int(os.environ.get("RANK", "0"))
@@ -207,11 +378,15 @@ def main():
         run_reference_arm(args, cfg, rank)
         return
 
-    import numpy as np
+    # Page-locked frame buffers must live on the GPU's own NUMA node (20 vs 55 GB/s H2D on these 2-socket boxes): bind
+    # the rank to that node's CPUs before anything is allocated; the original affinity comes back for the CPU baseline.
+    from transform360_b200.stream import bind_to_gpu_numa_node
+    affinity0 = os.sched_getaffinity(0)
+    numa = None if args.no_numa_bind else bind_to_gpu_numa_node(local_rank)
+
     import torch
     import transform360_b200 as t360
-    from transform360_b200 import synth
-    from transform360_b200.stream import FrameTransformer, StreamSpec, broadcast_parameters
+    from transform360_b200.stream import StreamSpec, broadcast_parameters
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the product has no CPU fallback; use --impl reference for the CPU arm)")
@@ -223,140 +398,63 @@ def main():
     if world != args.gpus and rank == 0:
         print(f"bench.py: note: WORLD_SIZE={world} but --gpus {args.gpus}; using WORLD_SIZE", file=sys.stderr)
 
-    # ---- parameters: rank 0 decides, one NCCL broadcast of 112 + 28 bytes (the path's only collective) -----
-    ctx = spec = None
-    if rank == 0:
-        ctx = t360.make_context(**cfg["ov"])
-        spec = StreamSpec(cfg["inp"][0], cfg["inp"][1], cfg["out"][0], cfg["out"][1])
-    ctx, spec = broadcast_parameters(ctx, spec, rank, world, device=dev)
-    t_plan = time.perf_counter()
-    ft = FrameTransformer(ctx, spec)
-    plan_seconds = time.perf_counter() - t_plan
-    in_px, out_px = spec.input_pixels_per_frame(), spec.output_pixels_per_frame()
-
-    # ---- device-resident ring of frames, larger than L2 (126 MB) so that every step streams from HBM ----------
-    frame_bytes = in_px
-    ring = max(4, -(-200_000_000 // frame_bytes))
-    pitch = lambda w: (w + 255) // 256 * 256
-    d_in, d_out = [], []
-    for f in range(ring):
-        gframe = rank + f * world  # global frame index handled by this rank (round-robin sharding)
-        planes = []
-        for p in range(3):
-            iw, ih = spec.plane_dims(p)[:2]
-            planes.append(synth.noise_plane_torch(iw, ih, plane=p, frame=gframe, device=dev, pitch=pitch(iw)))
-        d_in.append(planes)
-    for f in range(2):
-        d_out.append([torch.zeros((spec.plane_dims(p)[3], pitch(spec.plane_dims(p)[2])), dtype=torch.uint8, device=dev) for p in range(3)])
-    in_args = [[(t.data_ptr(), t.stride(0)) for t in fr] for fr in d_in]
-    out_args = [[(t.data_ptr(), t.stride(0)) for t in fr] for fr in d_out]
-    # a real (non-default) stream: handle 0 would make the library fall back to its own stream and the events
-    # below would not bracket the kernels
-    tstream = torch.cuda.Stream(device=dev)
-    stream = tstream.cuda_stream
-    assert stream != 0
-
     def barrier():
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
             torch.cuda.synchronize()
 
-    # one prebuilt whole-frame call per (input ring slot, output slot): T360B200_transformFrameAsync runs the low-pass
-    # of the three planes side by side (chroma on the transform's internal lanes) and gathers them in one launch
-    frame_calls = [[ft.frame_call(in_args[i], out_args[o]) for o in range(2)] for i in range(ring)]
-
-    def step_device(i):
-        if not frame_calls[i % ring][i % 2](stream):
-            raise RuntimeError("T360B200_transformFrameAsync failed")
-
-    sampler = ClockSampler(local_rank) if rank == 0 else None
-    torch.cuda.synchronize()  # the ring was filled on torch's default stream
-    for i in range(args.warmup):
-        step_device(i)
-    barrier()
-    K = args.steps
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    launches0 = t360.kernel_launch_count()
-    e0.record(tstream)
-    for i in range(K):
-        step_device(i)
-    e1.record(tstream)
-    barrier()
-    launches = t360.kernel_launch_count() - launches0
-    ms_total = e0.elapsed_time(e1)
-    t_max = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t_max, op=dist.ReduceOp.MAX)
-    ms_total_max = float(t_max.item())
-    value = in_px * K * world / (ms_total_max * 1e-3) / 1e6
-
-    # ---- kernel leg for the roofline: the dominant kernel of the step is the persistent gather that takes the tiles
-    # of all three planes of a frame in ONE launch.  Each launch is bracketed by CUDA events on its stream.  With the
-    # low-pass enabled a frame call also launches the blur kernels, so the gather is timed through a second transform
-    # with the same geometry and the low-pass switched off (same tiles, same records, same kernel).
-    ft_gather = ft
-    if cfg["ov"].get("enable_low_pass_filter"):
-        ctx_g = t360.make_context(**dict(cfg["ov"], enable_low_pass_filter=0))
-        ft_gather = FrameTransformer(ctx_g, spec)
-    gather_calls = [[ft_gather.frame_call(in_args[i], out_args[o]) for o in range(2)] for i in range(ring)]
-    for i in range(3):
-        gather_calls[i % ring][i % 2](stream)
-    barrier()
-    Kl = min(K, 200)
-    gl0 = t360.kernel_launch_count()
-    gather_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(Kl)]
-    for i in range(Kl):
-        gather_ev[i][0].record(tstream)
-        if not gather_calls[i % ring][i % 2](stream):
-            raise RuntimeError("frame gather failed")
-        gather_ev[i][1].record(tstream)
-    barrier()
-    gather_launches_per_call = (t360.kernel_launch_count() - gl0) / Kl
-    gather_ms = [a.elapsed_time(b) for a, b in gather_ev]
-
-    # ---- end to end through the reference-facing C-ABI with pinned host planes ------------------------------------
-    e2e = None
-    if not args.skip_e2e:
-        Ke = args.e2e_steps or min(K, 100)
-        h_ring = 2
-        h_in = [[torch.empty((spec.plane_dims(p)[1], spec.plane_dims(p)[0]), dtype=torch.uint8).pin_memory() for p in range(3)]
-                for _ in range(h_ring)]
-        for f in range(h_ring):
-            for p in range(3):
-                h_in[f][p].copy_(d_in[f][p][:, :spec.plane_dims(p)[0]].cpu())
-        h_out = [[torch.empty((spec.plane_dims(p)[3], spec.plane_dims(p)[2]), dtype=torch.uint8).pin_memory() for p in range(3)]
-                 for _ in range(h_ring)]
-        hin_args = [[(t.data_ptr(), t.stride(0)) for t in fr] for fr in h_in]
-        hout_args = [[(t.data_ptr(), t.stride(0)) for t in fr] for fr in h_out]
-        lib_stream = torch.cuda.ExternalStream(ft.vft.stream, device=dev)
-        for i in range(3):
-            ft.transform_frame_host(hin_args[i % h_ring], hout_args[i % h_ring])
-        barrier()
-        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        w0 = time.perf_counter()
-        s0.record(lib_stream)
-        for i in range(Ke):
-            ft.transform_frame_host(hin_args[i % h_ring], hout_args[i % h_ring])
-        s1.record(lib_stream)
-        barrier()
-        wall_ms = (time.perf_counter() - w0) * 1e3
-        ms_e2e = max(s0.elapsed_time(s1), 0.0)
-        ms_e2e = max(ms_e2e, wall_ms * 0.5) if ms_e2e <= 0 else ms_e2e
-        t2 = torch.tensor([ms_e2e, wall_ms], dtype=torch.float64, device=dev)
+    def max_over_ranks(values):
+        t = torch.tensor(values, dtype=torch.float64, device=dev)
         if world > 1:
-            dist.all_reduce(t2, op=dist.ReduceOp.MAX)
-        ms_e2e, wall_ms = float(t2[0].item()), float(t2[1].item())
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(v) for v in t.tolist()]
+
+    # ---- parameters: rank 0 decides, one NCCL broadcast of 112 + 28 bytes (the path's only collective) -----
+    ctx = spec = None
+    if rank == 0:
+        ctx = t360.make_context(**cfg["ov"])
+        spec = StreamSpec(cfg["inp"][0], cfg["inp"][1], cfg["out"][0], cfg["out"][1])
+    ctx, spec = broadcast_parameters(ctx, spec, rank, world, device=dev)
+    in_px, out_px = spec.input_pixels_per_frame(), spec.output_pixels_per_frame()
+    K = args.steps
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    m = measure_config(args.config, cfg, ctx, spec, K, args.warmup, dev, rank, world, barrier, not args.skip_e2e,
+                       args.e2e_steps or min(K, 100))
+    (ms_total_max,) = max_over_ranks([m["ms_total"]])
+    ms_per_step = ms_total_max / K
+    value = in_px * K * world / (ms_total_max * 1e-3) / 1e6
+    e2e = None
+    if "e2e" in m:
+        ms_e2e, wall_ms, med, best = max_over_ranks([m["e2e"]["ms_total"], m["e2e"]["wall_ms"], m["e2e"]["median_ms"], m["e2e"]["best_ms"]])
+        Ke = m["e2e"]["steps"]
         e2e = {"value": round(in_px * Ke * world / (ms_e2e * 1e-3) / 1e6, 1), "unit": "Mpx/s", "steps": Ke,
                "ms_per_step": round(ms_e2e / Ke, 4), "wall_ms_per_step": round(wall_ms / Ke, 4),
+               "median_ms_per_step": round(med, 4), "best_ms_per_step": round(best, 4),
                "h2d_bytes_per_step": in_px, "d2h_bytes_per_step": out_px,
-               "api": "VideoFrameTransform_transformFramePlane x3 planes, pinned host planes, synchronous"}
-        # sanity: the host path and the device path produce the same bytes for the same frame
-        ft.transform_frame_host(hin_args[0], hout_args[0])
-        step_device(0)
-        torch.cuda.synchronize()
-        same = all(torch.equal(h_out[0][p], d_out[0][p][:, :spec.plane_dims(p)[2]].cpu()) for p in range(3))
-        e2e["matches_device_leg"] = bool(same)
+               "api": "VideoFrameTransform_transformFramePlane x3 planes, pinned host planes (on the GPU's NUMA node), synchronous; large "
+                      "planes are streamed: chunked H2D || gather waves || D2H of finished rectangles",
+               "matches_device_leg": m["e2e"]["matches_device_leg"]}
+    cross_rank_identical = None
+    if world > 1:
+        shas = [None] * world
+        dist.all_gather_object(shas, m["common_frame_sha"])
+        cross_rank_identical = len(set(shas)) == 1
+
+    # ---- the other BASELINE configs, short legs in the same process (N = 1 only) -------------------------------------
+    others = {}
+    if world == 1 and not args.skip_other_configs:
+        for name in ("cfg3", "cfg4"):
+            if name == args.config:
+                continue
+            c2 = CONFIGS[name]
+            spec2 = StreamSpec(c2["inp"][0], c2["inp"][1], c2["out"][0], c2["out"][1])
+            K2 = min(K, 60)
+            m2 = measure_config(name, c2, t360.make_context(**c2["ov"]), spec2, K2, 3, dev, 0, 1, barrier, False, 0)
+            ms2 = m2["ms_total"] / K2
+            others[name] = {"workload": c2["desc"], "steps": K2, "ms_per_step": round(ms2, 5),
+                            "value": round(spec2.input_pixels_per_frame() / (ms2 * 1e-3) / 1e6, 1), "unit": "Mpx/s",
+                            "gpu_launches_per_step": m2["launches"] / K2, "roofline": roofline_of(name, c2, spec2, m2, ms2)}
     clocks = sampler.stop() if sampler else None
 
     if rank != 0:
@@ -364,46 +462,27 @@ def main():
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel (frame gather) -------------------------------------------------------------
-    peak, peak_src = measured_hbm_peak()
-    gather_bytes = in_px + out_px  # every input byte read once, every output byte written once
-    gather_avg_ms = statistics.mean(gather_ms)
-    achieved = gather_bytes / (gather_avg_ms * 1e-3) / 1e9
-    traffic = None
-    tp = ROOT / "profiles" / "traffic.json"
-    if tp.exists():
-        try:
-            traffic = json.loads(tp.read_text()).get(args.config, {}).get("frame_gather_dram_bytes_per_launch")
-        except Exception:
-            traffic = None
-    ksize = {1: 2, 2: 4, 4: 8}.get(cfg["ov"]["interpolation_alg"], 0)
-    roofline = {"bound": "hbm", "kernel": f"gatherFrameKernel<{ksize}> (Y+U+V tiles of one frame, one persistent launch)",
-                "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                "traffic": traffic, "algorithmic_bytes_per_launch": gather_bytes, "avg_launch_ms": round(gather_avg_ms, 5),
-                "median_launch_ms": round(statistics.median(gather_ms), 5),
-                "share_of_step": round(gather_avg_ms / (ms_total_max / K), 3),
-                "launches_per_timed_call": gather_launches_per_call,
-                "read_only_frac": round(in_px / (gather_avg_ms * 1e-3) / 1e9 / peak, 4), "peak_source": peak_src,
-                "timing": f"{len(gather_ms)} launches, each bracketed by CUDA events on the launch stream, inputs from the >L2 ring"}
-
     cpu_baseline = None
     if world == 1 and not args.skip_cpu_baseline:
+        os.sched_setaffinity(0, affinity0)  # the CPU path gets every core again
         times, kind, cores, sample = reference_cpu_run(cfg, args.cpu_steps, 2, budget_s=30.0)
         cpu_baseline = {"value": round(in_px * len(times) / sum(times) / 1e6, 1), "unit": "Mpx/s", "cores": cores, "kind": kind,
-                        "sample": sample, "best": round(in_px / min(times) / 1e6, 1)}
+                        "sample": sample, "median": round(in_px / statistics.median(times) / 1e6, 1), "best": round(in_px / min(times) / 1e6, 1)}
 
     line = {
         "metric": METRIC, "value": round(value, 1), "unit": "Mpx/s", "n_gpus": world, "steps": K, "warmup": args.warmup,
-        "ms_per_step": round(ms_total_max / K, 5), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": round(ms_per_step, 5), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8", "data": "synthetic",
-        "config": {"workload": f"{args.config}: {cfg['desc']}", "frames_resident_ring": ring,
-                   "l2": f"inputs larger than L2: ring of {ring} x {frame_bytes / 1e6:.1f} MB frames per GPU",
+        "config": {"workload": f"{args.config}: {cfg['desc']}", "frames_resident_ring": m["ring"],
+                   "l2": f"inputs larger than L2: ring of {m['ring']} x {in_px / 1e6:.1f} MB frames per GPU",
                    "sharding": "frames round-robin over ranks; one NCCL broadcast of context+dims; no pixel traffic",
+                   "numa": f"rank bound to NUMA node {numa[0]} ({numa[1]} CPUs) of its GPU" if numa else "no NUMA binding",
                    "output_mpx_per_s": round(out_px * K * world / (ms_total_max * 1e-3) / 1e6, 1),
-                   "frames_per_s": round(K * world / (ms_total_max * 1e-3), 1), "plan_seconds": round(plan_seconds, 3),
-                   "tiles_luma[gather_tma_staged,gather_general,lowpass_strip_jobs,lowpass_general_jobs]": list(ft.vft.plan_tile_counts(0)),
-                   "tiles_chroma": list(ft.vft.plan_tile_counts(1))},
-        "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks,
+                   "frames_per_s": round(K * world / (ms_total_max * 1e-3), 1), "plan_seconds": round(m["plan_seconds"], 3),
+                   "jobs_luma[gather_staged,gather_general,lowpass_strip_jobs,lowpass_general_jobs]": m["tiles"][0],
+                   "jobs_chroma": m["tiles"][1]},
+        "e2e": e2e, "gpu_launches": int(m["launches"]), "roofline": roofline_of(args.config, cfg, spec, m, ms_per_step),
+        "configs": others or None, "cross_rank_identical": cross_rank_identical, "cpu_baseline": cpu_baseline, "clocks": clocks,
     }
     print(json.dumps(line), flush=True)
     if world > 1:

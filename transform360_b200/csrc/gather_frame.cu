@@ -544,12 +544,18 @@ gatherFrameKernel(const __grid_constant__ FrameGatherParams p, StagedParams jobs
 }
 
 template <int K, int COPIES, int GROUPS>
-cudaError_t launchFrameK(const FrameGatherParams& p, const StagedParams& jobs, const FrameTensorMaps& maps, int numSMs,
-                         cudaStream_t stream) {
+cudaError_t prepareFrameK(LaunchCfg& cfg) {
   static DeviceLaunchCfg cfgs;
   constexpr int threads = GROUPS * (kGroupWarps + 1) * 32, smemBytes = FrameLayout<K, COPIES, GROUPS>::kTotal;
+  return prepare<gatherFrameKernel<K, COPIES, GROUPS>>(cfgs, threads, smemBytes, cfg);
+}
+
+template <int K, int COPIES, int GROUPS>
+cudaError_t launchFrameK(const FrameGatherParams& p, const StagedParams& jobs, const FrameTensorMaps& maps, int numSMs,
+                         cudaStream_t stream, bool programmatic) {
+  constexpr int threads = GROUPS * (kGroupWarps + 1) * 32, smemBytes = FrameLayout<K, COPIES, GROUPS>::kTotal;
   LaunchCfg cfg;
-  cudaError_t err = prepare<gatherFrameKernel<K, COPIES, GROUPS>>(cfgs, threads, smemBytes, cfg);
+  cudaError_t err = prepareFrameK<K, COPIES, GROUPS>(cfg);
   if (err != cudaSuccess) return err;
   const int grid = std::min(numSMs * cfg.perSM, (jobs.numTiles + GROUPS * 2 * kClaimBatch - 1) / (GROUPS * 2 * kClaimBatch));  // persistent: one CTA per SM
   cudaLaunchConfig_t lc{};
@@ -561,7 +567,7 @@ cudaError_t launchFrameK(const FrameGatherParams& p, const StagedParams& jobs, c
   attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;  // see griddepcontrol.* in the kernel
   attr.val.programmaticStreamSerializationAllowed = 1;
   lc.attrs = &attr;
-  lc.numAttrs = 1;
+  lc.numAttrs = programmatic ? 1 : 0;
   err = cudaLaunchKernelEx(&lc, gatherFrameKernel<K, COPIES, GROUPS>, p, jobs, maps);
   gLaunches.fetch_add(1, std::memory_order_relaxed);
   return err;
@@ -569,8 +575,18 @@ cudaError_t launchFrameK(const FrameGatherParams& p, const StagedParams& jobs, c
 
 }  // namespace
 
+cudaError_t prepareGatherFrame(int kernelSize) {
+  LaunchCfg cfg;
+  switch (kernelSize) {
+    case 2: return prepareFrameK<2, weightCopies(2), gatherGroups(2)>(cfg);
+    case 4: return prepareFrameK<4, weightCopies(4), gatherGroups(4)>(cfg);
+    case 8: return prepareFrameK<8, weightCopies(8), gatherGroups(8)>(cfg);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
 cudaError_t launchGatherFrame(const FrameGatherParams& p, const StagedParams& jobs, const void* tensorMaps, int numSMs,
-                              cudaStream_t stream) {
+                              cudaStream_t stream, bool programmatic) {
   if (jobs.numTiles <= 0) return cudaSuccess;
   if (p.numPlanes < 1 || p.numPlanes > kMaxFramePlanes) return cudaErrorInvalidValue;
   FrameTensorMaps maps;
@@ -578,9 +594,9 @@ cudaError_t launchGatherFrame(const FrameGatherParams& p, const StagedParams& jo
   for (int i = p.numPlanes; i < kMaxFramePlanes; ++i)  // unused entries: valid descriptors that no job refers to
     for (int c = 0; c < kNumBoxClasses; ++c) maps.map[i][c] = maps.map[0][c];
   switch (p.kernelSize) {
-    case 2: return launchFrameK<2, weightCopies(2), gatherGroups(2)>(p, jobs, maps, numSMs, stream);
-    case 4: return launchFrameK<4, weightCopies(4), gatherGroups(4)>(p, jobs, maps, numSMs, stream);
-    case 8: return launchFrameK<8, weightCopies(8), gatherGroups(8)>(p, jobs, maps, numSMs, stream);
+    case 2: return launchFrameK<2, weightCopies(2), gatherGroups(2)>(p, jobs, maps, numSMs, stream, programmatic);
+    case 4: return launchFrameK<4, weightCopies(4), gatherGroups(4)>(p, jobs, maps, numSMs, stream, programmatic);
+    case 8: return launchFrameK<8, weightCopies(8), gatherGroups(8)>(p, jobs, maps, numSMs, stream, programmatic);
     default: return cudaErrorInvalidValue;
   }
 }

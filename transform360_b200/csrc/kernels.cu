@@ -456,5 +456,6 @@ cudaError_t launchBlurDirect(const BlurParams& p, cudaStream_t stream) {
 }
 
 unsigned long long kernelLaunchCount() { return gLaunches.load(std::memory_order_relaxed); }
+void countKernelLaunches(long long n) { gLaunches.fetch_add(static_cast<unsigned long long>(n), std::memory_order_relaxed); }
 
 }  // namespace t360

@@ -230,12 +230,17 @@ cudaError_t launchGather(const GatherParams& p, int numSMs, cudaStream_t stream)
 // Whole planes in one persistent kernel: `jobs` lists the jobs of every plane, sorted by kind (general, seam, class 1,
 // share, class 0).  tensorMaps: per plane kNumBoxClasses CUtensorMap (128 bytes each) describing its source with the
 // staging boxes of p.kernelSize, i.e. [numPlanes][kNumBoxClasses].  BORDER_WRAP only.
+// programmatic: allow the launch to overlap the tail of the previous kernel on the stream (programmatic dependent launch).
 cudaError_t launchGatherFrame(const FrameGatherParams& p, const StagedParams& jobs, const void* tensorMaps, int numSMs,
-                              cudaStream_t stream);
+                              cudaStream_t stream, bool programmatic = true);
+// one-time set-up of the frame kernel for kernelSize on the current device (shared-memory opt-in, occupancy): call it
+// before capturing launchGatherFrame into a CUDA graph
+cudaError_t prepareGatherFrame(int kernelSize);
 cudaError_t launchBlurStrips(const StripParams& p, int hy, cudaStream_t stream);  // register-resident, hy <= kStripMaxHy
 cudaError_t launchBlur(const BlurParams& p, cudaStream_t stream);        // shared-memory tiles
 cudaError_t launchBlurDirect(const BlurParams& p, cudaStream_t stream);  // any kernel size, slow
 unsigned long long kernelLaunchCount();
+void countKernelLaunches(long long n);  // kernels launched through a replayed CUDA graph
 
 // bytes of dynamic shared memory a blur tile of (w x h) with the given tap counts needs
 inline int blurTileSmem(int w, int h, int nkx, int nky) {

@@ -192,6 +192,8 @@ class VideoFrameTransform {
     const char* e = std::getenv("T360B200_PIN_HOST_PLANES");
     pinHostPlanes_ = e && *e && *e != '0';
     if (const char* m = std::getenv("T360B200_PIPELINE_MIN_BYTES")) pipelineMinBytes_ = std::atoll(m);  // tests: 0 = always
+    if (const char* m = std::getenv("T360B200_PIPELINE_CHUNKS")) pipelineChunks_ = std::atoi(m);       // tuning
+    if (const char* m = std::getenv("T360B200_PIPELINE_BLOCKS")) pipelineBlocks_ = std::atoi(m);
   }
   void setPinHostPlanes(bool on) { pinHostPlanes_ = on; }
 
@@ -218,6 +220,8 @@ class VideoFrameTransform {
       for (cudaEvent_t e : chunkIn_) cudaEventDestroy(e);
       for (cudaEvent_t e : waveDone_) cudaEventDestroy(e);
       for (WavePlan& w : wavePlans_) w.jobs.release();
+      for (PlaneGraph& g : planeGraphs_) cudaGraphExecDestroy(g.exec);
+      for (cudaEvent_t e : {graphFork_, graphJoinIn_, graphJoinOut_}) if (e) cudaEventDestroy(e);
       if (copyIn_) cudaStreamDestroy(copyIn_);
       if (copyOut_) cudaStreamDestroy(copyOut_);
       if (stream_) cudaStreamDestroy(stream_);
@@ -323,10 +327,12 @@ class VideoFrameTransform {
       return c;
     };
     std::vector<std::vector<GatherJob>> byWave(chunks);
-    // which output rectangles are complete after which wave: 32-row bands x column blocks that no job straddles
+    // Which output rectangles are complete after which wave: 32-row bands of the full width by default (contiguous
+    // copies: a band split into the three faces of a cube-map row finishes earlier per face, but strided rectangle
+    // copies ran at 11 GB/s where whole bands reach 16-45 GB/s; T360B200_PIPELINE_BLOCKS > 1 splits anyway).
     int blocks = 1;
     for (int nb : {4, 3, 2})
-      if (plan.mapW % (nb * t360::kShareW) == 0) { blocks = nb; break; }
+      if (plan.mapW % (nb * t360::kShareW) == 0 && nb <= pipelineBlocks_) { blocks = nb; break; }
     const int blockW = plan.mapW / blocks, bands = (plan.mapH + 31) / 32;
     std::vector<int> complete(static_cast<size_t>(bands) * blocks, 0);
     for (size_t i = 0; i < plan.hostJobs.size(); ++i) {
@@ -361,15 +367,26 @@ class VideoFrameTransform {
     return w;
   }
 
+  static bool isPinnedHost(const void* p) {
+    cudaPointerAttributes a{};
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+      cudaGetLastError();
+      return false;
+    }
+    return a.type == cudaMemoryTypeHost;
+  }
+
   // reference transformFramePlane for large host planes (same result as the plain path): chunked H2D || gather || D2H
   bool transformHostPlanePipelined(const DevicePlan& plan, uint8_t* in, uint8_t* out, int inW, int inH, int inPitch, int outW, int outH,
                                    int outPitch, int planIndex, int imagePlaneIndex) {
     const long long bytes = static_cast<long long>(inW) * inH;
-    const int chunks = static_cast<int>(std::min<long long>(8, std::max<long long>(2, bytes / (3ll << 20))));
+    const int chunks = pipelineChunks_ > 1 ? std::min(pipelineChunks_, 32)
+                                           : static_cast<int>(std::min<long long>(8, std::max<long long>(2, bytes / (3ll << 20))));
     WavePlan& w = wavePlanFor(plan, planIndex, chunks);
     if (!copyIn_) {
       CU(cudaStreamCreateWithFlags(&copyIn_, cudaStreamNonBlocking));
       CU(cudaStreamCreateWithFlags(&copyOut_, cudaStreamNonBlocking));
+      for (cudaEvent_t* e : {&graphFork_, &graphJoinIn_, &graphJoinOut_}) CU(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
     }
     while (static_cast<int>(chunkIn_.size()) < chunks) {
       cudaEvent_t a = nullptr, b = nullptr;
@@ -394,35 +411,140 @@ class VideoFrameTransform {
       return true;
     }
     armScheduler(lanes_[0].claimCounter, stream_);
-    t360::FrameGatherParams fp{};
-    fp.plane[0] = work.view;
-    fp.weightImage = reinterpret_cast<const uint4*>(weightImages_[plan.kernelSize].ptr);
-    fp.kernelSize = plan.kernelSize;
-    fp.numPlanes = 1;
-    bool copiedOut = false;
-    for (int c = 0; c < chunks; ++c) {
-      const int r0 = c ? w.chunkRowEnd[c - 1] : 0, r1 = w.chunkRowEnd[c];
-      if (r1 > r0)
+    CU(t360::prepareGatherFrame(plan.kernelSize));
+    auto issue = [&](bool forkJoin) {
+      if (forkJoin) {  // (capture: the side streams become branches of the graph)
+        CU(cudaEventRecord(graphFork_, stream_));
+        CU(cudaStreamWaitEvent(copyIn_, graphFork_, 0));
+        CU(cudaStreamWaitEvent(copyOut_, graphFork_, 0));
+      }
+      t360::FrameGatherParams fp{};
+      fp.plane[0] = work.view;
+      fp.weightImage = reinterpret_cast<const uint4*>(weightImages_[plan.kernelSize].ptr);
+      fp.kernelSize = plan.kernelSize;
+      fp.numPlanes = 1;
+      for (int c = 0; c < chunks; ++c) {
+        const int r0 = c ? w.chunkRowEnd[c - 1] : 0, r1 = w.chunkRowEnd[c];
+        if (r1 > r0)
+          CU(cudaMemcpy2DAsync(stagingIn_.ptr + static_cast<size_t>(r0) * dInPitch, dInPitch, in + static_cast<size_t>(r0) * inPitch, inPitch, inW,
+                               r1 - r0, cudaMemcpyHostToDevice, copyIn_));
+        CU(cudaEventRecord(chunkIn_[c], copyIn_));
+        CU(cudaStreamWaitEvent(stream_, chunkIn_[c], 0));
+        const int n = w.waveStart[c + 1] - w.waveStart[c];
+        if (n > 0) {
+          t360::StagedParams jobs{w.jobs.ptr + w.waveStart[c], n, lanes_[0].claimCounter.ptr, nullptr};
+          CU(t360::launchGatherFrame(fp, jobs, work.maps, numSMs_, stream_, /*programmatic=*/false));
+        }
+        if (!w.rects[c].empty()) {
+          CU(cudaEventRecord(waveDone_[c], stream_));
+          CU(cudaStreamWaitEvent(copyOut_, waveDone_[c], 0));
+          for (const WavePlan::Rect& r : w.rects[c])
+            CU(cudaMemcpy2DAsync(out + static_cast<size_t>(r.y) * outPitch + r.x, outPitch,
+                                 stagingOut_.ptr + static_cast<size_t>(r.y) * dOutPitch + r.x, dOutPitch, r.w, r.h, cudaMemcpyDeviceToHost, copyOut_));
+        }
+      }
+      if (forkJoin) {
+        CU(cudaEventRecord(graphJoinIn_, copyIn_));
+        CU(cudaEventRecord(graphJoinOut_, copyOut_));
+        CU(cudaStreamWaitEvent(stream_, graphJoinIn_, 0));
+        CU(cudaStreamWaitEvent(stream_, graphJoinOut_, 0));
+      }
+    };
+    if (std::getenv("T360B200_PIPELINE_TIMING")) {  // tuning aid: the timeline of one streamed call on stdout
+      std::vector<cudaEvent_t> ev(3 * chunks + 1);
+      for (cudaEvent_t& e : ev) CU(cudaEventCreate(&e));
+      CU(cudaStreamSynchronize(stream_));
+      CU(cudaEventRecord(ev[3 * chunks], stream_));
+      CU(cudaStreamWaitEvent(copyIn_, ev[3 * chunks], 0));
+      CU(cudaStreamWaitEvent(copyOut_, ev[3 * chunks], 0));
+      t360::FrameGatherParams fp{};
+      fp.plane[0] = work.view;
+      fp.weightImage = reinterpret_cast<const uint4*>(weightImages_[plan.kernelSize].ptr);
+      fp.kernelSize = plan.kernelSize;
+      fp.numPlanes = 1;
+      for (int c = 0; c < chunks; ++c) {
+        const int r0 = c ? w.chunkRowEnd[c - 1] : 0, r1 = w.chunkRowEnd[c];
         CU(cudaMemcpy2DAsync(stagingIn_.ptr + static_cast<size_t>(r0) * dInPitch, dInPitch, in + static_cast<size_t>(r0) * inPitch, inPitch, inW,
                              r1 - r0, cudaMemcpyHostToDevice, copyIn_));
-      CU(cudaEventRecord(chunkIn_[c], copyIn_));
-      CU(cudaStreamWaitEvent(stream_, chunkIn_[c], 0));
-      const int n = w.waveStart[c + 1] - w.waveStart[c];
-      if (n > 0) {
-        t360::StagedParams jobs{w.jobs.ptr + w.waveStart[c], n, lanes_[0].claimCounter.ptr, nullptr};
-        CU(t360::launchGatherFrame(fp, jobs, work.maps, numSMs_, stream_));
-      }
-      if (!w.rects[c].empty()) {
-        CU(cudaEventRecord(waveDone_[c], stream_));
-        CU(cudaStreamWaitEvent(copyOut_, waveDone_[c], 0));
+        CU(cudaEventRecord(ev[3 * c], copyIn_));
+        CU(cudaStreamWaitEvent(stream_, ev[3 * c], 0));
+        const int n = w.waveStart[c + 1] - w.waveStart[c];
+        if (n > 0) {
+          t360::StagedParams jobs{w.jobs.ptr + w.waveStart[c], n, lanes_[0].claimCounter.ptr, nullptr};
+          CU(t360::launchGatherFrame(fp, jobs, work.maps, numSMs_, stream_, false));
+        }
+        CU(cudaEventRecord(ev[3 * c + 1], stream_));
+        CU(cudaStreamWaitEvent(copyOut_, ev[3 * c + 1], 0));
         for (const WavePlan::Rect& r : w.rects[c])
           CU(cudaMemcpy2DAsync(out + static_cast<size_t>(r.y) * outPitch + r.x, outPitch, stagingOut_.ptr + static_cast<size_t>(r.y) * dOutPitch + r.x,
                                dOutPitch, r.w, r.h, cudaMemcpyDeviceToHost, copyOut_));
-        copiedOut = true;
+        CU(cudaEventRecord(ev[3 * c + 2], copyOut_));
       }
+      CU(cudaStreamSynchronize(stream_));
+      CU(cudaStreamSynchronize(copyOut_));
+      std::printf("streamed plane %d (%dx%d -> %dx%d, %d chunks): chunk | H2D done | wave done (jobs) | D2H done (rects, bytes) [us]\n", imagePlaneIndex, inW,
+                  inH, outW, outH, chunks);
+      for (int c = 0; c < chunks; ++c) {
+        float a = 0, b = 0, d = 0;
+        cudaEventElapsedTime(&a, ev[3 * chunks], ev[3 * c]);
+        cudaEventElapsedTime(&b, ev[3 * chunks], ev[3 * c + 1]);
+        cudaEventElapsedTime(&d, ev[3 * chunks], ev[3 * c + 2]);
+        long long bytes = 0;
+        for (const WavePlan::Rect& r : w.rects[c]) bytes += static_cast<long long>(r.w) * r.h;
+        std::printf("  %2d | %7.1f | %7.1f (%5d) | %7.1f (%2zu, %lld)\n", c, a * 1e3, b * 1e3, w.waveStart[c + 1] - w.waveStart[c], d * 1e3,
+                    w.rects[c].size(), bytes);
+      }
+      for (cudaEvent_t e : ev) cudaEventDestroy(e);
+      return true;
     }
+    if (isPinnedHost(in) && isPinnedHost(out)) {
+      PlaneGraph* g = nullptr;
+      for (size_t i = 0; i < planeGraphs_.size();) {
+        PlaneGraph& c = planeGraphs_[i];
+        if (c.stagingIn != stagingIn_.ptr || c.stagingOut != stagingOut_.ptr || c.generation != planGeneration_) {
+          cudaGraphExecDestroy(c.exec);
+          planeGraphs_.erase(planeGraphs_.begin() + static_cast<long>(i));
+          continue;
+        }
+        if (c.plan == &plan && c.in == in && c.out == out && c.inPitch == inPitch && c.outPitch == outPitch) g = &c;
+        ++i;
+      }
+      if (!g) {
+        if (planeGraphs_.size() >= 24) {  // (a frame pool recycles a handful of buffers; forget the least recently used)
+          auto oldest = std::min_element(planeGraphs_.begin(), planeGraphs_.end(), [](const PlaneGraph& a, const PlaneGraph& b) { return a.lastUse < b.lastUse; });
+          cudaGraphExecDestroy(oldest->exec);
+          planeGraphs_.erase(oldest);
+        }
+        CU(cudaStreamSynchronize(stream_));
+        cudaGraph_t graph = nullptr;
+        CU(cudaStreamBeginCapture(stream_, cudaStreamCaptureModeThreadLocal));
+        try {
+          issue(true);
+        } catch (...) {
+          cudaStreamEndCapture(stream_, &graph);
+          if (graph) cudaGraphDestroy(graph);
+          throw;
+        }
+        CU(cudaStreamEndCapture(stream_, &graph));
+        cudaGraphExec_t exec = nullptr;
+        const cudaError_t e = cudaGraphInstantiate(&exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (e != cudaSuccess) throw CudaFail{e, "cudaGraphInstantiate"};
+        int kernels = 0;
+        for (int c = 0; c < chunks; ++c) kernels += w.waveStart[c + 1] > w.waveStart[c];
+        planeGraphs_.push_back(PlaneGraph{&plan, planGeneration_, in, out, inPitch, outPitch, stagingIn_.ptr, stagingOut_.ptr, kernels, exec, 0});
+        g = &planeGraphs_.back();
+        t360::countKernelLaunches(-kernels);  // (counted once while capturing; every replay counts below)
+      }
+      g->lastUse = ++graphClock_;
+      CU(cudaGraphLaunch(g->exec, stream_));
+      t360::countKernelLaunches(g->kernels);
+      CU(cudaStreamSynchronize(stream_));
+      return true;
+    }
+    issue(false);
     CU(cudaStreamSynchronize(stream_));
-    if (copiedOut) CU(cudaStreamSynchronize(copyOut_));
+    CU(cudaStreamSynchronize(copyOut_));
     return true;
   }
 
@@ -981,6 +1103,19 @@ class VideoFrameTransform {
   std::vector<cudaEvent_t> chunkIn_, waveDone_;
   WavePlan wavePlans_[2];  // plan index 0 / 1
   long long pipelineMinBytes_ = 6ll << 20;
+  int pipelineChunks_ = 0, pipelineBlocks_ = 0;  // 0: automatic
+  // The streamed call is ~100 runtime calls (chunk copies, events, wave launches, rectangle copies); issued one by one
+  // the host thread becomes the bottleneck (measured: no faster than the plain path).  For page-locked caller planes the
+  // whole sequence is captured once per (plan, buffers) into a CUDA graph and replayed with one launch.
+  struct PlaneGraph {
+    const void* plan; unsigned long long generation; const void* in; const void* out; int inPitch, outPitch;
+    const void* stagingIn; const void* stagingOut;  // (the staging planes grow on demand: a graph made for old ones is stale)
+    int kernels;
+    cudaGraphExec_t exec; unsigned long long lastUse;
+  };
+  std::vector<PlaneGraph> planeGraphs_;
+  unsigned long long graphClock_ = 0;
+  cudaEvent_t graphFork_ = nullptr, graphJoinIn_ = nullptr, graphJoinOut_ = nullptr;
   // opt-in page-locking of recurring pageable caller planes (ffmpeg recycles its frame pool): see pinIfRecurring()
   struct HostRange { uintptr_t base; size_t bytes; int seen; bool pinned; };
   std::vector<HostRange> hostRanges_;

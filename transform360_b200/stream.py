@@ -49,6 +49,33 @@ class StreamSpec:
         return StreamSpec(*[int(x) for x in v])
 
 
+def bind_to_gpu_numa_node(gpu_index: int):
+    """Pins the calling process to the CPUs of the NUMA node the GPU hangs off (PCI sysfs), BEFORE it allocates the
+    page-locked frame buffers, so that they are first-touched on that node.  On the 2-socket B200 boxes a pinned host
+    plane on the far socket is DMA'd at 20 GB/s instead of 55 GB/s (H2D), and 8 ranks without affinity fight over the
+    inter-socket link.  Returns (node, cpus bound) or None when the topology cannot be read."""
+    import os
+    import subprocess
+    try:
+        bus = subprocess.run(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                             capture_output=True, text=True, timeout=30).stdout.strip().lower()
+        if bus.startswith("0000"):
+            bus = bus[4:]
+        base = f"/sys/bus/pci/devices/{bus}/"
+        node = int(open(base + "numa_node").read())
+        cpus = set()
+        for part in open(base + "local_cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if node < 0 or not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node, len(cpus)
+    except Exception:
+        return None
+
+
 def frames_for_rank(num_frames: int, rank: int, world_size: int):
     """Round-robin sharding: frame k goes to GPU k mod N."""
     return range(rank, num_frames, world_size)
