@@ -65,6 +65,13 @@ SMALL = {
                                          num_vertical_segments=7, num_horizontal_segments=2), inp=(640, 320), out=(96, 64)),
     "scaled_3x1": dict(ov=dict(width_scale_factor=3.0, height_scale_factor=1.0, interpolation_alg=I_LANCZOS4,
                                enable_low_pass_filter=0), inp=(512, 256), out=(96, 64)),
+    # scale factors below 1: cv::resize(INTER_AREA) ENLARGES (its bilinear variant, ref:770-776)
+    "scaled_half": dict(ov=dict(width_scale_factor=0.5, height_scale_factor=0.5, interpolation_alg=I_CUBIC,
+                                enable_low_pass_filter=0), inp=(512, 256), out=(192, 128)),
+    "scaled_075_lp": dict(ov=dict(width_scale_factor=0.75, height_scale_factor=0.75, interpolation_alg=I_LINEAR,
+                                  num_vertical_segments=7, num_horizontal_segments=2), inp=(640, 320), out=(192, 128)),
+    "scaled_mixed": dict(ov=dict(width_scale_factor=0.5, height_scale_factor=2.0, interpolation_alg=I_LANCZOS4,
+                                 enable_low_pass_filter=0), inp=(512, 256), out=(190, 126)),
     "barrel": dict(ov=dict(output_layout=L_BARREL, interpolation_alg=I_CUBIC, enable_low_pass_filter=0),
                    inp=(512, 256), out=(250, 100)),
     "barrel_split_linear": dict(ov=dict(output_layout=L_BARREL_SPLIT, interpolation_alg=I_LINEAR,

@@ -545,3 +545,24 @@ def test_concurrent_calls_on_different_planes(torch_cuda):
         iw, ih, ow, oh, idx = plane_dims(case, plane)
         want = co.transform_plane(octx, co.OraclePlan(octx, iw, ih, ow, oh), src, ow, oh, map_index=idx)
         assert np.array_equal(got, want), f"plane {plane} frame {frame}"
+
+
+@pytest.mark.parametrize("name,out2,in2", [("cube_cubic", (150, 90), None), ("cube_linear", (250, 200), None), ("lp_tiles", (240, 160), (900, 440)),
+                                           ("lp_default", (200, 100), (600, 300)), ("scaled_2x2", (96, 64), (480, 250))])
+def test_sizes_that_differ_from_the_generated_map(name, out2, in2, torch_cuda):
+    """The reference decides per call (cpp:735-737): an output size other than the map's takes the render + cv::resize
+    (INTER_AREA, shrinking or enlarging) branch; an input plane of another size is sampled with BORDER_WRAP against ITS
+    size, and its low-pass applies the planned segments that still fit (cpp:173-204)."""
+    case = SMALL[name]
+    ctx, octx = _ctxs(case)
+    iw, ih, ow, oh, _ = plane_dims(case, 0)
+    iw2, ih2 = in2 or (iw, ih)
+    src = co.noise_plane(iw2, ih2, plane=0, frame=4)
+    with t360.VideoFrameTransform(ctx) as vft:
+        assert vft.generateMapForPlane(iw, ih, ow, oh, 0)
+        got = vft.transform_plane(src, out2[0], out2[1], 0)
+        again = vft.transform_plane(src, out2[0], out2[1], 0)
+    plan = co.OraclePlan(octx, iw, ih, ow, oh)
+    want = co.transform_plane(octx, plan, src, out2[0], out2[1])
+    assert np.array_equal(got, want), f"{(got != want).sum()} px differ"
+    assert np.array_equal(again, got)

@@ -40,11 +40,21 @@ struct AreaAxis {
   std::vector<AreaTap> taps;   // grouped by destination index, in OpenCV's order
   std::vector<int> first;      // [dst + 1]: taps of destination i are taps[first[i] .. first[i+1])
 };
+// One axis of cv::resize(INTER_AREA) when at least one axis ENLARGES (a scale factor below 1): OpenCV runs its 8-bit
+// fixed-point bilinear kernel with "area mode" coefficients on both axes.  Destination d reads source ofs[d] and
+// ofs[d] + 1 with the 11-bit weights coef[2d], coef[2d + 1]; from d == dmax on only source ofs[d] (weight 2048).
+struct AreaLinearAxis {
+  std::vector<int> ofs;
+  std::vector<int16_t> coef;
+  int dmax = 0;
+};
 struct AreaResizePlan {
-  bool needed = false, supported = true;
+  bool needed = false;
+  bool enlarge = false;      // the bilinear variant (lx, ly) instead of the area tables
   int srcW = 0, srcH = 0, dstW = 0, dstH = 0;
   int cellW = 0, cellH = 0;  // > 0: both ratios are integers (fast path), else use the axes below
   AreaAxis x, y;
+  AreaLinearAxis lx, ly;
 };
 
 struct HostPlan {
@@ -84,6 +94,8 @@ inline int kernelSizeOf(int interpolationAlg) {
   }
 }
 
+// cv::resize(INTER_AREA) from srcW x srcH to dstW x dstH (reference cpp:770-776).
+void buildAreaResize(int srcW, int srcH, int dstW, int dstH, AreaResizePlan& r);
 // Fills plan.resize for (mapW x mapH) -> (outW x outH).
 void buildAreaResizePlan(HostPlan& plan);
 

@@ -400,6 +400,25 @@ cudaError_t launchNearest(const GatherParams& p, int numSMs, cudaStream_t stream
   return cudaGetLastError();
 }
 
+// cv::resize(INTER_AREA) with an enlarging axis (scale factors below 1): OpenCV's 8-bit fixed-point bilinear kernel with
+// "area mode" weights (sampling.cpp: areaLinearAxis), horizontal pass in 11-bit fixed point, vertical pass with the
+// shifts of VResizeLinear<uchar>.  Integer arithmetic: bit-exact.
+__global__ void __launch_bounds__(256) areaEnlargeKernel(AreaParams p) {
+  const int dx = blockIdx.x * 32 + (threadIdx.x & 31), dy = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (dx >= p.dstW || dy >= p.dstH) return;
+  const int2 tx = __ldg(p.xLinear + dx), ty = __ldg(p.yLinear + dy);
+  const int a0 = (int16_t)(tx.y & 0xffff), a1 = tx.y >> 16, b0 = (int16_t)(ty.y & 0xffff), b1 = ty.y >> 16;
+  int H[2];
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const int sy = min(max(ty.x + k, 0), p.srcH - 1);
+    const uint8_t* S = p.src + (size_t)sy * p.srcPitch;
+    H[k] = dx < p.xMax ? __ldg(S + tx.x) * a0 + __ldg(S + tx.x + 1) * a1 : __ldg(S + tx.x) * 2048;
+  }
+  const int v = (((b0 * (H[0] >> 4)) >> 16) + ((b1 * (H[1] >> 4)) >> 16) + 2) >> 2;
+  p.dst[(size_t)dy * p.dstPitch + dx] = (uint8_t)min(max(v, 0), 255);
+}
+
 }  // namespace
 
 cudaError_t launchGather(const GatherParams& p, int numSMs, cudaStream_t stream) {
@@ -417,7 +436,8 @@ cudaError_t launchGather(const GatherParams& p, int numSMs, cudaStream_t stream)
 cudaError_t launchAreaResize(const AreaParams& p, cudaStream_t stream) {
   if (p.dstW <= 0 || p.dstH <= 0) return cudaSuccess;
   const dim3 grid((p.dstW + 31) / 32, (p.dstH + 7) / 8);
-  areaResizeKernel<<<grid, 256, 0, stream>>>(p);
+  if (p.cellW < 0) areaEnlargeKernel<<<grid, 256, 0, stream>>>(p);
+  else areaResizeKernel<<<grid, 256, 0, stream>>>(p);
   gLaunches.fetch_add(1, std::memory_order_relaxed);
   return cudaGetLastError();
 }

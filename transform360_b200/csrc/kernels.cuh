@@ -216,6 +216,12 @@ struct AreaParams {
   const int* xFirst;
   const int2* yTaps;
   const int* yFirst;
+  // enlarging variant (cellW < 0): per destination column / row {source index, weight0 | weight1 << 16} (11-bit weights);
+  // from xMax on a column reads its first source only.  dst = (((b0 * (H0 >> 4)) >> 16) + ((b1 * (H1 >> 4)) >> 16) + 2) >> 2,
+  // H = S[sx] * a0 + S[sx + 1] * a1 per row.
+  const int2* xLinear;
+  const int2* yLinear;
+  int xMax;
 };
 cudaError_t launchAreaResize(const AreaParams& p, cudaStream_t stream);
 

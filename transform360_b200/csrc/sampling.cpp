@@ -174,16 +174,46 @@ AreaAxis areaAxis(int ssize, int dsize, double scale) {
 }
 }  // namespace
 
-void buildAreaResizePlan(HostPlan& plan) {
-  AreaResizePlan& r = plan.resize;
+namespace {
+// OpenCV 4.x imgproc/resize.cpp, the INTER_LINEAR set-up with its "area mode" coefficients (interpolation ==
+// INTER_AREA, scale < 1 on some axis): sx = floor(dx * scale); fx = (dx + 1) - (sx + 1) * inv_scale, 0 if not positive,
+// else its fractional part; clamped at the last source sample; weights = cvRound({1 - fx, fx} * 2048).  Pinned
+// bit-exact against cv2 4.13 through the oracle (tests/test_oracle_pin.py).
+AreaLinearAxis areaLinearAxis(int dn, int sn, double scale, double inv) {
+  AreaLinearAxis a;
+  a.ofs.resize(static_cast<size_t>(dn));
+  a.coef.resize(static_cast<size_t>(dn) * 2);
+  a.dmax = dn;
+  for (int d = 0; d < dn; ++d) {
+    int s = static_cast<int>(std::floor(d * scale));
+    float f = static_cast<float>((d + 1) - (s + 1) * inv);
+    f = f <= 0 ? 0.f : f - static_cast<float>(std::floor(f));
+    if (s < 0) { f = 0; s = 0; }
+    if (s + 1 >= sn) {
+      a.dmax = std::min(a.dmax, d);
+      if (s >= sn - 1) { f = 0; s = sn - 1; }
+    }
+    a.ofs[d] = s;
+    const long c0 = std::lrintf((1.f - f) * 2048.f), c1 = std::lrintf(f * 2048.f);
+    a.coef[2 * d] = static_cast<int16_t>(std::min(c0, 32767l));
+    a.coef[2 * d + 1] = static_cast<int16_t>(std::min(c1, 32767l));
+  }
+  return a;
+}
+}  // namespace
+
+void buildAreaResize(int srcW, int srcH, int dstW, int dstH, AreaResizePlan& r) {
   r = AreaResizePlan{};
-  r.srcW = plan.mapW; r.srcH = plan.mapH; r.dstW = plan.outW; r.dstH = plan.outH;
+  r.srcW = srcW; r.srcH = srcH; r.dstW = dstW; r.dstH = dstH;
   r.needed = r.srcW != r.dstW || r.srcH != r.dstH;  // reference cpp:735-737
   if (!r.needed) return;
   // cv::resize: scale = 1. / ((double)dsize / ssize); INTER_AREA takes the area paths only when shrinking both ways
-  const double sx = 1.0 / (static_cast<double>(r.dstW) / r.srcW), sy = 1.0 / (static_cast<double>(r.dstH) / r.srcH);
+  const double invX = static_cast<double>(r.dstW) / r.srcW, invY = static_cast<double>(r.dstH) / r.srcH;
+  const double sx = 1.0 / invX, sy = 1.0 / invY;
   if (sx < 1.0 || sy < 1.0) {
-    r.supported = false;  // enlarging INTER_AREA is a bilinear variant: not implemented (scale factors < 1)
+    r.enlarge = true;
+    r.lx = areaLinearAxis(r.dstW, r.srcW, sx, invX);
+    r.ly = areaLinearAxis(r.dstH, r.srcH, sy, invY);
     return;
   }
   const int ix = static_cast<int>(std::lrint(sx)), iy = static_cast<int>(std::lrint(sy));
@@ -194,6 +224,8 @@ void buildAreaResizePlan(HostPlan& plan) {
   r.x = areaAxis(r.srcW, r.dstW, sx);
   r.y = areaAxis(r.srcH, r.dstH, sy);
 }
+
+void buildAreaResizePlan(HostPlan& plan) { buildAreaResize(plan.mapW, plan.mapH, plan.outW, plan.outH, plan.resize); }
 
 bool buildHostPlan(const FrameTransformContext& ctx, int inW, int inH, int outW, int outH, HostPlan& plan) {
   plan = HostPlan{};

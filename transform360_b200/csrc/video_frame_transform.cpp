@@ -77,7 +77,7 @@ struct DeviceBuffer {
 struct DevicePlan {
   int inW = 0, inH = 0, outW = 0, outH = 0, mapW = 0, mapH = 0;
   int kernelSize = 0;
-  bool transparent = false, lowPass = false, blurNeedsClear = false;
+  bool transparent = false, lowPass = false;
   DeviceBuffer<int2> samples;      // full records: tile-major, lane-ordered, 8 bytes per pixel (general kernels / jobs)
   DeviceBuffer<uint32_t> records;  // compact records of the staged jobs (kernels.cuh): 2.5 - 4 bytes per pixel
   int tilesPerRow = 0;
@@ -87,19 +87,33 @@ struct DevicePlan {
   std::vector<int> jobNeedRows;        // per host job: the source rows [0, n) it reads (streaming host planes in)
   int numJobs = 0, numStaged[2] = {}, numSeam = 0, numShare = 0, numFallback = 0;
   int totalStaged() const { return numSeam + numShare + numStaged[0] + numStaged[1]; }
-  // low-pass: register-resident strip jobs grouped by vertical half-size 1..3, and the rest (large vertical kernels)
-  DeviceBuffer<StripJob> stripJobs[t360::kStripMaxHy];
-  int numStripJobs[t360::kStripMaxHy] = {};
-  DeviceBuffer<BlurJob> tileJobs, directJobs;
-  int numTileJobs = 0, numDirectJobs = 0, tileSmem = 0;
-  DeviceBuffer<float> taps;
-  // area down-scale after the gather (only when the scale factors are not 1)
-  bool resizeNeeded = false, resizeSupported = true;
-  int cellW = 0, cellH = 0;
-  DeviceBuffer<int2> areaXTaps, areaYTaps;
-  DeviceBuffer<int> areaXFirst, areaYFirst;
+  // low-pass: register-resident strip jobs grouped by vertical half-size 1..3, and the rest (large vertical kernels),
+  // for one plane size
+  struct BlurSet {
+    DeviceBuffer<StripJob> stripJobs[t360::kStripMaxHy];
+    int numStripJobs[t360::kStripMaxHy] = {};
+    DeviceBuffer<BlurJob> tileJobs, directJobs;
+    int numTileJobs = 0, numDirectJobs = 0, tileSmem = 0;
+    DeviceBuffer<float> taps;
+    bool needsClear = false;
+  };
+  BlurSet blur;  // for the plane size the plan was generated for
+  // (a caller may pass planes of another size: the reference then filters the segments that still fit, cpp:173-204)
+  std::vector<t360::LowPassSegment> segments;
+  std::vector<float> planTaps;
+  mutable std::map<std::pair<int, int>, BlurSet> otherBlurs;
+  // cv::resize(INTER_AREA) after the gather whenever the requested output size differs from the map's (reference
+  // cpp:735-737: decided per call): tables per output size, made on first use
+  struct Resize {
+    int cellW = 0, cellH = 0, xMax = 0;  // cellW > 0: integer ratios; < 0: the enlarging (bilinear) variant; 0: area tables
+    DeviceBuffer<int2> xTaps, yTaps, xLinear, yLinear;
+    DeviceBuffer<int> xFirst, yFirst;
+  };
+  bool resizeNeeded = false;  // for the size the map was generated for
+  mutable std::map<std::pair<int, int>, Resize> resizes;
   size_t deviceBytes() const {
-    return samples.bytes() + records.bytes() + gatherJobs.bytes() + stripJobs[0].bytes() + stripJobs[1].bytes() + stripJobs[2].bytes() + tileJobs.bytes() + directJobs.bytes() + taps.bytes();
+    return samples.bytes() + records.bytes() + gatherJobs.bytes() + blur.stripJobs[0].bytes() + blur.stripJobs[1].bytes() + blur.stripJobs[2].bytes() +
+           blur.tileJobs.bytes() + blur.directJobs.bytes() + blur.taps.bytes();
   }
 };
 
@@ -155,7 +169,8 @@ struct GatherWork {
   bool staged = false;                       // TMA-describable: may run in the persistent (per-plane / per-frame) kernel
   CUtensorMap maps[t360::kNumBoxClasses];
   uint8_t* finalOut = nullptr;               // where the area resize (if any) delivers
-  int finalPitch = 0, imagePlane = 0;
+  int finalPitch = 0, finalW = 0, finalH = 0, imagePlane = 0;
+  const void* resizeTables = nullptr;
 };
 
 // The tiles of all planes of a frame in one list (general, class 1, class 0; luma first inside each kind), rebuilt
@@ -308,8 +323,8 @@ class VideoFrameTransform {
 
   // ---- streaming a large host plane through the device -------------------------------------------------------
   bool pipelineEligible(const DevicePlan& plan, int inW, int inH, int outW, int outH) const {
-    return plan.totalStaged() > 0 && !plan.transparent && !plan.lowPass && !plan.resizeNeeded && inW == plan.inW && inH == plan.inH &&
-           outW == plan.outW && outH == plan.outH && static_cast<long long>(inW) * inH >= pipelineMinBytes_ && inH >= 64;
+    return plan.totalStaged() > 0 && !plan.transparent && !plan.lowPass && inW == plan.inW && inH == plan.inH &&
+           outW == plan.mapW && outH == plan.mapH && static_cast<long long>(inW) * inH >= pipelineMinBytes_ && inH >= 64;
   }
 
   WavePlan& wavePlanFor(const DevicePlan& plan, int planIndex, int chunks) {
@@ -673,8 +688,8 @@ class VideoFrameTransform {
     auto it = plans_.find(planIndex);
     if (it == plans_.end()) return false;
     counts[0] = it->second.totalStaged(); counts[1] = it->second.numFallback;
-    counts[2] = it->second.numStripJobs[0] + it->second.numStripJobs[1] + it->second.numStripJobs[2];
-    counts[3] = it->second.numTileJobs + it->second.numDirectJobs;
+    counts[2] = it->second.blur.numStripJobs[0] + it->second.blur.numStripJobs[1] + it->second.blur.numStripJobs[2];
+    counts[3] = it->second.blur.numTileJobs + it->second.blur.numDirectJobs;
     return true;
   }
   size_t planBytes(int planIndex) {
@@ -794,11 +809,42 @@ class VideoFrameTransform {
       d.jobNeedRows = std::move(g.jobNeedRows);
     }
     d.lowPass = ctx_.enable_low_pass_filter != 0;
-    if (d.lowPass) buildBlurJobs(h, d);
+    if (d.lowPass) {
+      d.segments = h.segments;
+      d.planTaps = h.taps;
+      buildBlurJobs(d.segments, d.planTaps, h.inW, h.inH, d.blur);
+    }
     d.resizeNeeded = h.resize.needed;
-    d.resizeSupported = h.resize.supported;
-    d.cellW = h.resize.cellW; d.cellH = h.resize.cellH;
-    if (d.resizeNeeded && d.resizeSupported && d.cellW == 0) {
+    if (d.resizeNeeded) resizeFor(d, d.outW, d.outH);
+    return d;
+  }
+
+  // the INTER_AREA tables from the plan's map size to outW x outH, on the device
+  const DevicePlan::Resize& resizeFor(const DevicePlan& plan, int outW, int outH) {
+    std::lock_guard<std::mutex> lock(lazyMu_);
+    auto it = plan.resizes.find({outW, outH});
+    if (it != plan.resizes.end()) return it->second;
+    t360::AreaResizePlan r;
+    t360::buildAreaResize(plan.mapW, plan.mapH, outW, outH, r);
+    DevicePlan::Resize& d = plan.resizes[{outW, outH}];
+    auto upload2 = [](const std::vector<int2>& v, DeviceBuffer<int2>& buf) {
+      buf.reserve(std::max<size_t>(v.size(), 1));
+      if (!v.empty()) CU(cudaMemcpy(buf.ptr, v.data(), v.size() * sizeof(int2), cudaMemcpyHostToDevice));
+    };
+    if (r.enlarge) {
+      d.cellW = d.cellH = -1;
+      d.xMax = r.lx.dmax;
+      auto pack = [](const t360::AreaLinearAxis& a) {
+        std::vector<int2> v(a.ofs.size());
+        for (size_t i = 0; i < a.ofs.size(); ++i)
+          v[i] = int2{a.ofs[i], static_cast<int>(static_cast<uint16_t>(a.coef[2 * i]) | (static_cast<uint32_t>(static_cast<uint16_t>(a.coef[2 * i + 1])) << 16))};
+        return v;
+      };
+      upload2(pack(r.lx), d.xLinear);
+      upload2(pack(r.ly), d.yLinear);
+    } else if (r.cellW > 0) {
+      d.cellW = r.cellW; d.cellH = r.cellH;
+    } else {
       auto uploadAxis = [&](const t360::AreaAxis& a, DeviceBuffer<int2>& taps, DeviceBuffer<int>& first) {
         std::vector<int2> packed(a.taps.size());
         for (size_t i = 0; i < a.taps.size(); ++i) {
@@ -806,20 +852,21 @@ class VideoFrameTransform {
           std::memcpy(&bits, &a.taps[i].alpha, sizeof(bits));
           packed[i] = int2{a.taps[i].src, bits};
         }
-        taps.reserve(packed.size());
-        CU(cudaMemcpy(taps.ptr, packed.data(), packed.size() * sizeof(int2), cudaMemcpyHostToDevice));
+        upload2(packed, taps);
         first.reserve(a.first.size());
         CU(cudaMemcpy(first.ptr, a.first.data(), a.first.size() * sizeof(int), cudaMemcpyHostToDevice));
       };
-      uploadAxis(h.resize.x, d.areaXTaps, d.areaXFirst);
-      uploadAxis(h.resize.y, d.areaYTaps, d.areaYFirst);
+      uploadAxis(r.x, d.xTaps, d.xFirst);
+      uploadAxis(r.y, d.yTaps, d.yFirst);
     }
     return d;
   }
 
   // Tiles of the plan, applied once (mono) or to both halves of a stereo frame (reference cpp:630-691), cut
   // into CTA-sized jobs.  Segments that do not fit the plane are dropped, like the reference's caught cv::Exception.
-  void buildBlurJobs(const HostPlan& h, DevicePlan& d) {
+  void buildBlurJobs(const std::vector<t360::LowPassSegment>& segments, const std::vector<float>& planTaps, int planeW, int planeH,
+                     DevicePlan::BlurSet& d) {
+    struct { const std::vector<t360::LowPassSegment>& segments; const std::vector<float>& taps; int inW, inH; } h{segments, planTaps, planeW, planeH};
     std::vector<BlurJob> tiles, direct;
     std::vector<StripJob> strips[t360::kStripMaxHy];
     std::vector<float> taps = h.taps;  // original taps first (offsets of the plan stay valid), padded copies appended
@@ -860,13 +907,20 @@ class VideoFrameTransform {
     for (int pass = 0; pass < passes; ++pass) {
       // segments of one band that are horizontally adjacent and carry bit-identical kernels (always the case when
       // the view-dependent scale is 1, e.g. no off-centre projection) are merged into one wide segment
+      // a segment that does not fit the plane is dropped, like the reference's caught cv::Exception (cpp:183-203) -- each
+      // one on its own, before any merging
+      auto fits = [&](const t360::LowPassSegment& g) {
+        const int l = g.left + offX[pass], t = g.top + offY[pass];
+        return l >= 0 && t >= 0 && g.width > 0 && g.height > 0 && l + g.width <= h.inW && t + g.height <= h.inH;
+      };
       size_t i = 0;
       while (i < h.segments.size()) {
         t360::LowPassSegment s = h.segments[i];
         size_t j = i + 1;
+        if (!fits(s)) { i = j; continue; }
         while (j < h.segments.size()) {
           const t360::LowPassSegment& n = h.segments[j];
-          if (n.top != s.top || n.height != s.height || n.left != s.left + s.width ||
+          if (n.top != s.top || n.height != s.height || n.left != s.left + s.width || !fits(n) ||
               !sameTaps(n.kxOffset, n.kxCount, s.kxOffset, s.kxCount) || !sameTaps(n.kyOffset, n.kyCount, s.kyOffset, s.kyCount))
             break;
           s.width += n.width;
@@ -874,8 +928,6 @@ class VideoFrameTransform {
         }
         i = j;
         const int left = s.left + offX[pass], top = s.top + offY[pass];
-        // a segment that does not fit the plane is dropped, like the reference's caught cv::Exception (cpp:183-203)
-        if (left < 0 || top < 0 || s.width <= 0 || s.height <= 0 || left + s.width > h.inW || top + s.height > h.inH) continue;
         for (int y = 0; y < s.height; ++y) std::memset(&covered[static_cast<size_t>(top + y) * h.inW + left], 1, s.width);
         const int hy = s.kyCount / 2;
         if (hy <= t360::kStripMaxHy && (s.kyCount & 1) && (s.kxCount & 1)) {
@@ -907,7 +959,7 @@ class VideoFrameTransform {
         }
       }
     }
-    d.blurNeedsClear = std::find(covered.begin(), covered.end(), 0) != covered.end();
+    d.needsClear = std::find(covered.begin(), covered.end(), 0) != covered.end();
     for (int c = 0; c < t360::kStripMaxHy; ++c) {
       // heaviest jobs first: the hardware block scheduler then balances the tail
       std::stable_sort(strips[c].begin(), strips[c].end(), [](const StripJob& a, const StripJob& b) {
@@ -935,24 +987,31 @@ class VideoFrameTransform {
     }
   }
 
+  // the low-pass jobs of a plan for planes of w x h (the planned size, or whatever the caller passes)
+  const DevicePlan::BlurSet& blurFor(const DevicePlan& plan, int w, int h) {
+    if (w == plan.inW && h == plan.inH) return plan.blur;
+    std::lock_guard<std::mutex> lock(lazyMu_);
+    auto it = plan.otherBlurs.find({w, h});
+    if (it != plan.otherBlurs.end()) return it->second;
+    DevicePlan::BlurSet& set = plan.otherBlurs[{w, h}];
+    buildBlurJobs(plan.segments, plan.planTaps, w, h, set);
+    return set;
+  }
+
   void runLowPass(const DevicePlan& plan, const uint8_t* dIn, uint8_t* dOut, int w, int h, int inPitch, int outPitch,
                   cudaStream_t s) {
-    if (plan.blurNeedsClear || w != plan.inW || h != plan.inH) CU(cudaMemset2DAsync(dOut, outPitch, 0, w, h, s));
-    if (w != plan.inW || h != plan.inH) {
-      // the tiles were laid out for other dimensions; the reference would filter whatever fits and leave the rest 0.
-      // Not reproduced tile by tile: refuse rather than silently differ.
-      throw std::runtime_error("plane size differs from the size the low-pass plan was generated for");
-    }
+    const DevicePlan::BlurSet& b = blurFor(plan, w, h);
+    if (b.needsClear) CU(cudaMemset2DAsync(dOut, outPitch, 0, w, h, s));  // reference cpp:625: Mat::zeros under dropped segments
     for (int c = 0; c < t360::kStripMaxHy; ++c) {
-      if (!plan.numStripJobs[c]) continue;
-      t360::StripParams sp{dIn, dOut, w, h, inPitch, outPitch, plan.stripJobs[c].ptr, plan.numStripJobs[c], plan.taps.ptr};
+      if (!b.numStripJobs[c]) continue;
+      t360::StripParams sp{dIn, dOut, w, h, inPitch, outPitch, b.stripJobs[c].ptr, b.numStripJobs[c], b.taps.ptr};
       CU(t360::launchBlurStrips(sp, c + 1, s));
     }
-    t360::BlurParams bp{dIn, dOut, w, h, inPitch, outPitch, plan.tileJobs.ptr, plan.numTileJobs, plan.taps.ptr, plan.tileSmem};
-    if (plan.numTileJobs) CU(t360::launchBlur(bp, s));
-    if (plan.numDirectJobs) {
-      bp.jobs = plan.directJobs.ptr;
-      bp.numJobs = plan.numDirectJobs;
+    t360::BlurParams bp{dIn, dOut, w, h, inPitch, outPitch, b.tileJobs.ptr, b.numTileJobs, b.taps.ptr, b.tileSmem};
+    if (b.numTileJobs) CU(t360::launchBlur(bp, s));
+    if (b.numDirectJobs) {
+      bp.jobs = b.directJobs.ptr;
+      bp.numJobs = b.numDirectJobs;
       CU(t360::launchBlurDirect(bp, s));
     }
   }
@@ -977,24 +1036,19 @@ class VideoFrameTransform {
       std::printf("Could not find interpolation algorithm for plane %d", imagePlaneIndex);  // reference cpp:780-784
       return true;
     }
-    if (outW != plan.outW || outH != plan.outH) {
-      std::printf("Could not transform the plane %d. Error: output %dx%d differs from the %dx%d the map was generated for\n",
-                  imagePlaneIndex, outW, outH, plan.outW, plan.outH);
-      return false;
-    }
-    // reference cpp:735-737, 755-777: when the map was planned at a scaled size, render at that size into a plane
-    // pre-filled with 0 (luma) / 128 (chroma), then cv::resize(INTER_AREA) down to the requested size
+    // reference cpp:735-737, 755-777: whenever the requested output size is not the map's (scale factors, or a caller
+    // that asks for another size than it planned), render at the map's size into a plane pre-filled with 0 (plan index
+    // 0) / 128 (others), then cv::resize(INTER_AREA) to the requested size
     w.finalOut = dOut;
     w.finalPitch = outPitch;
-    if (plan.resizeNeeded) {
-      if (!plan.resizeSupported) {
-        std::printf("Could not transform the plane %d. Error: scale factors below 1 (INTER_AREA enlarging) are not supported\n",
-                    imagePlaneIndex);
-        return false;
-      }
+    w.finalW = outW;
+    w.finalH = outH;
+    w.resizeTables = nullptr;
+    if (outW != plan.mapW || outH != plan.mapH) {
+      w.resizeTables = &resizeFor(plan, outW, outH);
       const int sp = alignedPitch(plan.mapW);
       lane.scaled.reserve(static_cast<size_t>(sp) * plan.mapH + 64);
-      if (plan.transparent) CU(cudaMemset2DAsync(lane.scaled.ptr, sp, imagePlaneIndex ? 128 : 0, plan.mapW, plan.mapH, s));
+      if (plan.transparent) CU(cudaMemset2DAsync(lane.scaled.ptr, sp, planIndexOf(plan) ? 128 : 0, plan.mapW, plan.mapH, s));
       dOut = lane.scaled.ptr;
       outPitch = sp;
       outW = plan.mapW;
@@ -1086,14 +1140,23 @@ class VideoFrameTransform {
   // What follows the gather: the INTER_AREA down-scale when the map was rendered at a scaled size.
   void finishGather(const GatherWork& w, cudaStream_t s) {
     const DevicePlan& plan = *w.plan;
-    if (!plan.resizeNeeded) return;
-    t360::AreaParams ap{w.view.dst, w.finalOut, plan.mapW, plan.mapH, w.view.dstPitch, plan.outW, plan.outH, w.finalPitch,
-                        plan.cellW, plan.cellH, plan.areaXTaps.ptr, plan.areaXFirst.ptr, plan.areaYTaps.ptr, plan.areaYFirst.ptr};
+    if (!w.resizeTables) return;
+    const DevicePlan::Resize& r = *static_cast<const DevicePlan::Resize*>(w.resizeTables);
+    t360::AreaParams ap{w.view.dst, w.finalOut, plan.mapW, plan.mapH, w.view.dstPitch, w.finalW, w.finalH, w.finalPitch,
+                        r.cellW, r.cellH, r.xTaps.ptr, r.xFirst.ptr, r.yTaps.ptr, r.yFirst.ptr, r.xLinear.ptr, r.yLinear.ptr, r.xMax};
     CU(t360::launchAreaResize(ap, s));
+  }
+
+  int planIndexOf(const DevicePlan& plan) {  // the transformMatPlaneIndex a plan was generated for
+    std::lock_guard<std::mutex> lock(mu_);
+    for (auto& kv : plans_)
+      if (&kv.second == &plan) return kv.first;
+    return 0;
   }
 
   FrameTransformContext ctx_;
   std::mutex mu_;
+  std::mutex lazyMu_;  // per-size tables made on first use (resizeFor, blurFor)
   std::map<int, DevicePlan> plans_;
   DeviceBuffer<int16_t> weights_[9];       // OpenCV's tables [1024][k][k] (general kernels), by kernel size
   DeviceBuffer<uint8_t> weightImages_[9];  // their shared-memory images for the frame kernel
