@@ -51,7 +51,8 @@ int T360B200_remapTable(int interpolationAlg, const int16_t** table);
 /* ---- device-resident / asynchronous entry points ----------------------------------------------- */
 /* Same contract as VideoFrameTransform_transformFramePlane, but both planes are CUDA device pointers,
  * the work is enqueued on `cudaStream` (a cudaStream_t; NULL = the transform's own stream) and the call
- * returns without synchronising.  Returns 1 if everything was enqueued. */
+ * returns without synchronising.  Returns 1 if everything was enqueued.  Scratch planes and job schedulers are kept
+ * per stream: work on one stream is ordered, different streams (also from different host threads) do not interfere. */
 int T360B200_transformFramePlaneAsync(VideoFrameTransform* transform, const uint8_t* deviceInput,
                                       uint8_t* deviceOutput, int inputWidth, int inputHeight, int inputPitch,
                                       int outputWidth, int outputHeight, int outputPitch,
@@ -60,8 +61,8 @@ int T360B200_transformFramePlaneAsync(VideoFrameTransform* transform, const uint
  * planes 1 and 2 plan index 1 (the reference filter's convention, vf_transform360.c:372).  The low-pass stages of the
  * planes run side by side (chroma on internal streams); one gather launch then takes the tiles of every plane;
  * `cudaStream` observes the completion of all of it.  Arrays have numPlanes (1..3) entries: device pointers, per-plane
- * widths / heights / pitches in bytes.  Not re-entrant per transform (scratch planes and the tile scheduler are
- * per transform): enqueue the frames of one transform from one thread. */
+ * widths / heights / pitches in bytes.  Scratch planes and schedulers are per stream (see above); generateMapForPlane
+ * must not run concurrently with frames in flight. */
 int T360B200_transformFrameAsync(VideoFrameTransform* transform, int numPlanes, const uint8_t* const* deviceInputs,
                                  uint8_t* const* deviceOutputs, const int* inputWidths, const int* inputHeights,
                                  const int* inputPitches, const int* outputWidths, const int* outputHeights,

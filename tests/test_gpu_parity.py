@@ -566,3 +566,41 @@ def test_sizes_that_differ_from_the_generated_map(name, out2, in2, torch_cuda):
     want = co.transform_plane(octx, plan, src, out2[0], out2[1])
     assert np.array_equal(got, want), f"{(got != want).sum()} px differ"
     assert np.array_equal(again, got)
+
+
+def test_async_entry_points_on_several_streams(torch_cuda):
+    """Per-plane and whole-frame asynchronous calls interleaved on three streams (scratch planes and job schedulers are
+    kept per stream): every output still matches the oracle."""
+    torch = torch_cuda
+    from transform360_b200.stream import FrameTransformer, StreamSpec
+    case = SMALL["lp_tiles"]
+    ctx, octx = _ctxs(case)
+    spec = StreamSpec(case["inp"][0], case["inp"][1], case["out"][0], case["out"][1])
+    ft = FrameTransformer(ctx, spec)
+    pitch = lambda w: (w + 255) // 256 * 256
+    plans = {idx: co.OraclePlan(octx, *spec.plane_dims(p)[:4]) for p, idx in ((0, 0), (1, 1))}
+    streams = [torch.cuda.Stream() for _ in range(3)]
+    dims = [spec.plane_dims(p)[:4] for p in range(3)]
+    work = []
+    for f in range(9):
+        srcs = [co.noise_plane(*spec.plane_dims(p)[:2], plane=p, frame=f) for p in range(3)]
+        d_in = [_pitched(torch, srcs[p], pitch(spec.plane_dims(p)[0])) for p in range(3)]
+        d_out = [torch.zeros((spec.plane_dims(p)[3], pitch(spec.plane_dims(p)[2])), dtype=torch.uint8, device="cuda") for p in range(3)]
+        work.append((srcs, d_in, d_out))
+    torch.cuda.synchronize()
+    for f, (srcs, d_in, d_out) in enumerate(work):
+        st = streams[f % 3].cuda_stream
+        if f % 2:
+            call = ft.vft.make_frame_call([(t.data_ptr(), t.stride(0)) for t in d_in], [(t.data_ptr(), t.stride(0)) for t in d_out], dims)
+            assert call(st)
+        else:
+            for p in range(3):
+                iw, ih, ow, oh, idx = spec.plane_dims(p)
+                assert ft.vft.transform_plane_async(d_in[p].data_ptr(), d_out[p].data_ptr(), iw, ih, d_in[p].stride(0), ow, oh, d_out[p].stride(0), idx, st)
+    torch.cuda.synchronize()
+    for f, (srcs, d_in, d_out) in enumerate(work):
+        for p in range(3):
+            iw, ih, ow, oh, idx = spec.plane_dims(p)
+            want = co.transform_plane(octx, plans[idx], srcs[p], ow, oh, map_index=idx)
+            assert np.array_equal(d_out[p][:, :ow].cpu().numpy(), want), f"frame {f} plane {p}"
+    ft.close()

@@ -195,6 +195,15 @@ struct WavePlan {
   std::vector<std::vector<Rect>> rects;
 };
 
+// Everything asynchronous work on ONE caller stream shares: the lanes (scratch planes, side streams, job schedulers) and
+// the scheduler of the whole-frame launch.  Work on the same stream is ordered, so one set per stream is enough; callers
+// that enqueue on several streams at once get a set per stream instead of racing for one.
+struct StreamSlot {
+  PlaneLane lanes[kPlaneLanes];
+  DeviceBuffer<int> frameClaim;
+  cudaEvent_t fork = nullptr;
+};
+
 constexpr int kPitchAlign = 256;
 inline int alignedPitch(int w) { return (w + kPitchAlign - 1) / kPitchAlign * kPitchAlign; }
 
@@ -221,17 +230,20 @@ class VideoFrameTransform {
       stagingIn_.release(); stagingOut_.release();
       for (HostRange& r : hostRanges_)
         if (r.pinned) cudaHostUnregister(reinterpret_cast<void*>(r.base));
-      for (PlaneLane& l : lanes_) {
-        l.blurred.release();
-        l.scaled.release();
-        l.claimCounter.release();
-        if (l.main) cudaStreamDestroy(l.main);
-        if (l.done) cudaEventDestroy(l.done);
+      for (auto& kv : slots_) {
+        for (PlaneLane& l : kv.second->lanes) {
+          l.blurred.release();
+          l.scaled.release();
+          l.claimCounter.release();
+          if (l.main) cudaStreamDestroy(l.main);
+          if (l.done) cudaEventDestroy(l.done);
+        }
+        kv.second->frameClaim.release();
+        if (kv.second->fork) cudaEventDestroy(kv.second->fork);
       }
       frameJobs_.tiles.release();
       trace_.release();
       frameJobs_.claimCounter.release();
-      if (frameFork_) cudaEventDestroy(frameFork_);
       for (cudaEvent_t e : chunkIn_) cudaEventDestroy(e);
       for (cudaEvent_t e : waveDone_) cudaEventDestroy(e);
       for (WavePlan& w : wavePlans_) w.jobs.release();
@@ -248,7 +260,7 @@ class VideoFrameTransform {
     try {
       HostPlan host;
       if (!t360::buildHostPlan(ctx_, inW, inH, outW, outH, host)) return false;
-      ensureDevice();
+      const DeviceRestore restoreDevice = ensureDevice();
       std::lock_guard<std::mutex> lock(mu_);
       plans_[planIndex] = upload(host);
       ++planGeneration_;
@@ -270,7 +282,7 @@ class VideoFrameTransform {
         std::printf("Could not transform the plane %d. Error: invalid plane description\n", imagePlaneIndex);
         return false;
       }
-      ensureDevice();
+      const DeviceRestore restoreDevice = ensureDevice();
       const bool inOnDevice = isDevicePointer(in), outOnDevice = isDevicePointer(out);
       const DevicePlan* plan = findPlan(planIndex, imagePlaneIndex);
       if (!plan) return false;
@@ -306,7 +318,7 @@ class VideoFrameTransform {
       } else if (plan->transparent && planIndex) {
         CU(cudaMemset2DAsync(dOut, dOutPitch, 128, outW, outH, stream_));
       }
-      if (!enqueue(*plan, dIn, dOut, inW, inH, dInPitch, outW, outH, dOutPitch, stream_, imagePlaneIndex, lanes_[0])) return false;
+      if (!enqueue(*plan, dIn, dOut, inW, inH, dInPitch, outW, outH, dOutPitch, stream_, imagePlaneIndex, slotFor(stream_).lanes[0])) return false;
       if (!outOnDevice)
         CU(cudaMemcpy2DAsync(out, outPitch, dOut, dOutPitch, outW, outH, cudaMemcpyDeviceToHost, stream_));
       CU(cudaStreamSynchronize(stream_));
@@ -415,17 +427,18 @@ class VideoFrameTransform {
     const int dInPitch = alignedPitch(inW), dOutPitch = alignedPitch(outW);
     stagingIn_.reserve(static_cast<size_t>(dInPitch) * inH + 64);
     stagingOut_.reserve(static_cast<size_t>(dOutPitch) * outH + 64);
+    PlaneLane& hostLane = slotFor(stream_).lanes[0];
     GatherWork work;
-    if (!prepareGather(plan, stagingIn_.ptr, stagingOut_.ptr, inW, inH, dInPitch, outW, outH, dOutPitch, stream_, imagePlaneIndex, lanes_[0], work))
+    if (!prepareGather(plan, stagingIn_.ptr, stagingOut_.ptr, inW, inH, dInPitch, outW, outH, dOutPitch, stream_, imagePlaneIndex, hostLane, work))
       return false;
     if (!work.staged) {  // the plane cannot be described to the TMA unit after all: plain path
       CU(cudaMemcpy2DAsync(stagingIn_.ptr, dInPitch, in, inPitch, inW, inH, cudaMemcpyHostToDevice, stream_));
-      gatherPlane(work, lanes_[0], stream_);
+      gatherPlane(work, hostLane, stream_);
       CU(cudaMemcpy2DAsync(out, outPitch, stagingOut_.ptr, dOutPitch, outW, outH, cudaMemcpyDeviceToHost, stream_));
       CU(cudaStreamSynchronize(stream_));
       return true;
     }
-    armScheduler(lanes_[0].claimCounter, stream_);
+    armScheduler(hostLane.claimCounter, stream_);
     CU(t360::prepareGatherFrame(plan.kernelSize));
     auto issue = [&](bool forkJoin) {
       if (forkJoin) {  // (capture: the side streams become branches of the graph)
@@ -447,7 +460,7 @@ class VideoFrameTransform {
         CU(cudaStreamWaitEvent(stream_, chunkIn_[c], 0));
         const int n = w.waveStart[c + 1] - w.waveStart[c];
         if (n > 0) {
-          t360::StagedParams jobs{w.jobs.ptr + w.waveStart[c], n, lanes_[0].claimCounter.ptr, nullptr};
+          t360::StagedParams jobs{w.jobs.ptr + w.waveStart[c], n, hostLane.claimCounter.ptr, nullptr};
           CU(t360::launchGatherFrame(fp, jobs, work.maps, numSMs_, stream_, /*programmatic=*/false));
         }
         if (!w.rects[c].empty()) {
@@ -485,7 +498,7 @@ class VideoFrameTransform {
         CU(cudaStreamWaitEvent(stream_, ev[3 * c], 0));
         const int n = w.waveStart[c + 1] - w.waveStart[c];
         if (n > 0) {
-          t360::StagedParams jobs{w.jobs.ptr + w.waveStart[c], n, lanes_[0].claimCounter.ptr, nullptr};
+          t360::StagedParams jobs{w.jobs.ptr + w.waveStart[c], n, hostLane.claimCounter.ptr, nullptr};
           CU(t360::launchGatherFrame(fp, jobs, work.maps, numSMs_, stream_, false));
         }
         CU(cudaEventRecord(ev[3 * c + 1], stream_));
@@ -567,12 +580,12 @@ class VideoFrameTransform {
   bool transformDevice(const uint8_t* dIn, uint8_t* dOut, int inW, int inH, int inPitch, int outW, int outH,
                        int outPitch, int planIndex, cudaStream_t stream) {
     try {
-      ensureDevice();
+      const DeviceRestore restoreDevice = ensureDevice();
       const DevicePlan* plan = findPlan(planIndex, planIndex);
       if (!plan) return false;
       cudaStream_t s = stream ? stream : stream_;
       if (plan->transparent && planIndex) CU(cudaMemset2DAsync(dOut, outPitch, 128, outW, outH, s));
-      return enqueue(*plan, dIn, dOut, inW, inH, inPitch, outW, outH, outPitch, s, planIndex, lanes_[0]);
+      return enqueue(*plan, dIn, dOut, inW, inH, inPitch, outW, outH, outPitch, s, planIndex, slotFor(s).lanes[0]);
     } catch (const CudaFail& f) {
       std::printf("Could not transform the plane %d. Error: CUDA %s (%s) in %s\n", planIndex, cudaGetErrorName(f.err),
                   cudaGetErrorString(f.err), f.what);
@@ -592,8 +605,11 @@ class VideoFrameTransform {
         std::printf("Could not transform the frame. Error: %d planes (1..%d supported)\n", numPlanes, kPlaneLanes);
         return false;
       }
-      ensureDevice();
+      const DeviceRestore restoreDevice = ensureDevice();
       cudaStream_t s = stream ? stream : stream_;
+      StreamSlot& slot = slotFor(s);
+      PlaneLane* lanes_ = slot.lanes;
+      cudaEvent_t frameFork_ = slot.fork;
       const DevicePlan* plans[kPlaneLanes];
       bool sideWork = false;  // does any chroma plane have work before its gather (low-pass, pre-fill)?
       for (int p = 0; p < numPlanes; ++p) {
@@ -620,7 +636,7 @@ class VideoFrameTransform {
             CU(cudaEventRecord(lanes_[p].done, lanes_[p].main));
             CU(cudaStreamWaitEvent(s, lanes_[p].done, 0));
           }
-        gatherFrame(work, numPlanes, s);
+        gatherFrame(work, numPlanes, s, slot);
         for (int p = 0; p < numPlanes; ++p) finishGather(work[p], s);
         return true;
       }
@@ -649,7 +665,7 @@ class VideoFrameTransform {
   bool lowPassDevice(const uint8_t* dIn, uint8_t* dOut, int w, int h, int inPitch, int outPitch, int planIndex,
                      cudaStream_t stream) {
     try {
-      ensureDevice();
+      const DeviceRestore restoreDevice = ensureDevice();
       const DevicePlan* plan = findPlan(planIndex, planIndex);
       if (!plan) return false;
       if (!plan->lowPass) {
@@ -680,7 +696,7 @@ class VideoFrameTransform {
     return cudaStreamSynchronize(stream_) == cudaSuccess;
   }
   cudaStream_t stream() {
-    try { ensureDevice(); } catch (...) { return nullptr; }
+    try { const DeviceRestore restoreDevice = ensureDevice(); } catch (...) { return nullptr; }
     return stream_;
   }
   bool tileCounts(int planIndex, int counts[4]) {
@@ -699,10 +715,41 @@ class VideoFrameTransform {
   }
 
  private:
-  void ensureDevice() {
+  StreamSlot& slotFor(cudaStream_t s) {
+    std::lock_guard<std::mutex> lock(slotMu_);
+    std::unique_ptr<StreamSlot>& slot = slots_[s];
+    if (!slot) {
+      slot.reset(new StreamSlot);
+      for (int i = 0; i < kPlaneLanes; ++i) {
+        PlaneLane& l = slot->lanes[i];
+        if (i > 0) CU(cudaStreamCreateWithFlags(&l.main, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&l.done, cudaEventDisableTiming));
+      }
+      CU(cudaEventCreateWithFlags(&slot->fork, cudaEventDisableTiming));
+    }
+    return *slot;
+  }
+
+  // The transform lives on the device that was current when it first touched CUDA.  Calls from a thread whose current
+  // device is another one switch to it for their duration and switch back (the guard), like a library should.
+  struct DeviceRestore {
+    int previous = -1;
+    DeviceRestore() = default;
+    DeviceRestore(const DeviceRestore&) = delete;
+    DeviceRestore& operator=(const DeviceRestore&) = delete;
+    DeviceRestore(DeviceRestore&& o) noexcept : previous(o.previous) { o.previous = -1; }
+    ~DeviceRestore() { if (previous >= 0) cudaSetDevice(previous); }
+  };
+  DeviceRestore ensureDevice() {
+    DeviceRestore guard;
     if (deviceReady_) {
-      CU(cudaSetDevice(device_));
-      return;
+      int current = device_;
+      CU(cudaGetDevice(&current));
+      if (current != device_) {
+        CU(cudaSetDevice(device_));
+        guard.previous = current;
+      }
+      return guard;
     }
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
@@ -712,13 +759,8 @@ class VideoFrameTransform {
     CU(cudaGetDeviceProperties(&prop, device_));
     numSMs_ = prop.multiProcessorCount;
     CU(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
-    for (int i = 0; i < kPlaneLanes; ++i) {
-      PlaneLane& l = lanes_[i];
-      if (i > 0) CU(cudaStreamCreateWithFlags(&l.main, cudaStreamNonBlocking));
-      CU(cudaEventCreateWithFlags(&l.done, cudaEventDisableTiming));
-    }
-    CU(cudaEventCreateWithFlags(&frameFork_, cudaEventDisableTiming));
     deviceReady_ = true;
+    return guard;
   }
 
   // Pageable host planes are copied through the driver's bounce buffers at a fraction of PCIe speed.  When enabled
@@ -1100,8 +1142,9 @@ class VideoFrameTransform {
   }
 
   // The gathers of all planes of a frame as ONE launch (every plane staged).
-  void gatherFrame(const GatherWork* work, int numPlanes, cudaStream_t s) {
+  void gatherFrame(const GatherWork* work, int numPlanes, cudaStream_t s, StreamSlot& slot) {
     FrameJobList& f = frameJobs_;
+    std::unique_lock<std::mutex> listLock(frameJobsMu_);
     if (f.generation != planGeneration_ || f.numPlanes != numPlanes) {
       std::vector<GatherJob> merged;
       for (int kind : {t360::kJobGeneral, t360::kJobSeam, t360::kJobClass1, t360::kJobShareStay, t360::kJobShare, t360::kJobClass0})
@@ -1112,14 +1155,15 @@ class VideoFrameTransform {
             merged.push_back(t);
           }
       t360::spreadGeneralJobs(merged);
-      CU(cudaStreamSynchronize(s));  // a previous frame may still be reading the old list
+      CU(cudaDeviceSynchronize());  // a previous frame (on any stream) may still be reading the old list
       f.tiles.reserve(merged.size());
       CU(cudaMemcpy(f.tiles.ptr, merged.data(), merged.size() * sizeof(GatherJob), cudaMemcpyHostToDevice));
       f.numTiles = static_cast<int>(merged.size());
       f.numPlanes = numPlanes;
       f.generation = planGeneration_;
     }
-    armScheduler(f.claimCounter, s);
+    listLock.unlock();
+    armScheduler(slot.frameClaim, s);
     t360::FrameGatherParams fp{};
     CUtensorMap maps[kPlaneLanes][t360::kNumBoxClasses];
     for (int p = 0; p < numPlanes; ++p) {
@@ -1133,7 +1177,7 @@ class VideoFrameTransform {
       trace_.reserve(static_cast<size_t>(numSMs_) * t360::gatherGroups(work[0].plan->kernelSize) * t360::kTraceJobsPerGroup * 4);
       CU(cudaMemsetAsync(trace_.ptr, 0, trace_.bytes(), s));
     }
-    t360::StagedParams jobs{f.tiles.ptr, f.numTiles, f.claimCounter.ptr, traceEnabled_ ? trace_.ptr : nullptr};
+    t360::StagedParams jobs{f.tiles.ptr, f.numTiles, slot.frameClaim.ptr, traceEnabled_ ? trace_.ptr : nullptr};
     CU(t360::launchGatherFrame(fp, jobs, maps, numSMs_, s));
   }
 
@@ -1183,12 +1227,13 @@ class VideoFrameTransform {
   struct HostRange { uintptr_t base; size_t bytes; int seen; bool pinned; };
   std::vector<HostRange> hostRanges_;
   bool pinHostPlanes_ = false;
-  PlaneLane lanes_[kPlaneLanes];
+  std::mutex slotMu_;
+  std::map<cudaStream_t, std::unique_ptr<StreamSlot>> slots_;
   FrameJobList frameJobs_;
+  std::mutex frameJobsMu_;
   DeviceBuffer<unsigned long long> trace_;
   bool traceEnabled_ = false;
   unsigned long long planGeneration_ = 0;
-  cudaEvent_t frameFork_ = nullptr;
   cudaStream_t stream_ = nullptr;
   int device_ = 0, numSMs_ = 0;
   bool deviceReady_ = false;
