@@ -301,11 +301,37 @@ __device__ __forceinline__ void stripBody(const StripParams& p, const StripJob& 
 }
 
 template <int HY>
-__global__ void __launch_bounds__(128, 3) blurStripKernel(StripParams p) {
+#ifndef T360_BLUR_PDL
+#define T360_BLUR_PDL 0
+#endif
+#ifndef T360_BLUR_MINBLOCKS
+#define T360_BLUR_MINBLOCKS 6  // 85 registers: 130.3 us per cfg3 frame against 137.9 at 3 blocks (128 registers)
+#endif
+__global__ void __launch_bounds__(128, T360_BLUR_MINBLOCKS) blurStripKernel(StripParams p) {
   const int job = blockIdx.x * 4 + (threadIdx.x >> 5);
   if (job >= p.numJobs) return;
   const StripJob j = p.jobs[job];
   if (j.edge) stripBody<HY, true>(p, j, threadIdx.x & 31);
+  else stripBody<HY, false>(p, j, threadIdx.x & 31);
+}
+
+template <int HY>
+__global__ void __launch_bounds__(128, T360_BLUR_MINBLOCKS) blurFrameStripKernel(const __grid_constant__ FrameStripParams fp) {
+#if T360_BLUR_PDL
+  // the frame gather that follows on the stream may place its CTAs on SMs this grid has already left and run its
+  // prologue there (it waits for this grid's completion before it touches the planes)
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+  const int job = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (job >= fp.numJobs) return;
+  const StripJob j = fp.jobs[job];
+  const int pl = j.edge >> kStripPlaneShift;
+  const FrameStripParams::Plane &a = fp.plane[0], &b = fp.plane[1], &c = fp.plane[2];
+#define T360_PICK(f) (pl == 0 ? a.f : (pl == 1 ? b.f : c.f))
+  const StripParams p{T360_PICK(src), T360_PICK(dst), T360_PICK(width), T360_PICK(height), T360_PICK(srcPitch), T360_PICK(dstPitch),
+                      fp.jobs, fp.numJobs, fp.taps};
+#undef T360_PICK
+  if (j.edge & 1) stripBody<HY, true>(p, j, threadIdx.x & 31);
   else stripBody<HY, false>(p, j, threadIdx.x & 31);
 }
 
@@ -449,6 +475,19 @@ cudaError_t launchBlurStrips(const StripParams& p, int hy, cudaStream_t stream) 
     case 0: case 1: blurStripKernel<1><<<grid, 128, 0, stream>>>(p); break;  // hy == 0: one tap, padded with two zeros
     case 2: blurStripKernel<2><<<grid, 128, 0, stream>>>(p); break;
     case 3: blurStripKernel<3><<<grid, 128, 0, stream>>>(p); break;
+    default: return cudaErrorInvalidValue;
+  }
+  gLaunches.fetch_add(1, std::memory_order_relaxed);
+  return cudaGetLastError();
+}
+
+cudaError_t launchBlurFrameStrips(const FrameStripParams& p, int hy, cudaStream_t stream) {
+  if (p.numJobs <= 0) return cudaSuccess;
+  const int grid = (p.numJobs + 3) / 4;
+  switch (hy) {
+    case 0: case 1: blurFrameStripKernel<1><<<grid, 128, 0, stream>>>(p); break;
+    case 2: blurFrameStripKernel<2><<<grid, 128, 0, stream>>>(p); break;
+    case 3: blurFrameStripKernel<3><<<grid, 128, 0, stream>>>(p); break;
     default: return cudaErrorInvalidValue;
   }
   gLaunches.fetch_add(1, std::memory_order_relaxed);

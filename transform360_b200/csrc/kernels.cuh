@@ -225,6 +225,21 @@ struct AreaParams {
 };
 cudaError_t launchAreaResize(const AreaParams& p, cudaStream_t stream);
 
+// The strip jobs of all planes of a frame in ONE launch (StripJob::edge carries the plane in bits 8-9; kxOffset / kyOffset
+// index the merged tap buffer): one launch and one tail instead of three launches on three streams.
+struct FrameStripParams {
+  struct Plane {
+    const uint8_t* src;
+    uint8_t* dst;
+    int width, height, srcPitch, dstPitch;
+  } plane[kMaxFramePlanes];
+  const StripJob* jobs;
+  int numJobs;
+  const float* taps;
+};
+constexpr int kStripPlaneShift = 8;
+cudaError_t launchBlurFrameStrips(const FrameStripParams& p, int hy, cudaStream_t stream);
+
 constexpr int kStripLanePx = 8, kStripW = 32 * kStripLanePx, kStripMaxHy = 3;
 
 constexpr int kBlurTileW = 64, kBlurTileH = 32;

@@ -96,6 +96,8 @@ struct DevicePlan {
     int numTileJobs = 0, numDirectJobs = 0, tileSmem = 0;
     DeviceBuffer<float> taps;
     bool needsClear = false;
+    std::vector<StripJob> hostStrips[t360::kStripMaxHy];  // (the whole-frame entry point merges the planes' strip jobs)
+    std::vector<float> hostTaps;
   };
   BlurSet blur;  // for the plane size the plan was generated for
   // (a caller may pass planes of another size: the reference then filters the segments that still fit, cpp:173-204)
@@ -204,6 +206,15 @@ struct StreamSlot {
   cudaEvent_t fork = nullptr;
 };
 
+// The strip jobs of all planes of a frame, by vertical half-size, with one merged tap buffer (rebuilt when a map is).
+struct FrameBlurList {
+  DeviceBuffer<StripJob> jobs[t360::kStripMaxHy];
+  int numJobs[t360::kStripMaxHy] = {};
+  DeviceBuffer<float> taps;
+  int numPlanes = 0;
+  unsigned long long generation = ~0ull;
+};
+
 constexpr int kPitchAlign = 256;
 inline int alignedPitch(int w) { return (w + kPitchAlign - 1) / kPitchAlign * kPitchAlign; }
 
@@ -242,6 +253,8 @@ class VideoFrameTransform {
         if (kv.second->fork) cudaEventDestroy(kv.second->fork);
       }
       frameJobs_.tiles.release();
+      for (auto& b : frameBlur_.jobs) b.release();
+      frameBlur_.taps.release();
       trace_.release();
       frameJobs_.claimCounter.release();
       for (cudaEvent_t e : chunkIn_) cudaEventDestroy(e);
@@ -612,10 +625,15 @@ class VideoFrameTransform {
       cudaEvent_t frameFork_ = slot.fork;
       const DevicePlan* plans[kPlaneLanes];
       bool sideWork = false;  // does any chroma plane have work before its gather (low-pass, pre-fill)?
+      bool anyTransparent = false;
       for (int p = 0; p < numPlanes; ++p) {
         if (!(plans[p] = findPlan(p ? 1 : 0, p))) return false;
         if (p) sideWork = sideWork || plans[p]->lowPass || plans[p]->transparent;
+        anyTransparent = anyTransparent || plans[p]->transparent;
       }
+      // Low-pass of all planes in one launch per vertical kernel size when every plane takes the strip kernel only
+      const bool mergedBlur = !anyTransparent && blurFrame(plans, numPlanes, dIn, inW, inH, inPitch, lanes_, s);
+      if (mergedBlur) sideWork = false;
       // Stage 1, planes side by side (chroma on its own lanes): everything before the gather.
       const bool fork = numPlanes > 1 && sideWork;
       if (fork) CU(cudaEventRecord(frameFork_, s));
@@ -625,7 +643,7 @@ class VideoFrameTransform {
         cudaStream_t ps = (p && fork) ? lanes_[p].main : s;
         if (p && fork) CU(cudaStreamWaitEvent(ps, frameFork_, 0));
         if (plans[p]->transparent && p) CU(cudaMemset2DAsync(dOut[p], outPitch[p], 128, outW[p], outH[p], ps));
-        if (!prepareGather(*plans[p], dIn[p], dOut[p], inW[p], inH[p], inPitch[p], outW[p], outH[p], outPitch[p], ps, p, lanes_[p], work[p]))
+        if (!prepareGather(*plans[p], dIn[p], dOut[p], inW[p], inH[p], inPitch[p], outW[p], outH[p], outPitch[p], ps, p, lanes_[p], work[p], mergedBlur))
           return false;
         allStaged = allStaged && work[p].staged;
       }
@@ -1008,6 +1026,7 @@ class VideoFrameTransform {
         return static_cast<long long>(a.kxChunks + 2) * a.h * (1 + 3 * a.edge) > static_cast<long long>(b.kxChunks + 2) * b.h * (1 + 3 * b.edge);
       });
       d.numStripJobs[c] = static_cast<int>(strips[c].size());
+      d.hostStrips[c] = strips[c];
       if (strips[c].empty()) continue;
       d.stripJobs[c].reserve(strips[c].size());
       CU(cudaMemcpy(d.stripJobs[c].ptr, strips[c].data(), strips[c].size() * sizeof(StripJob), cudaMemcpyHostToDevice));
@@ -1023,6 +1042,7 @@ class VideoFrameTransform {
       d.directJobs.reserve(direct.size());
       CU(cudaMemcpy(d.directJobs.ptr, direct.data(), direct.size() * sizeof(BlurJob), cudaMemcpyHostToDevice));
     }
+    d.hostTaps = taps;
     if (!taps.empty()) {
       d.taps.reserve(taps.size());
       CU(cudaMemcpy(d.taps.ptr, taps.data(), taps.size() * sizeof(float), cudaMemcpyHostToDevice));
@@ -1071,7 +1091,7 @@ class VideoFrameTransform {
 
   // Everything before the gather of one plane: argument checks, the render target, the low-pass stage.
   bool prepareGather(const DevicePlan& plan, const uint8_t* dIn, uint8_t* dOut, int inW, int inH, int inPitch, int outW,
-                     int outH, int outPitch, cudaStream_t s, int imagePlaneIndex, PlaneLane& lane, GatherWork& w) {
+                     int outH, int outPitch, cudaStream_t s, int imagePlaneIndex, PlaneLane& lane, GatherWork& w, bool blurDone = false) {
     w.plan = &plan;
     w.imagePlane = imagePlaneIndex;
     if (plan.kernelSize == 0) {
@@ -1101,7 +1121,7 @@ class VideoFrameTransform {
     if (plan.lowPass) {
       const int bp = alignedPitch(inW);
       lane.blurred.reserve(static_cast<size_t>(bp) * inH + 64);
-      runLowPass(plan, dIn, lane.blurred.ptr, inW, inH, inPitch, bp, s);
+      if (!blurDone) runLowPass(plan, dIn, lane.blurred.ptr, inW, inH, inPitch, bp, s);
       src = lane.blurred.ptr;
       srcPitch = bp;
     }
@@ -1139,6 +1159,68 @@ class VideoFrameTransform {
                             weights_[plan.kernelSize].ptr, plan.kernelSize, plan.transparent ? 1 : 0};
       CU(t360::launchGather(gp, numSMs_, s));
     }
+  }
+
+  // The low-pass of all planes of a frame: one launch per vertical kernel half-size.  false: not applicable (a plane
+  // without low-pass, of another size than planned, or with segments the strip kernel cannot take) -- per-plane launches.
+  bool blurFrame(const DevicePlan* const* plans, int numPlanes, const uint8_t* const* dIn, const int* inW, const int* inH, const int* inPitch,
+                 PlaneLane* lanes, cudaStream_t s) {
+    if (numPlanes < 2) return false;
+    for (int p = 0; p < numPlanes; ++p) {
+      const DevicePlan& plan = *plans[p];
+      if (!plan.lowPass || inW[p] != plan.inW || inH[p] != plan.inH || plan.blur.numTileJobs || plan.blur.numDirectJobs || plan.blur.needsClear)
+        return false;
+    }
+    FrameBlurList& f = frameBlur_;
+    {
+      std::lock_guard<std::mutex> lock(frameJobsMu_);
+      if (f.generation != planGeneration_ || f.numPlanes != numPlanes) {
+        std::vector<StripJob> merged[t360::kStripMaxHy];
+        std::vector<float> taps;
+        for (int p = 0; p < numPlanes; ++p) {
+          const DevicePlan::BlurSet& b = plans[p]->blur;
+          while (taps.size() % 4) taps.push_back(0.f);  // (the padded horizontal taps stay 16-byte aligned)
+          const int base = static_cast<int>(taps.size());
+          taps.insert(taps.end(), b.hostTaps.begin(), b.hostTaps.end());
+          for (int c = 0; c < t360::kStripMaxHy; ++c)
+            for (StripJob j : b.hostStrips[c]) {
+              j.kxOffset += base;
+              j.kyOffset += base;
+              j.edge |= p << t360::kStripPlaneShift;
+              merged[c].push_back(j);
+            }
+        }
+        CU(cudaDeviceSynchronize());  // a previous frame may still be reading the old lists
+        for (int c = 0; c < t360::kStripMaxHy; ++c) {
+          // heaviest jobs first: the hardware block scheduler then balances the tail
+          std::stable_sort(merged[c].begin(), merged[c].end(), [](const StripJob& a, const StripJob& b) {
+            return static_cast<long long>(a.kxChunks + 2) * a.h * (1 + 3 * (a.edge & 1)) > static_cast<long long>(b.kxChunks + 2) * b.h * (1 + 3 * (b.edge & 1));
+          });
+          f.numJobs[c] = static_cast<int>(merged[c].size());
+          if (merged[c].empty()) continue;
+          f.jobs[c].reserve(merged[c].size());
+          CU(cudaMemcpy(f.jobs[c].ptr, merged[c].data(), merged[c].size() * sizeof(StripJob), cudaMemcpyHostToDevice));
+        }
+        f.taps.reserve(std::max<size_t>(taps.size(), 4));
+        CU(cudaMemcpy(f.taps.ptr, taps.data(), taps.size() * sizeof(float), cudaMemcpyHostToDevice));
+        f.numPlanes = numPlanes;
+        f.generation = planGeneration_;
+      }
+    }
+    t360::FrameStripParams fp{};
+    for (int p = 0; p < numPlanes; ++p) {
+      const int bp = alignedPitch(inW[p]);
+      lanes[p].blurred.reserve(static_cast<size_t>(bp) * inH[p] + 64);
+      fp.plane[p] = {dIn[p], lanes[p].blurred.ptr, inW[p], inH[p], inPitch[p], bp};
+    }
+    fp.taps = f.taps.ptr;
+    for (int c = 0; c < t360::kStripMaxHy; ++c) {
+      if (!f.numJobs[c]) continue;
+      fp.jobs = f.jobs[c].ptr;
+      fp.numJobs = f.numJobs[c];
+      CU(t360::launchBlurFrameStrips(fp, c + 1, s));
+    }
+    return true;
   }
 
   // The gathers of all planes of a frame as ONE launch (every plane staged).
@@ -1230,6 +1312,7 @@ class VideoFrameTransform {
   std::mutex slotMu_;
   std::map<cudaStream_t, std::unique_ptr<StreamSlot>> slots_;
   FrameJobList frameJobs_;
+  FrameBlurList frameBlur_;
   std::mutex frameJobsMu_;
   DeviceBuffer<unsigned long long> trace_;
   bool traceEnabled_ = false;
