@@ -6,19 +6,22 @@
 //   (host-built, sampling.cpp), same integer arithmetic.
 //
 // This is a gather, not a contraction: no tensor cores.  What the design is built around (formats: kernels.cuh):
-//   * One CTA per SM, GROUPS independent job pipelines of 8 warps each, ONE weight-table image in shared memory for
-//     all of them (brought in by cp.async.bulk), so that the cubic table can be kept twice (bank-group balancing by
-//     the host: 4.2-4.5 wavefronts per 128-bit weight load instead of 6.3-7.5) and Lanczos4's 128 KB table serves 24
-//     warps instead of 16.
-//   * The source window of a job arrives by ONE cp.async.bulk.tensor.2d (TMA) box load from the pitch-linear plane,
-//     double-buffered against the arithmetic through mbarriers; taps are read as aligned 32-bit shared-memory words and
-//     aligned with a funnel shift; every window row is folded with IDP.2A (two s16 x u8 multiply-adds per instruction).
-//   * Share jobs (64 x 32 pixels, 2/3 of a cube map): a thread slides one K-row register window down its output
-//     column and fetches only the 0-2 new source rows per pixel; 2.5 bytes of plan per pixel.
-//   * Other staged jobs (32 x 32): a window per pixel, 4 bytes of plan per pixel; general jobs (pole caps, anything
-//     BORDER_WRAP touches vertically) read their taps through L1 inside the same launch.
-//   * Jobs are handed out by an atomic counter that re-arms itself; programmatic dependent launch lets the next
-//     frame's prologue run under this frame's tail.
+//   * One CTA per SM: GROUPS consumer groups of 8 warps + one producer warp per group, ONE weight-table image in shared
+//     memory for all of them (brought in by cp.async.bulk), so that the cubic table can be kept twice (bank-group
+//     balancing by the host: 4.5-5.0 wavefronts per 128-bit weight load instead of 6.3-7.5) and Lanczos4's 128 KB table
+//     serves two groups.
+//   * Producer: claims a job, waits for a free stage of its group's two-stage ring, and issues ONE
+//     cp.async.bulk.tensor.2d (TMA) box load of the job's source window from the pitch-linear plane plus ONE
+//     cp.async.bulk of its compact sampling records; both complete on the stage's "full" mbarrier.  Consumers wait for
+//     "full", compute out of shared memory and arrive on "empty": no global load, no claim, no CTA barrier on their side.
+//   * Taps are read as aligned 32-bit shared-memory words and aligned with a funnel shift; every window row is folded
+//     with IDP.2A (two s16 x u8 multiply-adds per instruction).
+//   * Share jobs (64 x 32 pixels, 3/5 of a cube map): a thread slides one K-row register window down its output column
+//     and fetches only the 1-2 new source rows per pixel, branch-free; 2.5 bytes of plan per pixel.
+//   * Tile jobs (32 x 32 or one 16 x 16 quadrant): a window per pixel, lanes cover 8 x 4 patches, 4 bytes of plan per
+//     pixel; seam jobs OR two boxes together; general jobs (pole caps) read their taps through L1 in the same launch.
+//   * Programmatic dependent launch lets the next frame's prologue run under this frame's tail; the job counter re-arms
+//     itself.
 #include "gather_common.cuh"
 
 #include <cuda.h>  // CUtensorMap (type only; no libcuda symbol is referenced)
@@ -89,17 +92,6 @@ __device__ __forceinline__ void bulkCopyToShared(void* dst, const void* src, uin
 }
 __device__ __forceinline__ void groupBarrier(int group) {  // the 8 warps of one job pipeline
   asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "n"(kGroupThreads) : "memory");
-}
-// compact records are streamed once per frame: read-only path, do not allocate in L1
-__device__ __forceinline__ uint4 loadRecords128(const uint4* p) {
-  uint4 r;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
-  return r;
-}
-__device__ __forceinline__ uint32_t loadRecords32(const uint32_t* p) {
-  uint32_t r;
-  asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r) : "l"(p));
-  return r;
 }
 
 // ---- window arithmetic -------------------------------------------------------------------------------------------
