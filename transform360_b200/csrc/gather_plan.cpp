@@ -425,13 +425,16 @@ void buildGatherPlan(const HostPlan& h, bool stageTiles, GatherPlan& g) {
   // launch order: general tiles (latency-bound: they run while every group of the SM is busy), seam, class 1 (both
   // need the two stage buffers), then the share jobs and finally the small class-0 tiles through the double-buffered
   // TMA pipeline, which leaves a short, fine-grained tail
-  const int order[6] = {kJobGeneral, kJobSeam, kJobClass1, kJobShareStay, kJobShare, kJobClass0};
+  // (the cheapest jobs, the 16 x 16 quadrants, come last of all: every group has up to three jobs claimed ahead, so the
+  // launch ends within about three of its last jobs)
+  const int order[7] = {kJobGeneral, kJobSeam, kJobClass1, kJobShareStay, kJobShare, kJobClass0, kJobClass0};
   size_t offset = 0;  // bytes
-  for (int kind : order)
+  for (int step = 0; step < 7; ++step)
     for (int ty = 0; ty < tilesY; ++ty)
       for (int tx = 0; tx < tilesX; ++tx) {
+        const int kind = order[step];
         const TileClass& c = cls[static_cast<size_t>(ty) * tilesX + tx];
-        if (c.kind != kind) continue;
+        if (c.kind != kind || (kind == kJobClass0 && c.quads != (step == 6))) continue;
         for (int q = 0; q < (c.quads ? 4 : 1); ++q) {
           GatherJob job{tx * 32, ty * kFrameTileH | (kind << kJobKindShift), c.boxX | (c.boxY << 16), 0};
           if (c.quads) {

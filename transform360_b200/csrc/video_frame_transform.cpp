@@ -1229,10 +1229,13 @@ class VideoFrameTransform {
     std::unique_lock<std::mutex> listLock(frameJobsMu_);
     if (f.generation != planGeneration_ || f.numPlanes != numPlanes) {
       std::vector<GatherJob> merged;
-      for (int kind : {t360::kJobGeneral, t360::kJobSeam, t360::kJobClass1, t360::kJobShareStay, t360::kJobShare, t360::kJobClass0})
+      const int order[7] = {t360::kJobGeneral, t360::kJobSeam, t360::kJobClass1, t360::kJobShareStay, t360::kJobShare, t360::kJobClass0, t360::kJobClass0};
+      for (int step = 0; step < 7; ++step)  // (quadrant jobs last, like in the per-plane lists)
         for (int p = 0; p < numPlanes; ++p)
           for (GatherJob t : work[p].plan->hostJobs) {
+            const int kind = order[step];
             if (((t.outY >> t360::kJobKindShift) & t360::kJobKindMask) != kind) continue;
+            if (kind == t360::kJobClass0 && ((t.outX & t360::kJobQuadMask) != 0) != (step == 6)) continue;
             t.outY |= p << t360::kJobPlaneShift;
             merged.push_back(t);
           }
