@@ -229,6 +229,7 @@ class VideoFrameTransform {
     if (const char* m = std::getenv("T360B200_PIPELINE_MIN_BYTES")) pipelineMinBytes_ = std::atoll(m);  // tests: 0 = always
     if (const char* m = std::getenv("T360B200_PIPELINE_CHUNKS")) pipelineChunks_ = std::atoi(m);       // tuning
     if (const char* m = std::getenv("T360B200_PIPELINE_BLOCKS")) pipelineBlocks_ = std::atoi(m);
+    if (const char* m = std::getenv("T360B200_PIPELINE_IN_STREAMS")) pipelineInStreams_ = std::atoi(m);
   }
   void setPinHostPlanes(bool on) { pinHostPlanes_ = on; }
 
@@ -263,6 +264,7 @@ class VideoFrameTransform {
       for (PlaneGraph& g : planeGraphs_) cudaGraphExecDestroy(g.exec);
       for (cudaEvent_t e : {graphFork_, graphJoinIn_, graphJoinOut_}) if (e) cudaEventDestroy(e);
       if (copyIn_) cudaStreamDestroy(copyIn_);
+      if (copyIn2_) cudaStreamDestroy(copyIn2_);
       if (copyOut_) cudaStreamDestroy(copyOut_);
       if (stream_) cudaStreamDestroy(stream_);
     }
@@ -296,9 +298,13 @@ class VideoFrameTransform {
         return false;
       }
       const DeviceRestore restoreDevice = ensureDevice();
-      const bool inOnDevice = isDevicePointer(in), outOnDevice = isDevicePointer(out);
       const DevicePlan* plan = findPlan(planIndex, imagePlaneIndex);
       if (!plan) return false;
+      {  // the same plan and caller buffers as in an earlier streamed call: replay its graph (no driver query, no set-up)
+        std::lock_guard<std::mutex> hostLock(hostCallMu_);
+        if (replayPlaneGraph(*plan, in, out, inW, inH, inPitch, outW, outH, outPitch)) return true;
+      }
+      const bool inOnDevice = isDevicePointer(in), outOnDevice = isDevicePointer(out);
       if (plan->kernelSize == 0) {  // reference cpp:780-784: message, output untouched, true
         std::printf("Could not find interpolation algorithm for plane %d", imagePlaneIndex);
         return true;
@@ -416,6 +422,21 @@ class VideoFrameTransform {
     return a.type == cudaMemoryTypeHost;
   }
 
+  bool replayPlaneGraph(const DevicePlan& plan, const uint8_t* in, const uint8_t* out, int inW, int inH, int inPitch, int outW, int outH,
+                        int outPitch) {
+    for (PlaneGraph& c : planeGraphs_) {
+      if (c.plan != &plan || c.in != in || c.out != out || c.inPitch != inPitch || c.outPitch != outPitch || c.generation != planGeneration_ ||
+          c.stagingIn != stagingIn_.ptr || c.stagingOut != stagingOut_.ptr || c.inW != inW || c.inH != inH || c.outW != outW || c.outH != outH)
+        continue;
+      c.lastUse = ++graphClock_;
+      CU(cudaGraphLaunch(c.exec, stream_));
+      t360::countKernelLaunches(c.kernels);
+      CU(cudaStreamSynchronize(stream_));
+      return true;
+    }
+    return false;
+  }
+
   // reference transformFramePlane for large host planes (same result as the plain path): chunked H2D || gather || D2H
   bool transformHostPlanePipelined(const DevicePlan& plan, uint8_t* in, uint8_t* out, int inW, int inH, int inPitch, int outW, int outH,
                                    int outPitch, int planIndex, int imagePlaneIndex) {
@@ -425,6 +446,7 @@ class VideoFrameTransform {
     WavePlan& w = wavePlanFor(plan, planIndex, chunks);
     if (!copyIn_) {
       CU(cudaStreamCreateWithFlags(&copyIn_, cudaStreamNonBlocking));
+      CU(cudaStreamCreateWithFlags(&copyIn2_, cudaStreamNonBlocking));
       CU(cudaStreamCreateWithFlags(&copyOut_, cudaStreamNonBlocking));
       for (cudaEvent_t* e : {&graphFork_, &graphJoinIn_, &graphJoinOut_}) CU(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
     }
@@ -457,6 +479,7 @@ class VideoFrameTransform {
       if (forkJoin) {  // (capture: the side streams become branches of the graph)
         CU(cudaEventRecord(graphFork_, stream_));
         CU(cudaStreamWaitEvent(copyIn_, graphFork_, 0));
+        if (pipelineInStreams_ > 1) CU(cudaStreamWaitEvent(copyIn2_, graphFork_, 0));
         CU(cudaStreamWaitEvent(copyOut_, graphFork_, 0));
       }
       t360::FrameGatherParams fp{};
@@ -466,10 +489,12 @@ class VideoFrameTransform {
       fp.numPlanes = 1;
       for (int c = 0; c < chunks; ++c) {
         const int r0 = c ? w.chunkRowEnd[c - 1] : 0, r1 = w.chunkRowEnd[c];
+        // (with two inbound streams the set-up of band c + 1 hides under the transfer of band c)
+        cudaStream_t inStream = (pipelineInStreams_ > 1 && (c & 1)) ? copyIn2_ : copyIn_;
         if (r1 > r0)
           CU(cudaMemcpy2DAsync(stagingIn_.ptr + static_cast<size_t>(r0) * dInPitch, dInPitch, in + static_cast<size_t>(r0) * inPitch, inPitch, inW,
-                               r1 - r0, cudaMemcpyHostToDevice, copyIn_));
-        CU(cudaEventRecord(chunkIn_[c], copyIn_));
+                               r1 - r0, cudaMemcpyHostToDevice, inStream));
+        CU(cudaEventRecord(chunkIn_[c], inStream));
         CU(cudaStreamWaitEvent(stream_, chunkIn_[c], 0));
         const int n = w.waveStart[c + 1] - w.waveStart[c];
         if (n > 0) {
@@ -485,6 +510,10 @@ class VideoFrameTransform {
         }
       }
       if (forkJoin) {
+        if (pipelineInStreams_ > 1) {  // (the second inbound stream joins through the first)
+          CU(cudaEventRecord(graphJoinIn_, copyIn2_));
+          CU(cudaStreamWaitEvent(copyIn_, graphJoinIn_, 0));
+        }
         CU(cudaEventRecord(graphJoinIn_, copyIn_));
         CU(cudaEventRecord(graphJoinOut_, copyOut_));
         CU(cudaStreamWaitEvent(stream_, graphJoinIn_, 0));
@@ -573,7 +602,8 @@ class VideoFrameTransform {
         if (e != cudaSuccess) throw CudaFail{e, "cudaGraphInstantiate"};
         int kernels = 0;
         for (int c = 0; c < chunks; ++c) kernels += w.waveStart[c + 1] > w.waveStart[c];
-        planeGraphs_.push_back(PlaneGraph{&plan, planGeneration_, in, out, inPitch, outPitch, stagingIn_.ptr, stagingOut_.ptr, kernels, exec, 0});
+        planeGraphs_.push_back(PlaneGraph{&plan, planGeneration_, in, out, inPitch, outPitch, stagingIn_.ptr, stagingOut_.ptr, inW, inH, outW, outH,
+                                          kernels, exec, 0});
         g = &planeGraphs_.back();
         t360::countKernelLaunches(-kernels);  // (counted once while capturing; every replay counts below)
       }
@@ -586,6 +616,7 @@ class VideoFrameTransform {
     issue(false);
     CU(cudaStreamSynchronize(stream_));
     CU(cudaStreamSynchronize(copyOut_));
+    if (pipelineInStreams_ > 1) CU(cudaStreamSynchronize(copyIn2_));
     return true;
   }
 
@@ -1291,17 +1322,19 @@ class VideoFrameTransform {
   DeviceBuffer<uint8_t> weightImages_[9];  // their shared-memory images for the frame kernel
   DeviceBuffer<uint8_t> stagingIn_, stagingOut_;
   std::mutex hostCallMu_;  // the synchronous host-pointer path shares the staging planes and the streams: one call at a time
-  cudaStream_t copyIn_ = nullptr, copyOut_ = nullptr;
+  cudaStream_t copyIn_ = nullptr, copyIn2_ = nullptr, copyOut_ = nullptr;
   std::vector<cudaEvent_t> chunkIn_, waveDone_;
   WavePlan wavePlans_[2];  // plan index 0 / 1
   long long pipelineMinBytes_ = 6ll << 20;
   int pipelineChunks_ = 0, pipelineBlocks_ = 0;  // 0: automatic
+  int pipelineInStreams_ = 1;
   // The streamed call is ~100 runtime calls (chunk copies, events, wave launches, rectangle copies); issued one by one
   // the host thread becomes the bottleneck (measured: no faster than the plain path).  For page-locked caller planes the
   // whole sequence is captured once per (plan, buffers) into a CUDA graph and replayed with one launch.
   struct PlaneGraph {
     const void* plan; unsigned long long generation; const void* in; const void* out; int inPitch, outPitch;
     const void* stagingIn; const void* stagingOut;  // (the staging planes grow on demand: a graph made for old ones is stale)
+    int inW, inH, outW, outH;
     int kernels;
     cudaGraphExec_t exec; unsigned long long lastUse;
   };
