@@ -29,13 +29,16 @@
 #define AV_LOG_VERBOSE 40
 #define AV_OPT_FLAG_VIDEO_PARAM 16
 #define AV_OPT_FLAG_FILTERING_PARAM (1 << 16)
+#define AVERROR_EXTERNAL (-0x20545845)
+#define FFALIGN(x, a) (((x) + (a) - 1) & ~((a) - 1))
+#define FF_FILTER_FLAG_HWFRAME_AWARE 1
 
 enum AVOptionType { AV_OPT_TYPE_FLAGS, AV_OPT_TYPE_INT, AV_OPT_TYPE_INT64, AV_OPT_TYPE_DOUBLE, AV_OPT_TYPE_FLOAT,
                     AV_OPT_TYPE_STRING, AV_OPT_TYPE_RATIONAL, AV_OPT_TYPE_BINARY, AV_OPT_TYPE_DICT, AV_OPT_TYPE_UINT64,
                     AV_OPT_TYPE_CONST, AV_OPT_TYPE_BOOL };
 enum AVMediaType { AVMEDIA_TYPE_VIDEO = 0 };
 enum { AV_CLASS_CATEGORY_FILTER = 8 };
-enum AVPixelFormat { AV_PIX_FMT_YUV420P = 0, AV_PIX_FMT_GRAY8 = 8 };
+enum AVPixelFormat { AV_PIX_FMT_NONE = -1, AV_PIX_FMT_YUV420P = 0, AV_PIX_FMT_GRAY8 = 8, AV_PIX_FMT_NV12 = 23, AV_PIX_FMT_CUDA = 117 };
 
 typedef struct AVOption {
   const char* name;
@@ -67,12 +70,94 @@ static inline const AVPixFmtDescriptor* av_pix_fmt_desc_get(int fmt) {
 }
 static inline int av_pix_fmt_count_planes(int fmt) { return av_pix_fmt_desc_get(fmt)->nb_components; }
 
+/* ---- the slice of libavutil/buffer.h + hwcontext(_cuda).h that a CUDA-frame filter touches ------------------- */
+typedef struct AVBufferRef {
+  uint8_t* data;
+  int* refs; /* shared count */
+} AVBufferRef;
+static inline AVBufferRef* ffshim_buffer_new(size_t bytes) {
+  AVBufferRef* r = (AVBufferRef*)calloc(1, sizeof(*r));
+  r->data = (uint8_t*)calloc(1, bytes);
+  r->refs = (int*)calloc(1, sizeof(int));
+  *r->refs = 1;
+  return r;
+}
+static inline AVBufferRef* av_buffer_ref(AVBufferRef* b) {
+  if (!b) return NULL;
+  AVBufferRef* r = (AVBufferRef*)calloc(1, sizeof(*r));
+  *r = *b;
+  ++*r->refs;
+  return r;
+}
+static inline void av_buffer_unref(AVBufferRef** b) {
+  if (!b || !*b) return;
+  if (--*(*b)->refs == 0) { free((*b)->data); free((*b)->refs); }
+  free(*b);
+  *b = NULL;
+}
+
+typedef void* CUcontext;
+typedef void* CUstream;
+typedef struct CudaFunctions { /* ffnvcodec's dynlink table: the three entries the filter calls */
+  int (*cuCtxPushCurrent)(CUcontext ctx);
+  int (*cuCtxPopCurrent)(CUcontext* ctx);
+  int (*cuStreamSynchronize)(CUstream stream);
+} CudaFunctions;
+typedef struct AVCUDADeviceContextInternal { CudaFunctions* cuda_dl; } AVCUDADeviceContextInternal;
+typedef struct AVCUDADeviceContext {
+  CUcontext cuda_ctx;
+  CUstream stream;
+  AVCUDADeviceContextInternal* internal;
+} AVCUDADeviceContext;
+typedef struct AVHWDeviceContext { void* hwctx; } AVHWDeviceContext;
+typedef struct AVHWFramesContext {
+  AVBufferRef* device_ref;
+  AVHWDeviceContext* device_ctx;
+  int format, sw_format, width, height;
+  int initialised;
+  /* stand-in for the frame pool: the driver lends the planes the next av_hwframe_get_buffer hands out */
+  uint8_t* lend[3];
+  int lend_pitch[3];
+} AVHWFramesContext;
+static inline AVBufferRef* av_hwframe_ctx_alloc(AVBufferRef* device_ref) {
+  if (!device_ref) return NULL;
+  AVBufferRef* r = ffshim_buffer_new(sizeof(AVHWFramesContext));
+  AVHWFramesContext* f = (AVHWFramesContext*)r->data;
+  f->device_ref = device_ref; /* borrowed: the driver keeps the device alive for the filter's lifetime */
+  f->device_ctx = (AVHWDeviceContext*)device_ref->data;
+  return r;
+}
+static inline int av_hwframe_ctx_init(AVBufferRef* ref) {
+  AVHWFramesContext* f = (AVHWFramesContext*)ref->data;
+  if (f->format != AV_PIX_FMT_CUDA || f->width <= 0 || f->height <= 0) return AVERROR(EINVAL);
+  f->initialised = 1;
+  return 0;
+}
+
 typedef struct AVFrame {
   uint8_t* data[8];
   int linesize[8];
   int width, height, format;
   uint8_t* owned[8];
+  AVBufferRef* hw_frames_ctx;
 } AVFrame;
+static inline AVFrame* av_frame_alloc(void) { return (AVFrame*)calloc(1, sizeof(AVFrame)); }
+static inline int av_hwframe_get_buffer(AVBufferRef* ref, AVFrame* frame, int flags) {
+  (void)flags;
+  AVHWFramesContext* f = (AVHWFramesContext*)ref->data;
+  if (!f->initialised) return AVERROR(EINVAL);
+  if (!f->lend[0]) return AVERROR(ENOMEM);
+  for (int p = 0; p < 3; p++) {
+    frame->data[p] = f->lend[p];
+    frame->linesize[p] = f->lend_pitch[p];
+    f->lend[p] = NULL;
+  }
+  frame->format = AV_PIX_FMT_CUDA;
+  frame->width = f->width;
+  frame->height = f->height;
+  frame->hw_frames_ctx = av_buffer_ref(ref);
+  return 0;
+}
 
 struct AVFilterContext;
 typedef struct AVFilterLink {
@@ -80,6 +165,7 @@ typedef struct AVFilterLink {
   struct AVFilterContext* dst;
   int w, h, format;
   AVFrame* delivered; /* what ff_filter_frame received last */
+  AVBufferRef* hw_frames_ctx;
 } AVFilterLink;
 
 typedef struct AVFilterPad {
@@ -93,6 +179,9 @@ typedef struct AVFilter {
   const char* name;
   const char* description;
   int (*init_dict)(struct AVFilterContext* ctx, AVDictionary** options);
+  int (*init)(struct AVFilterContext* ctx);
+  int (*query_formats)(struct AVFilterContext* ctx);
+  int flags_internal;
   void (*uninit)(struct AVFilterContext* ctx);
   int priv_size;
   const AVClass* priv_class;
@@ -106,7 +195,10 @@ typedef struct AVFilterContext {
   void* priv;
   AVFilterLink** inputs;
   AVFilterLink** outputs;
+  const int* common_formats; /* what query_formats announced */
 } AVFilterContext;
+static inline const int* ff_make_format_list(const int* fmts) { return fmts; }
+static inline int ff_set_common_formats(AVFilterContext* ctx, const int* fmts) { ctx->common_formats = fmts; return fmts ? 0 : AVERROR(ENOMEM); }
 
 static inline void av_log(void* avcl, int level, const char* fmt, ...) { (void)avcl; (void)level; (void)fmt; }
 
@@ -136,6 +228,7 @@ static inline AVFrame* ff_get_video_buffer(AVFilterLink* link, int w, int h) { r
 static inline void av_frame_free(AVFrame** f) {
   if (!f || !*f) return;
   for (int p = 0; p < 8; p++) free((*f)->owned[p]);
+  av_buffer_unref(&(*f)->hw_frames_ctx);
   free(*f);
   *f = NULL;
 }
