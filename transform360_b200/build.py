@@ -97,6 +97,8 @@ def install(prefix: str) -> None:
         for h in (ROOT / "include" / sub).glob("*.h"):
             sh.copy2(h, pre / "include" / sub / h.name)
     sh.copy2(ROOT / "include" / "transform360_b200.h", pre / "include" / "transform360_b200.h")
+    (pre / "share" / "transform360").mkdir(parents=True, exist_ok=True)  # the CUDA-frame ffmpeg filter goes into an ffmpeg tree as source
+    sh.copy2(PKG / "filter" / "vf_transform360_cuda.c", pre / "share" / "transform360" / "vf_transform360_cuda.c")
 
 
 if __name__ == "__main__":
