@@ -65,6 +65,9 @@ class WeightImage:
             idx = (field >> 1)[:, None] // 2 + np.arange(4)[None, :]
             return img16[idx]
         nv = self.k * self.k // 8
+        if self.k == 8:  # XOR-diagonal image (kernels.cuh): vector m of a slot sits at field ^ (m * 0x4010)
+            idx = (field[:, None, None] ^ (np.arange(nv)[None, :, None] * 0x4010)) // 2 + np.arange(8)[None, None, :]
+            return img16[idx].reshape(len(field), -1)
         idx = (field[:, None, None] + np.arange(nv)[None, :, None] * self.stride) // 2 + np.arange(8)[None, None, :]
         return img16[idx].reshape(len(field), -1)
 

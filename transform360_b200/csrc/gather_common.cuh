@@ -106,7 +106,7 @@ __device__ __forceinline__ void stageWeights(const int16_t* __restrict__ g, unsi
 // K x K window in GLOBAL memory (read-only path) whose rows are `pitch` bytes apart, starting at byte offset `off`
 // of a 4-byte aligned base.  No bounds handling: the caller guarantees the window (plus the tail of its last
 // aligned word) is readable.
-template <int K, int VSTRIDE>
+template <int K, int VSTRIDE, bool DIAG = false>
 __device__ __forceinline__ int foldWindow(const uint32_t* __restrict__ words, int off, int pitch,
                                           const unsigned char* wsmem, int phase) {
   phase = weightSlot<K>(phase);
@@ -135,7 +135,7 @@ __device__ __forceinline__ int foldWindow(const uint32_t* __restrict__ words, in
     const uint4* tab = reinterpret_cast<const uint4*>(wsmem);
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
-      const uint4 wt = tab[r * (VSTRIDE / 16) + phase];
+      const uint4 wt = tab[r * (VSTRIDE / 16) + (DIAG ? phase ^ r : phase)];
       const uint32_t q0 = ld(off >> 2), q1 = ld((off >> 2) + 1), q2 = ld((off >> 2) + 2);
       const int sh = (off & 3) * 8;
       const uint32_t b0 = __funnelshift_r(q0, q1, sh), b1 = __funnelshift_r(q1, q2, sh);
@@ -162,17 +162,18 @@ struct SrcView {
 
 // One output pixel through L1, any border case.  Returns the 8-bit value, or -1 when BORDER_TRANSPARENT
 // leaves the pixel untouched.
-template <int K, bool TRANSPARENT, int VSTRIDE>
+template <int K, bool TRANSPARENT, int VSTRIDE, bool DIAG = false>
 __device__ __forceinline__ int gatherPixel(const SrcView& s, const unsigned char* wsmem, int col0, int rowPhase) {
   const int row0 = rowPhase >> 10, phase = rowPhase & 1023;
   // interior: no wrapping, and the aligned word reads (2 words for K <= 4, 3 for K = 8, starting at col0 & ~3) stay
   // inside the row even when the pitch equals the width
   const bool interior = col0 >= 0 && row0 >= 0 && col0 + (K == 2 ? 8 : K + 4) <= s.w && row0 + K <= s.h;
   if (interior)
-    return roundToByte(foldWindow<K, VSTRIDE>(s.words, row0 * s.pitch + col0 + s.misalign, s.pitch, wsmem, phase));
+    return roundToByte(foldWindow<K, VSTRIDE, DIAG>(s.words, row0 * s.pitch + col0 + s.misalign, s.pitch, wsmem, phase));
 
   // window touches an edge: per-tap addressing.  BORDER_WRAP wraps columns AND rows (reference cpp:719).
-  const int16_t* wt = reinterpret_cast<const int16_t*>(wsmem) + weightSlot<K>(phase) * (K == 2 ? 4 : 8);
+  const int slot = weightSlot<K>(phase);
+  const int16_t* wt = reinterpret_cast<const int16_t*>(wsmem) + (DIAG ? 0 : slot * (K == 2 ? 4 : 8));
   if (TRANSPARENT) {
     // every interpolator leaves the pixel alone when its anchor sample lies outside the source
     const int ax = col0 + (K / 2 - 1), ay = row0 + (K / 2 - 1);
@@ -208,7 +209,8 @@ __device__ __forceinline__ int gatherPixel(const SrcView& s, const unsigned char
 #pragma unroll
     for (int c = 0; c < K; ++c) {
       const int e = r * K + c;  // element (r, c) lives in vector e / 8, lane e % 8 of the transposed table
-      acc += (K == 2 ? wt[e] : wt[(e >> 3) * (VSTRIDE / 2) + (e & 7)]) * px[c];
+      // (the diagonal image keeps vector e / 8 of the slot at position slot ^ (e / 8) of its plane)
+      acc += (K == 2 ? wt[e] : wt[(e >> 3) * (VSTRIDE / 2) + (DIAG ? (slot ^ (e >> 3)) * 8 : 0) + (e & 7)]) * px[c];
     }
   }
   return roundToByte(acc);

@@ -134,11 +134,46 @@ __device__ __forceinline__ int foldRows(const RowBytes<K> (&W)[K], uint32_t slot
   }
   return acc;
 }
-__device__ __forceinline__ int biasedToByte(int acc) { return min(max(acc >> 15, 0), 255); }  // acc already holds + 16384
-
 // K = 2 slots are 8 bytes: the record's slot field (slot << 4) is halved
 template <int K>
 __device__ __forceinline__ uint32_t slotOffset(uint32_t field) { return K == 2 ? field >> 1 : field; }
+
+// Lanczos4: the same sum with the vectors fetched in the lane's own XOR-rotated order (kernels.cuh: "XOR-DIAGONAL").
+// field = the record's slot field (slot << 4).
+template <int VS>
+__device__ __forceinline__ int foldRowsRotated(const RowBytes<8> (&W)[8], uint32_t wAddr, uint32_t field) {
+  static_assert(VS == 16384, "one copy of the table");
+  const uint32_t r = ((field >> 4) ^ threadIdx.x) & 7u;
+  const uint32_t first = field ^ (r * (uint32_t)kDiagonalStep);  // bank group bits: lane & 7; plane bits: r
+  const bool p0 = (r & 1u) != 0, p1 = (r & 2u) != 0, p2 = (r & 4u) != 0;
+  RowBytes<8> A[8], B[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int h = 0; h < 2; ++h) A[i].b[h] = p0 ? W[i ^ 1].b[h] : W[i].b[h];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int h = 0; h < 2; ++h) B[i].b[h] = p1 ? A[i ^ 2].b[h] : A[i].b[h];
+  int acc = 1 << 14;
+  staticFor<8>([&](auto V) {
+    constexpr int v = decltype(V)::value;
+    // row v ^ r of the window meets vector v ^ r of the slot
+    const uint4 wt = ldsVecImm<0>(wAddr + (first ^ (uint32_t)(v * kDiagonalStep)));
+    const uint32_t b0 = p2 ? B[v ^ 4].b[0] : B[v].b[0], b1 = p2 ? B[v ^ 4].b[1] : B[v].b[1];
+    acc = dp2aLo(wt.x, b0, acc); acc = dp2aHi(wt.y, b0, acc);
+    acc = dp2aLo(wt.z, b1, acc); acc = dp2aHi(wt.w, b1, acc);
+  });
+  return acc;
+}
+// the fold of a staged or general-interior pixel, whatever the table's layout
+template <int K, int VS>
+__device__ __forceinline__ int foldPixel(const RowBytes<K> (&W)[K], uint32_t wAddr, uint32_t field) {
+  if constexpr (K == 8) return foldRowsRotated<VS>(W, wAddr, field);
+  else return foldRows<K, VS>(W, wAddr + slotOffset<K>(field));
+}
+__device__ __forceinline__ int biasedToByte(int acc) { return min(max(acc >> 15, 0), 255); }  // acc already holds + 16384
+
 
 // ---- share job: one register window per output column, slid down ROWS rows -------------------------------------------
 // Consecutive pixels of a column start 1 or 2 source rows apart (bit 0 of the pixel record: the second row).  The part
@@ -197,7 +232,7 @@ __device__ __forceinline__ void computeShareJob(uint8_t* dst, int dstPitch, uint
       }
       base += d * PITCH;
     }
-    const int acc = foldRows<K, VS>(W, wAddr + (r & kSlotFieldMask)) >> 15;
+    const int acc = foldPixel<K, VS>(W, wAddr, r & kSlotFieldMask) >> 15;
     if constexpr (j & 1) {
       const uint32_t pair = packBytes(acc, accPrev);
       dst[(size_t)(j - 1) * dstPitch] = (uint8_t)pair;
@@ -226,7 +261,7 @@ __device__ __forceinline__ void computeTileJob(const PlaneView& pv, uint32_t sta
       const int sh = (int)(w << 3);
       RowBytes<K> W[K];
       staticFor<K>([&](auto R) { W[decltype(R)::value] = loadRow<K, decltype(R)::value * PITCH>(rowAddr, sh); });
-      const int acc = foldRows<K, VS>(W, wAddr + slotOffset<K>((w >> 17) & kSlotFieldMask));
+      const int acc = foldPixel<K, VS>(W, wAddr, (w >> 17) & kSlotFieldMask);
       dstRow[(size_t)row * dstPitch + col] = (uint8_t)biasedToByte(acc);
     }
   });
@@ -281,8 +316,8 @@ __device__ __forceinline__ void computeGeneralJob(const PlaneView& pv, int outX,
       const int j = jb + b;
       if (y0 + j >= pv.dstH) continue;
       int v;
-      if (interior[b]) v = biasedToByte(foldRows<K, VS>(W[b], wAddr + slotOffset<K>((uint32_t)weightSlotOf(K, full[j].y & 1023) << 4)));
-      else v = gatherPixel<K, false, VS>(sv, wsmem, recordCol0(full[j].x), full[j].y);
+      if (interior[b]) v = biasedToByte(foldPixel<K, VS>(W[b], wAddr, (uint32_t)weightSlotOf(K, full[j].y & 1023) << 4));
+      else v = gatherPixel<K, false, VS, weightDiagonal(K)>(sv, wsmem, recordCol0(full[j].x), full[j].y);
       pv.dst[(size_t)(y0 + j) * pv.dstPitch + outX + recordColumn(full[j].x)] = (uint8_t)v;
     }
   }

@@ -378,7 +378,7 @@ void spreadGeneralJobs(std::vector<GatherJob>& jobs) {
 }
 
 std::vector<uint8_t> buildWeightImage(int k, const int16_t* table) {
-  const int copies = weightCopies(k), vs = weightVectorStride(k, copies);
+  const int copies = weightCopies(k);
   std::vector<uint8_t> img(static_cast<size_t>(weightImageBytes(k, copies)), 0);
   for (int phase = 0; phase < 1024; ++phase) {
     const int slot = weightSlotOf(k, phase);
@@ -389,8 +389,7 @@ std::vector<uint8_t> buildWeightImage(int k, const int16_t* table) {
     }
     for (int c = 0; c < copies; ++c)
       for (int v = 0; v < k * k / 8; ++v)  // vector v = the 8 weights 8v .. 8v+7 of the row-major window
-        std::memcpy(&img[static_cast<size_t>(v) * vs + static_cast<size_t>(c) * 16384 + static_cast<size_t>(weightSlotInCopy(slot, c)) * 16],
-                    cell + v * 8, 16);
+        std::memcpy(&img[static_cast<size_t>(weightVectorOffset(k, copies, (weightSlotInCopy(slot, c) << 4) | (c << 14), v))], cell + v * 8, 16);
   }
   return img;
 }

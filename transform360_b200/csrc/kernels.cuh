@@ -107,6 +107,18 @@ __host__ __device__ constexpr int weightSlotField(int k, int phase, int copy) {
   return (weightSlotInCopy(weightSlotOf(k, phase), copy) << 4) | (copy << 14);
 }
 constexpr int kSlotFieldMask = 0x7FF0;
+// Lanczos4 has eight vectors per slot and room for one copy only (128 KB).  Its image is XOR-DIAGONAL: vector m of slot s
+// sits in plane m at position s ^ m (low three bits), i.e. at byte  slotField ^ (m * kDiagonalStep)  of the image.  A
+// pixel may then fetch its vectors in any XOR-rotated order m = v ^ r (v = 0 .. 7 the step, r private to the lane) and
+// lands in bank group (s ^ r ^ v) & 7; with r = (s ^ lane) & 7 that is (lane ^ v) & 7: the eight lanes of a quarter-warp
+// always ask for eight different bank groups, whatever their phases -- 4.0 wavefronts per 128-bit load by construction
+// (it was 8.0).  The window rows are paired with the vectors through a three-stage exchange network in registers
+// (integer sums do not care about the order).
+constexpr int kDiagonalStep = 0x4010;  // one plane (16384 bytes) + one bank group (16 bytes)
+__host__ __device__ constexpr bool weightDiagonal(int k) { return k == 8; }
+__host__ __device__ constexpr int weightVectorOffset(int k, int copies, int slotFieldValue, int vector) {
+  return weightDiagonal(k) ? (slotFieldValue ^ (vector * kDiagonalStep)) : slotFieldValue + vector * weightVectorStride(k, copies);
+}
 __host__ __device__ constexpr int weightBankGroups(int k) { return k == 2 ? 16 : 8; }
 __host__ __device__ constexpr int weightLanesPerPass(int k) { return k == 2 ? 16 : 8; }
 
