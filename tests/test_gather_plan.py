@@ -139,7 +139,7 @@ def test_gather_plan_invariants(group, name, plane):
     next_offset = 0
     for ox, oy, boxxy, rec_off in jobs:
         kind, y0 = (oy >> KIND_SHIFT) & 15, oy & ROW_MASK
-        bx, by = boxxy & 0xFFFF, boxxy >> 16
+        bx, by, chunks = boxxy & 0xFFF0, boxxy >> 16, (boxxy & 15) + 1  # the box arrives as `chunks` TMA boxes of 8 rows
         quad, ox = (ox & 7) - 1, ox & ~7  # 16 x 16 quadrant of the tile this job covers (-1: all of it)
         assert ox % 32 == 0 and y0 % 32 == 0 and quad < 4 and (quad < 0 or kind == CLASS0)
         if kind == GENERAL:
@@ -148,6 +148,9 @@ def test_gather_plan_invariants(group, name, plane):
             continue
         pitch, bh = box_w(kind), box_h(k, kind)
         assert bx % 16 == 0 and rec_off == next_offset, "records are laid out in launch order, 16-byte units"
+        assert bh % 8 == 0 and chunks * 8 <= bh, "the chunks of a box fit its stage buffer"
+        bh = chunks * 8  # what the kernel loads: every window must lie inside it (checked below) ...
+        rows_used = 0    # ... and the last chunk must be needed
         if kind in (SHARE, SHARE_STAY):
             R = share_rows(k)
             sh, nwords = 4 * R, R // 8 * 128 + 32  # job height; 32-bit words per warp
@@ -181,12 +184,21 @@ def test_gather_plan_invariants(group, name, plane):
                 # the whole column's windows stay inside the box and the plane
                 assert (col0 - bx + k <= pitch).all() and (row0[:, -1] - by + k <= bh).all()
                 assert (col0 >= 0).all() and (col0 + k <= iw).all() and (row0 >= 0).all() and (row0 + k <= ih).all()
+                rows_used = max(rows_used, int(row0.max()) - by + k)
+            assert rows_used > bh - 8, "no row chunk is loaded in vain"
             produced[y0:y0 + sh, ox:ox + 64] += 1
             continue
         # 32 x 32 jobs: class 0 (also one quadrant of a tile), class 1, seam.  Warp w, word j = one pixel of the 8 x 4
         # patch at rows 4w .., columns 8j ..
-        words = compact[rec_off * 4:rec_off * 4 + 8 * 128].reshape(8, 32, 4).astype(np.int64)  # [warp][lane][step]
-        next_offset += 8 * 128 // 4
+        if quad < 0:
+            words = compact[rec_off * 4:rec_off * 4 + 8 * 128].reshape(8, 32, 4).astype(np.int64)  # [warp][lane][step]
+            next_offset += 8 * 128 // 4
+        else:
+            # a quadrant job stores its four live warps x two live steps only; the kernel takes every other word as "skip"
+            words = np.broadcast_to(((np.arange(32, dtype=np.int64) << 16) | SKIP)[None, :, None], (8, 32, 4)).copy()
+            live_words = compact[rec_off * 4:rec_off * 4 + 4 * 64].reshape(4, 32, 2).astype(np.int64)
+            words[4 * (quad >> 1):4 * (quad >> 1) + 4, :, 2 * (quad & 1):2 * (quad & 1) + 2] = live_words
+            next_offset += 4 * 64 // 4
         off, pos, field, skip = words & 0x7FFF, (words >> 16) & 31, (words >> 17) & SLOT_MASK, (words & SKIP) != 0
         assert (np.sort(pos, axis=1) == np.arange(32)[None, :, None]).all(), "a patch holds every position once (also the skipped ones)"
         x = ox + 8 * np.arange(4)[None, None, :] + (pos & 7)
@@ -201,6 +213,7 @@ def test_gather_plan_invariants(group, name, plane):
         assert (row0 == want[..., 1] >> 10).all()
         wimg.check(fields, want[..., 1] & 1023)
         assert (offs % pitch + k <= pitch).all() and (offs // pitch + k <= bh).all() and (row0 >= 0).all() and (row0 + k <= ih).all()
+        assert int((offs // pitch).max()) + k > bh - 8, "no row chunk is loaded in vain"
         if kind == SEAM:
             assert iw % 16 == 0 and bx < iw < bx + pitch, "the box of a seam tile wraps around the border"
             assert (col0 % iw == want[..., 0] % iw).all()

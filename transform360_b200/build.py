@@ -38,7 +38,7 @@ def needs_build() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False, defines: tuple = (), out: Path | None = None) -> Path:
-    """defines / out: experiment variants (e.g. defines=("T360_STAGES=3",), out=lib/libTransform360_s3.so), loaded
+    """defines / out: experiment variants (e.g. defines=("T360_CLAIM_BATCH=2",), out=lib/libTransform360_c2.so), loaded
     with T360B200_LIB=<path>."""
     out = out or LIB
     if not force and not defines and not needs_build():

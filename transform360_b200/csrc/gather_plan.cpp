@@ -67,6 +67,41 @@ struct GroupMatcher {
     }
     return true;
   }
+  // After run(): evens the loads out below the cap as well.  A pass (quarter-warp) is full only if it finds a pixel in
+  // every group it may not take two of, so an EMPTY group costs as much as an overfull one (loads 4,4,4,0,5,5,5,5 deal
+  // to 2+2+2+2 = 8 wavefronts, 4,4,3,1,5,5,5,5 to 5).  Moves one pixel along a chain of groups from a group with load L
+  // to one with load <= L - 2 while such a chain exists (every move lowers the sum of squared loads).
+  void balance() {
+    for (bool improved = true; improved;) {
+      improved = false;
+      for (int src = 0; src < 8 && !improved; ++src) {
+        int from[8], via[8], queue[8], head = 0, tail = 0;
+        std::fill(from, from + 8, -1);
+        from[src] = src;
+        queue[tail++] = src;
+        while (head < tail && !improved) {
+          const int g = queue[head++];
+          for (int j = 0; j < n && !improved; ++j) {
+            if (groupOf[j] != g) continue;
+            for (int c = 0; c < copies; ++c) {
+              const int t = (base[j] + c) & 7;
+              if (from[t] >= 0) continue;
+              from[t] = g;
+              via[t] = j;
+              queue[tail++] = t;
+              if (load[t] + 2 <= load[src]) {  // shift one pixel along src -> .. -> t
+                for (int cur = t; cur != src; cur = from[cur]) groupOf[via[cur]] = cur;
+                ++load[t];
+                --load[src];
+                improved = true;
+                break;
+              }
+            }
+          }
+        }
+      }
+    }
+  }
 };
 
 // Full records: device order of the 8-byte sampling records the general kernels read.  Each row is cut into segments
@@ -102,10 +137,10 @@ void buildFullRecords(const HostPlan& h, std::vector<int2>& out, int tilesPerRow
 
 struct TileClass {
   int kind = -1;  // kJob*; -1: covered by the share job that starts at the tile to its left (or at this tile)
-  int boxX = 0, boxY = 0;
+  int boxX = 0, boxY = 0, boxRows = 0;  // boxRows: the source rows the job's windows really span (<= the class's box height)
   bool shareStart = false;
   bool quads = false;  // four class-0 jobs, one per 16 x 16 quadrant, each with its own box
-  int quadBoxX[4] = {}, quadBoxY[4] = {};
+  int quadBoxX[4] = {}, quadBoxY[4] = {}, quadBoxRows[4] = {};
 };
 
 // Bounding box of the source windows of a block of output pixels.
@@ -148,17 +183,19 @@ bool shareBlock(const HostPlan& h, int x0, int y0, TileClass& out) {
   out.kind = stays ? kJobShareStay : kJobShare;
   out.boxX = boxX;
   out.boxY = e.minR;
+  out.boxRows = e.maxR + k - e.minR;
   out.shareStart = true;
   return true;
 }
 
 // class of the box that holds the windows of the pixel block [x0, x1) x [y0, y1): 0, 1 or -1
-int boxClassFor(const HostPlan& h, int x0, int y0, int x1, int y1, int maxClass, int* boxX, int* boxY) {
+int boxClassFor(const HostPlan& h, int x0, int y0, int x1, int y1, int maxClass, int* boxX, int* boxY, int* boxRows) {
   const int k = h.kernelSize;
   const Extent e = extentOf(h, x0, y0, x1, y1);
   if (e.minC < 0 || e.minR < 0 || e.maxC + k > h.inW || e.maxR + k > h.inH) return -1;
   *boxX = e.minC & ~15;
   *boxY = e.minR;
+  *boxRows = e.maxR + k - e.minR;
   for (int cls = 0; cls <= maxClass; ++cls)
     if (e.maxC + k - *boxX <= stageBoxW(k, cls) && e.maxR + k - e.minR <= stageBoxH(k, cls)) return cls;
   return -1;
@@ -167,7 +204,7 @@ int boxClassFor(const HostPlan& h, int x0, int y0, int x1, int y1, int maxClass,
 void classifyTile(const HostPlan& h, int x0, int y0, bool seamPossible, TileClass& out) {
   const int k = h.kernelSize;
   const int x1 = std::min(h.mapW, x0 + kGatherTileW), y1 = std::min(h.mapH, y0 + kFrameTileH);
-  const int cls = boxClassFor(h, x0, y0, x1, y1, 1, &out.boxX, &out.boxY);
+  const int cls = boxClassFor(h, x0, y0, x1, y1, 1, &out.boxX, &out.boxY, &out.boxRows);
   if (cls == 0) {
     out.kind = kJobClass0;
     return;
@@ -179,7 +216,7 @@ void classifyTile(const HostPlan& h, int x0, int y0, bool seamPossible, TileClas
     bool all = true;
     for (int q = 0; q < 4 && all; ++q) {
       const int qx = x0 + 16 * (q & 1), qy = y0 + 16 * (q >> 1);
-      all = boxClassFor(h, qx, qy, qx + 16, qy + 16, 0, &out.quadBoxX[q], &out.quadBoxY[q]) == 0;
+      all = boxClassFor(h, qx, qy, qx + 16, qy + 16, 0, &out.quadBoxX[q], &out.quadBoxY[q], &out.quadBoxRows[q]) == 0;
     }
     if (all) {
       out.kind = kJobClass0;
@@ -209,11 +246,12 @@ void classifyTile(const HostPlan& h, int x0, int y0, bool seamPossible, TileClas
       out.kind = kJobSeam;
       out.boxX = bx;
       out.boxY = e.minR;
+      out.boxRows = e.maxR + k - e.minR;
       return;
     }
   }
   out.kind = kJobGeneral;
-  out.boxX = out.boxY = 0;
+  out.boxX = out.boxY = out.boxRows = 0;
 }
 
 inline uint32_t slotField(int k, int phase, int copy) { return static_cast<uint32_t>(weightSlotField(k, phase, copy)); }
@@ -221,7 +259,7 @@ inline uint32_t slotField(int k, int phase, int copy) { return static_cast<uint3
 // compact records of a share job (kernels.cuh)
 void writeShareRecords(const HostPlan& h, const GatherJob& job, uint32_t* out) {
   const int k = h.kernelSize, copies = weightCopies(k), kShareRows = shareRows(k), kShareH = shareH(k);
-  const int x0 = job.outX, y0 = job.outY & kJobRowMask, boxX = job.boxXY & 0xffff, boxY = job.boxXY >> 16;
+  const int x0 = job.outX, y0 = job.outY & kJobRowMask, boxX = jobBoxX(job.boxXY), boxY = jobBoxY(job.boxXY);
   const int pitch = stageBoxW(k, 2);
   const bool stay = ((job.outY >> kJobKindShift) & kJobKindMask) == kJobShareStay;
   for (int wx = 0; wx < kShareW / 32; ++wx) {
@@ -259,7 +297,7 @@ void writeShareRecords(const HostPlan& h, const GatherJob& job, uint32_t* out) {
 void writeTileRecords(const HostPlan& h, const GatherJob& job, uint32_t* out) {
   const int k = h.kernelSize, copies = weightCopies(k);
   const int kind = (job.outY >> kJobKindShift) & kJobKindMask;
-  const int x0 = job.outX & ~kJobQuadMask, y0 = job.outY & kJobRowMask, boxX = job.boxXY & 0xffff, boxY = job.boxXY >> 16;
+  const int x0 = job.outX & ~kJobQuadMask, y0 = job.outY & kJobRowMask, boxX = jobBoxX(job.boxXY), boxY = jobBoxY(job.boxXY);
   const int pitch = stageBoxW(k, boxClassOf(kind));
   // the live rectangle: the whole tile, or one quadrant
   const int quad = (job.outX & kJobQuadMask) - 1;
@@ -267,7 +305,10 @@ void writeTileRecords(const HostPlan& h, const GatherJob& job, uint32_t* out) {
   const int lx1 = quad < 0 ? x0 + kGatherTileW : lx0 + 16, ly1 = quad < 0 ? y0 + kFrameTileH : ly0 + 16;
   for (int w = 0; w < kGroupWarps; ++w)
     for (int j = 0; j < kRowsPerPatchStep; ++j) {
-      uint32_t* words = out + static_cast<size_t>(w) * 32 * 4;
+      // a quadrant job: only its live warps (rows) and steps (columns) have records, 32 x uint2 per warp
+      if (quad >= 0 && ((w >> 2) != (quad >> 1) || (j >> 1) != (quad & 1))) continue;
+      uint32_t* words = quad < 0 ? out + static_cast<size_t>(w) * 32 * 4 : out + static_cast<size_t>(w & 3) * 32 * 2;
+      const int stride = quad < 0 ? 4 : 2, word = quad < 0 ? j : (j & 1);
       // the pixels of the patch that exist, in position order; the others keep a position that fails the bounds check
       int slot[32], laneOf[32], copyOf[32], posOf[32], n = 0;
       bool present[32] = {};
@@ -281,7 +322,7 @@ void writeTileRecords(const HostPlan& h, const GatherJob& job, uint32_t* out) {
       dealLanes(k, copies, n, slot, laneOf, copyOf);  // n < 32: identity order
       int lane = n;
       for (int pos = 0; pos < 32; ++pos)
-        if (!present[pos]) words[(lane++) * 4 + j] = (static_cast<uint32_t>(pos) << 16) | kRecordSkip;
+        if (!present[pos]) words[(lane++) * stride + word] = (static_cast<uint32_t>(pos) << 16) | kRecordSkip;
       for (int i = 0; i < n; ++i) {
         const int pos = posOf[i];
         const int x = x0 + kTilePatchW * j + (pos & (kTilePatchW - 1)), y = y0 + kTilePatchH * w + pos / kTilePatchW;
@@ -293,13 +334,53 @@ void writeTileRecords(const HostPlan& h, const GatherJob& job, uint32_t* out) {
           col0 = boxX + (cw - boxX + h.inW) % h.inW;
         }
         const int off = ((sp.rowPhase >> 10) - boxY) * pitch + (col0 - boxX);
-        words[laneOf[i] * 4 + j] = static_cast<uint32_t>(off) | (static_cast<uint32_t>(pos) << 16) |
-                                   (slotField(k, sp.rowPhase & 1023, copyOf[i]) << 17);
+        words[laneOf[i] * stride + word] = static_cast<uint32_t>(off) | (static_cast<uint32_t>(pos) << 16) |
+                                           (slotField(k, sp.rowPhase & 1023, copyOf[i]) << 17);
       }
     }
 }
 
 }  // namespace
+
+// Deals load[g] pixels of every group to passes of `lanes` pixels with at most h[q] pixels of one group in pass q
+// (augmenting paths: a pixel that finds its admissible passes full moves a pixel of another group on).
+struct PassDealer {
+  int groups, passes, lanes;
+  int h[4], share[16][4], fill[4];
+  bool seen[4];
+
+  bool put(int g) {
+    for (int q = 0; q < passes; ++q) {
+      if (seen[q] || share[g][q] >= h[q]) continue;
+      seen[q] = true;
+      if (fill[q] < lanes) {
+        ++share[g][q];
+        ++fill[q];
+        return true;
+      }
+      for (int other = 0; other < groups; ++other) {
+        if (other == g || share[other][q] == 0) continue;
+        --share[other][q];
+        if (put(other)) {  // `other` found a seat in a pass not visited yet: g takes the one it left
+          ++share[g][q];
+          return true;
+        }
+        ++share[other][q];
+      }
+    }
+    return false;
+  }
+  bool deal(const int* load) {
+    std::memset(share, 0, sizeof(share));
+    std::fill(fill, fill + 4, 0);
+    for (int g = 0; g < groups; ++g)
+      for (int i = 0; i < load[g]; ++i) {
+        std::fill(seen, seen + 4, false);
+        if (!put(g)) return false;
+      }
+    return true;
+  }
+};
 
 int dealLanes(int k, int copies, int n, const int* slot, int* laneOf, int* copyOf) {
   const int groups = weightBankGroups(k), lanesPerPass = weightLanesPerPass(k), passes = 32 / lanesPerPass;
@@ -312,6 +393,7 @@ int dealLanes(int k, int copies, int n, const int* slot, int* laneOf, int* copyO
     GroupMatcher m{n, copies, 0, base, {}, {}, {}};
     for (m.cap = 4; m.cap <= 32; ++m.cap)
       if (m.run()) break;
+    m.balance();
     for (int i = 0; i < n; ++i) {
       group[i] = m.groupOf[i];
       copyOf[i] = (m.groupOf[i] - base[i]) & 7;
@@ -320,27 +402,38 @@ int dealLanes(int k, int copies, int n, const int* slot, int* laneOf, int* copyO
     for (int i = 0; i < n; ++i) group[i] = slot[i] & (groups - 1);
   }
   // How many pixels of each group go to each pass (quarter-warp).  A pass costs as many wavefronts as its fullest group
-  // holds pixels, so a group with more pixels than passes should put its surplus into the pass where another group
-  // already did: groups in order of decreasing load, every pixel to the pass (with a free lane) where it raises the
-  // cost least, then where the group has fewest pixels, then the emptiest.
-  int load[16] = {}, byLoad[16];
+  // holds pixels, so the load costs H = h[0] + .. + h[passes - 1] when no group has more than h[q] pixels in pass q.
+  // Exact: the smallest H (from max(passes, fullest group) upwards) and pass heights h for which the pixels can be dealt
+  // -- a transportation problem of groups x passes, solved with augmenting paths.  (A greedy deal ended at 6 - 8
+  // wavefronts for most warps whose fullest group holds 5 pixels; cfg2: 4.97 -> 4.5 per load in tile jobs.)
+  int load[16] = {};
   for (int i = 0; i < n; ++i) ++load[group[i]];
-  for (int g = 0; g < groups; ++g) byLoad[g] = g;
-  std::stable_sort(byLoad, byLoad + groups, [&](int a, int b) { return load[a] > load[b]; });
-  int height[4] = {}, fill[4] = {}, share[16][4] = {};
-  for (int gi = 0; gi < groups; ++gi) {
-    const int g = byLoad[gi];
-    for (int item = 0; item < load[g]; ++item) {
-      int best = -1;
-      for (int q = 0; q < passes; ++q) {
-        if (fill[q] >= lanesPerPass) continue;
-        if (best < 0) { best = q; continue; }
-        const int raiseQ = share[g][q] + 1 > height[q], raiseB = share[g][best] + 1 > height[best];
-        if (raiseQ != raiseB ? raiseQ < raiseB : (share[g][q] != share[g][best] ? share[g][q] < share[g][best] : fill[q] < fill[best])) best = q;
+  int share[16][4] = {}, height[4] = {};
+  {
+    int fullest = 0;
+    for (int g = 0; g < groups; ++g) fullest = std::max(fullest, load[g]);
+    PassDealer d{groups, passes, lanesPerPass, {}, {}, {}, {}};
+    bool done = false;
+    for (int total = std::max(passes, fullest); !done; ++total) {
+      // non-increasing heights h[0] >= h[1] >= .. >= 1 with sum `total`, most balanced first
+      int h[4] = {1, 1, 1, 1};
+      auto tryHeights = [&]() {
+        std::copy(h, h + 4, d.h);
+        if (!d.deal(load)) return false;
+        std::memcpy(share, d.share, sizeof(share));
+        std::copy(h, h + 4, height);
+        return true;
+      };
+      if (passes == 2) {
+        for (h[1] = total / 2; h[1] >= 1 && !done; --h[1]) { h[0] = total - h[1]; done = tryHeights(); }
+      } else {
+        for (h[3] = total / 4; h[3] >= 1 && !done; --h[3])
+          for (h[2] = (total - h[3]) / 3; h[2] >= h[3] && !done; --h[2])
+            for (h[1] = (total - h[3] - h[2]) / 2; h[1] >= h[2] && !done; --h[1]) {
+              h[0] = total - h[3] - h[2] - h[1];
+              done = tryHeights();
+            }
       }
-      ++fill[best];
-      ++share[g][best];
-      height[best] = std::max(height[best], share[g][best]);
     }
   }
   // Which pixels: neighbouring columns of a group stay in one pass -- they tend to carry the same phase (the same slot:
@@ -435,14 +528,14 @@ void buildGatherPlan(const HostPlan& h, bool stageTiles, GatherPlan& g) {
         const TileClass& c = cls[static_cast<size_t>(ty) * tilesX + tx];
         if (c.kind != kind || (kind == kJobClass0 && c.quads != (step == 6))) continue;
         for (int q = 0; q < (c.quads ? 4 : 1); ++q) {
-          GatherJob job{tx * 32, ty * kFrameTileH | (kind << kJobKindShift), c.boxX | (c.boxY << 16), 0};
+          GatherJob job{tx * 32, ty * kFrameTileH | (kind << kJobKindShift), kind == kJobGeneral ? 0 : jobBoxField(c.boxX, c.boxY, c.boxRows), 0};
           if (c.quads) {
             job.outX |= q + 1;
-            job.boxXY = c.quadBoxX[q] | (c.quadBoxY[q] << 16);
+            job.boxXY = jobBoxField(c.quadBoxX[q], c.quadBoxY[q], c.quadBoxRows[q]);
           }
           if (kind != kJobGeneral) {
             job.recordOffset = static_cast<int>(offset / 16);
-            offset += boxClassOf(kind) == 2 ? shareJobRecordBytes(k) : kTileJobRecordBytes;
+            offset += boxClassOf(kind) == 2 ? shareJobRecordBytes(k) : tileJobRecordBytes(job.outX);
           }
           g.jobs.push_back(job);
         }

@@ -5,10 +5,6 @@
 
 #include <cstdint>
 
-#ifndef T360_STAGES
-#define T360_STAGES 2
-#endif
-
 namespace t360 {
 
 // One gather launch: dst[y][x] = interpolate(src, samples[y][x]) for a whole plane.
@@ -35,9 +31,19 @@ struct GatherParams {
 // A JOB is a block of output pixels of one image plane:
 struct GatherJob {
   int outX, outY;    // outY carries the job kind (kJobKindShift) and the image plane (kJobPlaneShift)
-  int boxXY;         // boxX | boxY << 16 (boxX % 16 == 0)
+  int boxXY;         // boxX | boxY << 16 | (row chunks - 1): boxX % 16 == 0, its low four bits carry the chunk count
   int recordOffset;  // of the job's compact records, in 16-byte units from the plane's record buffer
 };
+// A job's source box is brought in as 1 .. 16 TMA boxes of kBoxChunkRows rows each, only as many as its windows span
+// (cfg2: the share jobs span 63 of the 72 rows their stage buffer holds, the 32 x 32 tiles 47 of 64, the quadrants 36
+// of 64: 21 % fewer bytes from L2 into shared memory than with whole boxes).  The tensor maps describe one chunk.
+constexpr int kBoxChunkRows = 8;
+__host__ __device__ constexpr int jobBoxField(int boxX, int boxY, int rows) {
+  return boxX | (boxY << 16) | ((rows + kBoxChunkRows - 1) / kBoxChunkRows - 1);
+}
+__host__ __device__ constexpr int jobBoxX(int boxXY) { return boxXY & 0xfff0; }
+__host__ __device__ constexpr int jobBoxY(int boxXY) { return (int)((unsigned)boxXY >> 16); }
+__host__ __device__ constexpr int jobBoxChunks(int boxXY) { return (boxXY & 15) + 1; }
 using StagedTile = GatherJob;
 constexpr int kJobClass0 = 0, kJobClass1 = 1, kJobGeneral = 2, kJobShareStay = 3, kJobShare = 4, kJobNop = 5, kJobExit = 6, kJobSeam = 7;
 // A 32 x 32 job may cover one 16 x 16 quadrant of its tile only (a tile whose windows fit no box as a whole, but whose
@@ -68,17 +74,13 @@ __host__ __device__ constexpr int shareH(int k) { return 4 * shareRows(k); }
 constexpr int kNumBoxClasses = 3;  // tensor map index: 0 = class 0 / seam, 1 = class 1, 2 = share
 __host__ __device__ constexpr int boxClassOf(int kind) { return (kind == kJobShare || kind == kJobShareStay) ? 2 : (kind == kJobClass1 ? 1 : 0); }
 __host__ __device__ constexpr int stageBoxW(int /*k*/, int cls) { return cls == 2 ? 192 : (cls == 0 ? 208 : 240); }
-__host__ __device__ constexpr int stageBoxH(int k, int cls) {
-#if T360_STAGES == 3
-  return k == 8 ? (cls == 2 ? 80 : (cls == 0 ? 72 : 128)) : (cls == 2 ? 68 : (cls == 0 ? 63 : 96));
-#else
+__host__ __device__ constexpr int stageBoxH(int k, int cls) {  // multiples of kBoxChunkRows
   return k == 8 ? (cls == 2 ? 80 : (cls == 0 ? 72 : 128)) : (cls == 2 ? 72 : (cls == 0 ? 64 : 96));
-#endif
 }
 // Stages of a group's ring (a stage = one box + one record buffer).  Three fit beside the cubic tables if the boxes lose
 // a few rows, but measured slower (64.9 vs 58.1 us per cfg2 frame): they leave the SM only ~3 KB of L1 for the general
 // jobs and the job headers.
-__host__ __device__ constexpr int gatherStages(int k) { return (T360_STAGES == 3 && k != 8) ? 3 : 2; }
+__host__ __device__ constexpr int gatherStages(int /*k*/) { return 2; }
 // one stage buffer (TMA destinations need 128-byte alignment; the tail absorbs the over-read of a window's last word)
 __host__ __device__ constexpr int stageBytesOf(int k) {
   const int a = stageBoxW(k, 2) * stageBoxH(k, 2), b = stageBoxW(k, 0) * stageBoxH(k, 0);
@@ -89,13 +91,18 @@ __host__ __device__ constexpr int stageBytesOf(int k) {
 // weights of a slot are K*K/8 16-byte vectors (k >= 4), vector v of copy c at byte
 //     v * weightVectorStride(k, copies) + c * 16384 + slot * 16
 // A 128-bit shared load is served 8 lanes (one quarter-warp) at a time out of 8 bank groups of 16 bytes, the group
-// being slot & 7.  With 32 pixels per warp the fullest group holds ~6-7 of them whatever the hash (bank model: 6.3
-// wavefronts per load instead of 4).  So the cubic table is kept TWICE, the second copy rotated by one bank group
-// (slot s of copy 1 sits where slot (s & ~7) | ((s + 1) & 7) of copy 0 would), and the host -- which already deals the
-// pixels of a row segment to lanes -- picks the copy per pixel so that no group is asked more than ~4 times: 4.2-4.5.
+// being slot & 7 = (fracX >> 1) & 7.  With 32 pixels per warp the fullest group holds ~6-7 of them whatever the hash
+// (bank model: 6.3 wavefronts per load instead of 4).  So the cubic table is kept TWICE, the second copy rotated by one
+// bank group (slot s of copy 1 sits where slot (s & ~7) | ((s + 1) & 7) of copy 0 would; rotations by 2 - 5 groups
+// model worse), and the host -- which already deals the pixels of a row segment to lanes -- picks the copy per pixel so
+// that the groups are evenly filled (an EMPTY group costs as much as an overfull one: a quarter-warp that finds no pixel
+// in one group must take two of another) and then deals the pixels to quarter-warps exactly (gather_plan.cpp:
+// GroupMatcher, PassDealer): 4.4 wavefronts per load in share jobs, 4.5 in tile jobs of the cfg2 plan in the bank model
+// (which reproduces ncu's per-instruction counts to 1 %); with the group taken from fracX >> 2 it is 4.3 / 4.75, with a
+// group that depends on fracY a share job's column could not keep its lane.
 __host__ __device__ constexpr int weightSlotOf(int k, int phase) {
-  return k == 2 ? ((phase & ~31) | ((phase & 1) << 4) | ((phase & 31) >> 1))
-                : ((phase & ~31) | ((phase & 3) << 3) | ((phase & 31) >> 2));
+  (void)k;
+  return (phase & ~31) | ((phase & 1) << 4) | ((phase & 31) >> 1);
 }
 __host__ __device__ constexpr int weightCopies(int k) { return k == 4 ? 2 : 1; }
 __host__ __device__ constexpr int weightVectorStride(int k, int copies) { return (k == 2 ? 8192 : 16384) * copies; }
@@ -138,6 +145,10 @@ __host__ __device__ constexpr int weightLanesPerPass(int k) { return k == 2 ? 16
 __host__ __device__ constexpr int shareWarpRecordBytes(int k) { return shareRows(k) / 8 * 32 * 16 + 32 * 4; }
 __host__ __device__ constexpr int shareJobRecordBytes(int k) { return kGroupWarps * shareWarpRecordBytes(k); }
 constexpr int kTileJobRecordBytes = kGroupWarps * 32 * 16;
+// a quadrant job keeps the records of its four live warps and two live steps only: warp w & 3, 32 x uint2 by lane (words
+// of steps 2 * (quadrant & 1) and 2 * (quadrant & 1) + 1)
+constexpr int kQuadJobRecordBytes = kGroupWarps / 2 * 32 * 8;
+__host__ __device__ constexpr int tileJobRecordBytes(int outXField) { return (outXField & kJobQuadMask) ? kQuadJobRecordBytes : kTileJobRecordBytes; }
 // one stage of a ring: the header (padded to 128 bytes) and the records of a job
 __host__ __device__ constexpr int stageRecordBytes(int k) {
   return 128 + (shareJobRecordBytes(k) > kTileJobRecordBytes ? shareJobRecordBytes(k) : kTileJobRecordBytes);
