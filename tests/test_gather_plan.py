@@ -32,6 +32,14 @@ def box_h(k, kind):
     return 72 if kind in (SHARE, SHARE_STAY) else (96 if kind == CLASS1 else 64)
 
 
+def box_variant_rows(k, kind, v):
+    """kernels.cuh boxVariantRows: the box a job names is one of three heights of its class (class 1: one)."""
+    h = box_h(k, kind)
+    if kind == CLASS1 or v == 0:
+        return h
+    return h - 8 * v if kind in (SHARE, SHARE_STAY) else h - 8 - 8 * v
+
+
 def share_rows(k):
     return 8
 
@@ -139,7 +147,7 @@ def test_gather_plan_invariants(group, name, plane):
     next_offset = 0
     for ox, oy, boxxy, rec_off in jobs:
         kind, y0 = (oy >> KIND_SHIFT) & 15, oy & ROW_MASK
-        bx, by, chunks = boxxy & 0xFFF0, boxxy >> 16, (boxxy & 15) + 1  # the box arrives as `chunks` TMA boxes of 8 rows
+        bx, by, variant = boxxy & 0xFFF0, boxxy >> 16, boxxy & 15  # variant: which of the class's box heights is loaded
         quad, ox = (ox & 7) - 1, ox & ~7  # 16 x 16 quadrant of the tile this job covers (-1: all of it)
         assert ox % 32 == 0 and y0 % 32 == 0 and quad < 4 and (quad < 0 or kind == CLASS0)
         if kind == GENERAL:
@@ -148,9 +156,10 @@ def test_gather_plan_invariants(group, name, plane):
             continue
         pitch, bh = box_w(kind), box_h(k, kind)
         assert bx % 16 == 0 and rec_off == next_offset, "records are laid out in launch order, 16-byte units"
-        assert bh % 8 == 0 and chunks * 8 <= bh, "the chunks of a box fit its stage buffer"
-        bh = chunks * 8  # what the kernel loads: every window must lie inside it (checked below) ...
-        rows_used = 0    # ... and the last chunk must be needed
+        assert variant < 3 and (kind != CLASS1 or variant == 0)
+        bh = box_variant_rows(k, kind, variant)  # what the kernel loads: every window must lie inside it (checked below) ...
+        lower = box_variant_rows(k, kind, variant + 1) if variant < 2 and kind != CLASS1 else 0  # ... but not inside the next lower box
+        rows_used = 0
         if kind in (SHARE, SHARE_STAY):
             R = share_rows(k)
             sh, nwords = 4 * R, R // 8 * 128 + 32  # job height; 32-bit words per warp
@@ -185,7 +194,7 @@ def test_gather_plan_invariants(group, name, plane):
                 assert (col0 - bx + k <= pitch).all() and (row0[:, -1] - by + k <= bh).all()
                 assert (col0 >= 0).all() and (col0 + k <= iw).all() and (row0 >= 0).all() and (row0 + k <= ih).all()
                 rows_used = max(rows_used, int(row0.max()) - by + k)
-            assert rows_used > bh - 8, "no row chunk is loaded in vain"
+            assert rows_used > lower, "the job names the lowest box that holds its windows"
             produced[y0:y0 + sh, ox:ox + 64] += 1
             continue
         # 32 x 32 jobs: class 0 (also one quadrant of a tile), class 1, seam.  Warp w, word j = one pixel of the 8 x 4
@@ -213,7 +222,7 @@ def test_gather_plan_invariants(group, name, plane):
         assert (row0 == want[..., 1] >> 10).all()
         wimg.check(fields, want[..., 1] & 1023)
         assert (offs % pitch + k <= pitch).all() and (offs // pitch + k <= bh).all() and (row0 >= 0).all() and (row0 + k <= ih).all()
-        assert int((offs // pitch).max()) + k > bh - 8, "no row chunk is loaded in vain"
+        assert int((offs // pitch).max()) + k > lower, "the job names the lowest box that holds its windows"
         if kind == SEAM:
             assert iw % 16 == 0 and bx < iw < bx + pitch, "the box of a seam tile wraps around the border"
             assert (col0 % iw == want[..., 0] % iw).all()

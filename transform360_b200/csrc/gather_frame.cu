@@ -279,8 +279,6 @@ __device__ __forceinline__ void computeGeneralJob(const PlaneView& pv, int outX,
   sv.misalign = (int)(reinterpret_cast<uintptr_t>(pv.src) & 3);
   sv.words = reinterpret_cast<const uint32_t*>(pv.src - sv.misalign);
   sv.w = pv.srcW; sv.h = pv.srcH; sv.pitch = pv.srcPitch;
-  const int misalign8 = (int)(reinterpret_cast<uintptr_t>(pv.src) & 7);
-  const uint2* chunks = reinterpret_cast<const uint2*>(pv.src - misalign8);
   const int y0 = outY + warp * kRowsPerThread;
   if (outX + lane >= pv.dstW) return;
   // full records, tile-major over tiles of 32 x gatherTileH(K) pixels
@@ -297,35 +295,19 @@ __device__ __forceinline__ void computeGeneralJob(const PlaneView& pv, int outX,
 #pragma unroll
     for (int b = 0; b < kBatch; ++b) {
       const int col0 = recordCol0(full[jb + b].x), row0 = full[jb + b].y >> 10;
-      // Window rows are fetched as the 8-byte aligned chunk that holds their first byte, plus the next word(s) only in
-      // the lanes whose window crosses the chunk's end: these windows lie a sector apart from each other, so every
-      // load instruction costs the data pipe one wavefront per lane -- 1.4 loads per row instead of two (three for
-      // K = 8).  Interior = no wrapping, and nothing is read outside [src, src + (h - 1) * pitch + w): the first chunk
-      // must not start before the plane, the last one not end behind it.
-      const int first = row0 * sv.pitch + col0 + misalign8, last = first + (K - 1) * sv.pitch + K - 1;
-      interior[b] = y0 + jb + b < pv.dstH && col0 >= 0 && row0 >= 0 && col0 + K <= sv.w && row0 + K <= sv.h &&
-                    (first & ~7) >= misalign8 && (last | 7) + 1 - misalign8 <= (sv.h - 1) * sv.pitch + sv.w;
+      // no wrapping, and the aligned word reads stay inside the row even when the pitch equals the width
+      interior[b] = y0 + jb + b < pv.dstH && col0 >= 0 && row0 >= 0 && col0 + (K == 2 ? 8 : K + 4) <= sv.w && row0 + K <= sv.h;
 #pragma unroll
       for (int r = 0; r < K; ++r) {
         W[b][r].b[0] = 0;
         if constexpr (K == 8) W[b][r].b[1] = 0;
         if (interior[b]) {
-          const int off = first + r * sv.pitch;
-          const uint2* q = chunks + (off >> 3);
-          const int sh = (off & 7) * 8;  // 0, 8 .. 56; the funnel shifts below take it modulo 32
-          const uint2 a = __ldg(q);
-          const bool upper = (sh & 32) != 0;
-          if constexpr (K == 8) {
-            uint2 c = make_uint2(0u, 0u);
-            if (sh != 0) c = __ldg(q + 1);
-            const uint32_t w0 = upper ? a.y : a.x, w1 = upper ? c.x : a.y, w2 = upper ? c.y : c.x;
-            W[b][r].b[0] = __funnelshift_r(w0, w1, sh);
-            W[b][r].b[1] = __funnelshift_r(w1, w2, sh);
-          } else {
-            uint32_t c = 0;
-            if ((off & 7) + K > 8) c = __ldg(reinterpret_cast<const uint32_t*>(q + 1));
-            W[b][r].b[0] = __funnelshift_r(upper ? a.y : a.x, upper ? c : a.y, sh);
-          }
+          const int off = (row0 + r) * sv.pitch + col0 + sv.misalign;
+          const uint32_t* q = sv.words + (off >> 2);
+          const int sh = (off & 3) * 8;
+          const uint32_t q0 = __ldg(q), q1 = __ldg(q + 1);
+          W[b][r].b[0] = __funnelshift_r(q0, q1, sh);
+          if constexpr (K == 8) W[b][r].b[1] = __funnelshift_r(q1, __ldg(q + 2), sh);
         }
       }
     }
@@ -342,7 +324,7 @@ __device__ __forceinline__ void computeGeneralJob(const PlaneView& pv, int outX,
 }
 
 struct FrameTensorMaps {
-  CUtensorMap map[kMaxFramePlanes][kNumBoxClasses];
+  CUtensorMap map[kMaxFramePlanes][kNumBoxClasses][kBoxVariants];
 };
 
 __device__ __forceinline__ void mbarArrive(uint64_t* bar) {
@@ -382,9 +364,7 @@ gatherFrameKernel(const __grid_constant__ FrameGatherParams p, StagedParams jobs
   constexpr uint32_t kBox0 = stageBoxW(K, 0) * stageBoxH(K, 0), kBox1 = stageBoxW(K, 1) * stageBoxH(K, 1),
                      kBoxShare = stageBoxW(K, 2) * stageBoxH(K, 2);
   static_assert(kBox1 + 64 <= 2 * kStage && kBox0 + 64 <= kStage && kBoxShare + 64 <= kStage, "boxes must fit their stage buffers");
-  static_assert(stageBoxH(K, 0) % kBoxChunkRows == 0 && stageBoxH(K, 1) % kBoxChunkRows == 0 && stageBoxH(K, 2) % kBoxChunkRows == 0 &&
-                stageBoxH(K, 1) <= 16 * kBoxChunkRows && (stageBoxW(K, 0) * kBoxChunkRows) % 128 == 0 && (stageBoxW(K, 1) * kBoxChunkRows) % 128 == 0 &&
-                (stageBoxW(K, 2) * kBoxChunkRows) % 128 == 0, "a box is a whole number of chunks, each a 128-byte aligned TMA destination");
+  static_assert(boxVariantRows(K, 0, kBoxVariants - 1) > 0 && boxVariantRows(K, 2, kBoxVariants - 1) > 0, "");
   extern __shared__ __align__(128) unsigned char smem[];
   unsigned char* wsmem = smem;
   PlaneView* planes = reinterpret_cast<PlaneView*>(smem + L::kPlanes);
@@ -436,9 +416,8 @@ gatherFrameKernel(const __grid_constant__ FrameGatherParams p, StagedParams jobs
       const int pl = h.y >> kJobPlaneShift;
       const uint32_t recBytes = boxClassOf(kind) == 2 ? shareJobRecordBytes(K) : tileJobRecordBytes(h.x);
       asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(planes[pl].records + (unsigned)h.w), "r"(recBytes) : "memory");
-      for (int c = 0; c < jobBoxChunks(h.z); ++c)  // (a seam job's second box is left to the copy itself)
-        asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];"
-                     ::"l"(reinterpret_cast<uint64_t>(&maps.map[pl][boxClassOf(kind)])), "r"(jobBoxX(h.z)), "r"(jobBoxY(h.z) + c * kBoxChunkRows) : "memory");
+      asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];"
+                   ::"l"(reinterpret_cast<uint64_t>(&maps.map[pl][boxClassOf(kind)][jobBoxVariant(h.z)])), "r"(jobBoxX(h.z)), "r"(jobBoxY(h.z)) : "memory");
     };
     // (the first TWO batches are static, so that the first job is not held up by the round trip of an atomic)
     int4 batch = loadBatch(producer * 2 * kClaimBatch);
@@ -489,16 +468,14 @@ gatherFrameKernel(const __grid_constant__ FrameGatherParams p, StagedParams jobs
         if (kind == kJobShare || kind == kJobShareStay || kind == kJobClass0 || kind == kJobClass1 || kind == kJobSeam) {
           const int pl = h.y >> kJobPlaneShift;
           const bool share = boxClassOf(kind) == 2;
-          // the source box: only the row chunks the job's windows span (kernels.cuh: kBoxChunkRows), one TMA box each
-          const int cls = boxClassOf(kind), chunks = jobBoxChunks(h.z), boxX = jobBoxX(h.z), boxY = jobBoxY(h.z);
-          const uint32_t chunkBytes = (share ? kBoxShare / stageBoxH(K, 2) : (kind == kJobClass1 ? kBox1 / stageBoxH(K, 1) : kBox0 / stageBoxH(K, 0))) * kBoxChunkRows;
+          // the source box: the lowest variant of its class that holds the rows the job's windows span (kernels.cuh)
+          const int cls = boxClassOf(kind), variant = jobBoxVariant(h.z), boxX = jobBoxX(h.z), boxY = jobBoxY(h.z);
+          const uint32_t boxBytes = (uint32_t)(stageBoxW(K, cls) * boxVariantRows(K, cls, variant));
           const uint32_t recBytes = share ? shareJobRecordBytes(K) : tileJobRecordBytes(h.x);
-          mbarExpectTx(full + st, (kind == kJobSeam ? 2 : 1) * chunks * chunkBytes + recBytes);
-          for (int c = 0; c < chunks; ++c) {
-            tmaLoadBox(groupBase + st * kStage + c * chunkBytes, &maps.map[pl][cls], boxX, boxY + c * kBoxChunkRows, full + st);
-            if (kind == kJobSeam)  // the part of the window beyond the right border, from the left of the plane
-              tmaLoadBox(groupBase + (st + 1) * kStage + c * chunkBytes, &maps.map[pl][0], boxX - planes[pl].srcW, boxY + c * kBoxChunkRows, full + st);
-          }
+          mbarExpectTx(full + st, (kind == kJobSeam ? 2 : 1) * boxBytes + recBytes);
+          tmaLoadBox(groupBase + st * kStage, &maps.map[pl][cls][variant], boxX, boxY, full + st);
+          if (kind == kJobSeam)  // the part of the window beyond the right border, from the left of the plane
+            tmaLoadBox(groupBase + (st + 1) * kStage, &maps.map[pl][0][variant], boxX - planes[pl].srcW, boxY, full + st);
           bulkCopyToShared(rec + 128, planes[pl].records + (unsigned)h.w, recBytes, full + st);
         } else {
           mbarArrive(full + st);  // general job / end of list: the header is all there is
@@ -645,9 +622,10 @@ cudaError_t launchGatherFrame(const FrameGatherParams& p, const StagedParams& jo
   if (jobs.numTiles <= 0) return cudaSuccess;
   if (p.numPlanes < 1 || p.numPlanes > kMaxFramePlanes) return cudaErrorInvalidValue;
   FrameTensorMaps maps;
-  std::memcpy(&maps, tensorMaps, sizeof(CUtensorMap) * kNumBoxClasses * p.numPlanes);
+  std::memcpy(&maps, tensorMaps, sizeof(CUtensorMap) * kNumBoxClasses * kBoxVariants * p.numPlanes);
   for (int i = p.numPlanes; i < kMaxFramePlanes; ++i)  // unused entries: valid descriptors that no job refers to
-    for (int c = 0; c < kNumBoxClasses; ++c) maps.map[i][c] = maps.map[0][c];
+    for (int c = 0; c < kNumBoxClasses; ++c)
+      for (int v = 0; v < kBoxVariants; ++v) maps.map[i][c][v] = maps.map[0][c][v];
   switch (p.kernelSize) {
     case 2: return launchFrameK<2, weightCopies(2), gatherGroups(2)>(p, jobs, maps, numSMs, stream, programmatic);
     case 4: return launchFrameK<4, weightCopies(4), gatherGroups(4)>(p, jobs, maps, numSMs, stream, programmatic);

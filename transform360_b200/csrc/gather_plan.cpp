@@ -528,10 +528,11 @@ void buildGatherPlan(const HostPlan& h, bool stageTiles, GatherPlan& g) {
         const TileClass& c = cls[static_cast<size_t>(ty) * tilesX + tx];
         if (c.kind != kind || (kind == kJobClass0 && c.quads != (step == 6))) continue;
         for (int q = 0; q < (c.quads ? 4 : 1); ++q) {
-          GatherJob job{tx * 32, ty * kFrameTileH | (kind << kJobKindShift), kind == kJobGeneral ? 0 : jobBoxField(c.boxX, c.boxY, c.boxRows), 0};
+          GatherJob job{tx * 32, ty * kFrameTileH | (kind << kJobKindShift),
+                        kind == kJobGeneral ? 0 : jobBoxField(c.boxX, c.boxY, boxVariantFor(k, boxClassOf(kind), c.boxRows)), 0};
           if (c.quads) {
             job.outX |= q + 1;
-            job.boxXY = jobBoxField(c.quadBoxX[q], c.quadBoxY[q], c.quadBoxRows[q]);
+            job.boxXY = jobBoxField(c.quadBoxX[q], c.quadBoxY[q], boxVariantFor(k, 0, c.quadBoxRows[q]));
           }
           if (kind != kJobGeneral) {
             job.recordOffset = static_cast<int>(offset / 16);

@@ -31,19 +31,20 @@ struct GatherParams {
 // A JOB is a block of output pixels of one image plane:
 struct GatherJob {
   int outX, outY;    // outY carries the job kind (kJobKindShift) and the image plane (kJobPlaneShift)
-  int boxXY;         // boxX | boxY << 16 | (row chunks - 1): boxX % 16 == 0, its low four bits carry the chunk count
+  int boxXY;         // boxX | boxY << 16 | box variant: boxX % 16 == 0, its low four bits name the tensor map (box height)
   int recordOffset;  // of the job's compact records, in 16-byte units from the plane's record buffer
 };
-// A job's source box is brought in as 1 .. 16 TMA boxes of kBoxChunkRows rows each, only as many as its windows span
-// (cfg2: the share jobs span 63 of the 72 rows their stage buffer holds, the 32 x 32 tiles 47 of 64, the quadrants 36
-// of 64: 21 % fewer bytes from L2 into shared memory than with whole boxes).  The tensor maps describe one chunk.
-constexpr int kBoxChunkRows = 8;
-__host__ __device__ constexpr int jobBoxField(int boxX, int boxY, int rows) {
-  return boxX | (boxY << 16) | ((rows + kBoxChunkRows - 1) / kBoxChunkRows - 1);
-}
+// A job's source box is ONE TMA box, but not always the whole stage buffer: every box class has kBoxVariants tensor maps
+// of decreasing height (boxVariantRows below), and a job names the lowest one that still holds the rows its windows span
+// (cfg2: the share jobs span 63 of the 72 rows their stage buffer holds, the 32 x 32 tiles 47 of 64, the quadrants 36 of
+// 64: 18 % fewer bytes from L2 into shared memory than with whole boxes).  Loading a box as a series of 8-row TMA boxes
+// instead -- one tensor map per class, any height -- saved 21 % of the bytes but cost 0.3 us of producer time per job
+// (6 - 9 TMA instructions + as many L2 prefetches): 67.3 us per cfg2 frame against 56.4.
+constexpr int kBoxVariants = 3;
+__host__ __device__ constexpr int jobBoxField(int boxX, int boxY, int variant) { return boxX | (boxY << 16) | variant; }
 __host__ __device__ constexpr int jobBoxX(int boxXY) { return boxXY & 0xfff0; }
 __host__ __device__ constexpr int jobBoxY(int boxXY) { return (int)((unsigned)boxXY >> 16); }
-__host__ __device__ constexpr int jobBoxChunks(int boxXY) { return (boxXY & 15) + 1; }
+__host__ __device__ constexpr int jobBoxVariant(int boxXY) { return boxXY & 15; }
 using StagedTile = GatherJob;
 constexpr int kJobClass0 = 0, kJobClass1 = 1, kJobGeneral = 2, kJobShareStay = 3, kJobShare = 4, kJobNop = 5, kJobExit = 6, kJobSeam = 7;
 // A 32 x 32 job may cover one 16 x 16 quadrant of its tile only (a tile whose windows fit no box as a whole, but whose
@@ -74,8 +75,20 @@ __host__ __device__ constexpr int shareH(int k) { return 4 * shareRows(k); }
 constexpr int kNumBoxClasses = 3;  // tensor map index: 0 = class 0 / seam, 1 = class 1, 2 = share
 __host__ __device__ constexpr int boxClassOf(int kind) { return (kind == kJobShare || kind == kJobShareStay) ? 2 : (kind == kJobClass1 ? 1 : 0); }
 __host__ __device__ constexpr int stageBoxW(int /*k*/, int cls) { return cls == 2 ? 192 : (cls == 0 ? 208 : 240); }
-__host__ __device__ constexpr int stageBoxH(int k, int cls) {  // multiples of kBoxChunkRows
+__host__ __device__ constexpr int stageBoxH(int k, int cls) {
   return k == 8 ? (cls == 2 ? 80 : (cls == 0 ? 72 : 128)) : (cls == 2 ? 72 : (cls == 0 ? 64 : 96));
+}
+// rows of variant v of a class's box (v = 0: the whole stage buffer): share H, H - 8, H - 16; class 0 H, H - 16, H - 24
+// (the best three heights for the cfg2 plan, whose tiles need 40 / 48 / 56 / 64 rows in 3744 / 1852 / 1084 / 848 jobs
+// and whose share jobs 56 / 64 / 72 in 624 / 2644 / 1120); class 1 has the whole box only
+__host__ __device__ constexpr int boxVariantRows(int k, int cls, int v) {
+  return cls == 1 || v == 0 ? stageBoxH(k, cls) : (cls == 2 ? stageBoxH(k, cls) - 8 * v : stageBoxH(k, cls) - 8 - 8 * v);
+}
+// the lowest variant that holds `rows` rows
+__host__ __device__ constexpr int boxVariantFor(int k, int cls, int rows) {
+  int v = 0;
+  while (v + 1 < kBoxVariants && cls != 1 && boxVariantRows(k, cls, v + 1) >= rows) ++v;
+  return v;
 }
 // Stages of a group's ring (a stage = one box + one record buffer).  Three fit beside the cubic tables if the boxes lose
 // a few rows, but measured slower (64.9 vs 58.1 us per cfg2 frame): they leave the SM only ~3 KB of L1 for the general

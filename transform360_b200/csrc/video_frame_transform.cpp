@@ -138,14 +138,15 @@ EncodeTiledFn tensorMapEncoder() {
   return fn;
 }
 
-// Describes a pitch-linear 8-bit plane to the TMA unit with the staging box of class `cls` of kernel size k.
-bool encodePlaneMap(CUtensorMap* map, const uint8_t* base, int w, int h, int pitch, int k, int cls) {
+// Describes a pitch-linear 8-bit plane to the TMA unit with variant `variant` of the staging box of class `cls` of kernel
+// size k (kernels.cuh: boxVariantRows).
+bool encodePlaneMap(CUtensorMap* map, const uint8_t* base, int w, int h, int pitch, int k, int cls, int variant) {
   EncodeTiledFn enc = tensorMapEncoder();
   if (!enc) return false;
   if ((reinterpret_cast<uintptr_t>(base) & 15) || (pitch & 15)) return false;
   const cuuint64_t dims[2] = {static_cast<cuuint64_t>(w), static_cast<cuuint64_t>(h)};
   const cuuint64_t strides[1] = {static_cast<cuuint64_t>(pitch)};
-  const cuuint32_t box[2] = {static_cast<cuuint32_t>(t360::stageBoxW(k, cls)), static_cast<cuuint32_t>(t360::kBoxChunkRows)};  // one row chunk of the class's box
+  const cuuint32_t box[2] = {static_cast<cuuint32_t>(t360::stageBoxW(k, cls)), static_cast<cuuint32_t>(t360::boxVariantRows(k, cls, variant))};
   const cuuint32_t elem[2] = {1, 1};
   return enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<uint8_t*>(base), dims, strides, box, elem,
              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -156,7 +157,18 @@ bool encodePlaneMap(CUtensorMap* map, const uint8_t* base, int w, int h, int pit
 // luma plane on the caller's stream and the two chroma planes on their own lanes.
 constexpr int kPlaneLanes = 3;
 static_assert(kPlaneLanes == t360::kMaxFramePlanes, "the frame kernel takes one PlaneView per lane");
+// The tensor maps of one source plane (every box class and variant): encoding one takes the driver about a
+// microsecond, a frame needs 21, and callers come back with the same few planes (a decoder's surface pool, the
+// library's own low-pass plane), so every lane remembers the last few.
+struct PlaneMaps {
+  const uint8_t* base = nullptr;
+  int w = 0, h = 0, pitch = 0, k = 0;
+  CUtensorMap maps[t360::kNumBoxClasses][t360::kBoxVariants];
+};
 struct PlaneLane {
+  static constexpr int kMapCache = 8;
+  PlaneMaps mapCache[kMapCache];
+  int mapCacheNext = 0;
   cudaStream_t main = nullptr;                       // chroma lanes only (lane 0 runs on the caller's stream)
   cudaEvent_t done = nullptr;                        // recorded when this lane's plane has been enqueued completely
   DeviceBuffer<uint8_t> blurred;                     // low-pass output of this plane
@@ -169,7 +181,7 @@ struct GatherWork {
   const DevicePlan* plan = nullptr;
   t360::PlaneView view{};
   bool staged = false;                       // TMA-describable: may run in the persistent (per-plane / per-frame) kernel
-  CUtensorMap maps[t360::kNumBoxClasses];
+  CUtensorMap maps[t360::kNumBoxClasses][t360::kBoxVariants];
   uint8_t* finalOut = nullptr;               // where the area resize (if any) delivers
   int finalPitch = 0, finalW = 0, finalH = 0, imagePlane = 0;
   const void* resizeTables = nullptr;
@@ -230,6 +242,7 @@ class VideoFrameTransform {
     if (const char* m = std::getenv("T360B200_PIPELINE_CHUNKS")) pipelineChunks_ = std::atoi(m);       // tuning
     if (const char* m = std::getenv("T360B200_PIPELINE_BLOCKS")) pipelineBlocks_ = std::atoi(m);
     if (const char* m = std::getenv("T360B200_PIPELINE_IN_STREAMS")) pipelineInStreams_ = std::atoi(m);
+    if (const char* m = std::getenv("T360B200_PIPELINE_TAPER")) pipelineTaper_ = std::atoi(m) != 0;
   }
   void setPinHostPlanes(bool on) { pinHostPlanes_ = on; }
 
@@ -364,9 +377,19 @@ class VideoFrameTransform {
     w.chunks = chunks;
     w.plan = &plan;
     w.generation = planGeneration_;
-    const int rowsPer = ((plan.inH + chunks - 1) / chunks + 7) & ~7;
+    // Row bands: what the call still has to do when the last band has landed -- the gather wave that needs it and the
+    // copy back of whatever that wave completes -- runs with the inbound link idle, so the last bands are short: 1/16,
+    // 1/32 and 1/32 of the plane after equal bands over the first 7/8 (T360B200_PIPELINE_TAPER=0: equal bands).
     w.chunkRowEnd.assign(chunks, plan.inH);
-    for (int c = 0; c < chunks; ++c) w.chunkRowEnd[c] = std::min(plan.inH, (c + 1) * rowsPer);
+    const int tail = pipelineTaper_ && chunks >= 5 ? 3 : 0;
+    const int bodyRows = tail ? (plan.inH - plan.inH / 8) & ~7 : plan.inH;
+    const int rowsPer = ((bodyRows + (chunks - tail) - 1) / (chunks - tail) + 7) & ~7;
+    for (int c = 0; c < chunks - tail; ++c) w.chunkRowEnd[c] = std::min(bodyRows, (c + 1) * rowsPer);
+    if (tail) {
+      w.chunkRowEnd[chunks - 3] = (bodyRows + (plan.inH - bodyRows) / 2) & ~7;
+      w.chunkRowEnd[chunks - 2] = (bodyRows + (plan.inH - bodyRows) * 3 / 4) & ~7;
+      w.chunkRowEnd[chunks - 1] = plan.inH;
+    }
     auto waveOf = [&](int needRows) {
       int c = 0;
       while (c + 1 < chunks && w.chunkRowEnd[c] < needRows) ++c;
@@ -441,8 +464,10 @@ class VideoFrameTransform {
   bool transformHostPlanePipelined(const DevicePlan& plan, uint8_t* in, uint8_t* out, int inW, int inH, int inPitch, int outW, int outH,
                                    int outPitch, int planIndex, int imagePlaneIndex) {
     const long long bytes = static_cast<long long>(inW) * inH;
+    // equal bands of about 3 MB (at most six) + the three short ones at the end
     const int chunks = pipelineChunks_ > 1 ? std::min(pipelineChunks_, 32)
-                                           : static_cast<int>(std::min<long long>(8, std::max<long long>(2, bytes / (3ll << 20))));
+                       : pipelineTaper_  ? static_cast<int>(std::min<long long>(6, std::max<long long>(2, bytes / (3ll << 20)))) + 3
+                                         : static_cast<int>(std::min<long long>(8, std::max<long long>(2, bytes / (3ll << 20))));
     WavePlan& w = wavePlanFor(plan, planIndex, chunks);
     if (!copyIn_) {
       CU(cudaStreamCreateWithFlags(&copyIn_, cudaStreamNonBlocking));
@@ -1109,6 +1134,30 @@ class VideoFrameTransform {
     }
   }
 
+  // the tensor maps of a source plane, from the lane's cache or freshly encoded (false: not TMA-describable)
+  static bool planeMaps(PlaneLane& lane, const uint8_t* src, int w, int h, int pitch, int k,
+                        CUtensorMap (&out)[t360::kNumBoxClasses][t360::kBoxVariants]) {
+    for (const PlaneMaps& e : lane.mapCache)
+      if (e.base == src && e.w == w && e.h == h && e.pitch == pitch && e.k == k) {
+        std::memcpy(out, e.maps, sizeof(e.maps));
+        return true;
+      }
+    PlaneMaps fresh;
+    for (int c = 0; c < t360::kNumBoxClasses; ++c)
+      for (int v = 0; v < t360::kBoxVariants; ++v) {
+        if (v > 0 && t360::boxVariantRows(k, c, v) == t360::boxVariantRows(k, c, 0)) {
+          fresh.maps[c][v] = fresh.maps[c][0];  // (class 1 has one height)
+          continue;
+        }
+        if (!encodePlaneMap(&fresh.maps[c][v], src, w, h, pitch, k, c, v)) return false;
+      }
+    fresh.base = src; fresh.w = w; fresh.h = h; fresh.pitch = pitch; fresh.k = k;
+    lane.mapCache[lane.mapCacheNext] = fresh;
+    lane.mapCacheNext = (lane.mapCacheNext + 1) % PlaneLane::kMapCache;
+    std::memcpy(out, fresh.maps, sizeof(fresh.maps));
+    return true;
+  }
+
   // reference transformPlane (cpp:707-794): [low-pass] -> gather [-> area resize].  Device pointers, asynchronous.
   bool enqueue(const DevicePlan& plan, const uint8_t* dIn, uint8_t* dOut, int inW, int inH, int inPitch, int outW,
                int outH, int outPitch, cudaStream_t s, int imagePlaneIndex, PlaneLane& lane) {
@@ -1161,8 +1210,7 @@ class VideoFrameTransform {
     // staged tiles need the plane the plan was made for (their windows were proven in-bounds for it) and a
     // TMA-describable layout (16-byte aligned base and pitch); otherwise every tile takes the general kernel
     w.staged = plan.totalStaged() > 0 && !plan.transparent && inW == plan.inW && inH == plan.inH;
-    for (int c = 0; c < t360::kNumBoxClasses && w.staged; ++c)
-      w.staged = encodePlaneMap(&w.maps[c], src, inW, inH, srcPitch, plan.kernelSize, c);
+    if (w.staged) w.staged = planeMaps(lane, src, inW, inH, srcPitch, plan.kernelSize, w.maps);
     return true;
   }
 
@@ -1281,10 +1329,10 @@ class VideoFrameTransform {
     listLock.unlock();
     armScheduler(slot.frameClaim, s);
     t360::FrameGatherParams fp{};
-    CUtensorMap maps[kPlaneLanes][t360::kNumBoxClasses];
+    CUtensorMap maps[kPlaneLanes][t360::kNumBoxClasses][t360::kBoxVariants];
     for (int p = 0; p < numPlanes; ++p) {
       fp.plane[p] = work[p].view;
-      for (int c = 0; c < t360::kNumBoxClasses; ++c) maps[p][c] = work[p].maps[c];
+      std::memcpy(maps[p], work[p].maps, sizeof(work[p].maps));
     }
     fp.weightImage = reinterpret_cast<const uint4*>(weightImages_[work[0].plan->kernelSize].ptr);
     fp.kernelSize = work[0].plan->kernelSize;
@@ -1328,6 +1376,7 @@ class VideoFrameTransform {
   long long pipelineMinBytes_ = 6ll << 20;
   int pipelineChunks_ = 0, pipelineBlocks_ = 0;  // 0: automatic
   int pipelineInStreams_ = 1;
+  bool pipelineTaper_ = true;
   // The streamed call is ~100 runtime calls (chunk copies, events, wave launches, rectangle copies); issued one by one
   // the host thread becomes the bottleneck (measured: no faster than the plain path).  For page-locked caller planes the
   // whole sequence is captured once per (plan, buffers) into a CUDA graph and replayed with one launch.

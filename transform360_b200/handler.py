@@ -283,7 +283,7 @@ class HostPlan:
     def gather_plan(self):
         """Jobs and record layout the persistent gather kernel works from (T360B200_hostPlanGather).  Returns a dict:
         tiles_per_row, tile_rows, tile_h (grid of the full records), counts {class0, class1, seam, general, share},
-        jobs int32[n][4] = {outX, outY | kind << 24, boxX | boxY << 16 | (row chunks - 1), recordOffset / 16} (None when the plan is not
+        jobs int32[n][4] = {outX, outY | kind << 24, boxX | boxY << 16 | box variant, recordOffset / 16} (None when the plan is not
         staged), records int32[tiles][tile_h][32][2] (full records), compact uint32[] (compact records)."""
         info = (C.c_int * 10)()
         jobs, recs, comp = C.c_void_p(), C.c_void_p(), C.c_void_p()
