@@ -242,7 +242,6 @@ class VideoFrameTransform {
     if (const char* m = std::getenv("T360B200_PIPELINE_CHUNKS")) pipelineChunks_ = std::atoi(m);       // tuning
     if (const char* m = std::getenv("T360B200_PIPELINE_BLOCKS")) pipelineBlocks_ = std::atoi(m);
     if (const char* m = std::getenv("T360B200_PIPELINE_IN_STREAMS")) pipelineInStreams_ = std::atoi(m);
-    if (const char* m = std::getenv("T360B200_PIPELINE_TAPER")) pipelineTaper_ = std::atoi(m) != 0;
   }
   void setPinHostPlanes(bool on) { pinHostPlanes_ = on; }
 
@@ -377,19 +376,9 @@ class VideoFrameTransform {
     w.chunks = chunks;
     w.plan = &plan;
     w.generation = planGeneration_;
-    // Row bands: what the call still has to do when the last band has landed -- the gather wave that needs it and the
-    // copy back of whatever that wave completes -- runs with the inbound link idle, so the last bands are short: 1/16,
-    // 1/32 and 1/32 of the plane after equal bands over the first 7/8 (T360B200_PIPELINE_TAPER=0: equal bands).
+    const int rowsPer = ((plan.inH + chunks - 1) / chunks + 7) & ~7;
     w.chunkRowEnd.assign(chunks, plan.inH);
-    const int tail = pipelineTaper_ && chunks >= 5 ? 3 : 0;
-    const int bodyRows = tail ? (plan.inH - plan.inH / 8) & ~7 : plan.inH;
-    const int rowsPer = ((bodyRows + (chunks - tail) - 1) / (chunks - tail) + 7) & ~7;
-    for (int c = 0; c < chunks - tail; ++c) w.chunkRowEnd[c] = std::min(bodyRows, (c + 1) * rowsPer);
-    if (tail) {
-      w.chunkRowEnd[chunks - 3] = (bodyRows + (plan.inH - bodyRows) / 2) & ~7;
-      w.chunkRowEnd[chunks - 2] = (bodyRows + (plan.inH - bodyRows) * 3 / 4) & ~7;
-      w.chunkRowEnd[chunks - 1] = plan.inH;
-    }
+    for (int c = 0; c < chunks; ++c) w.chunkRowEnd[c] = std::min(plan.inH, (c + 1) * rowsPer);
     auto waveOf = [&](int needRows) {
       int c = 0;
       while (c + 1 < chunks && w.chunkRowEnd[c] < needRows) ++c;
@@ -464,10 +453,8 @@ class VideoFrameTransform {
   bool transformHostPlanePipelined(const DevicePlan& plan, uint8_t* in, uint8_t* out, int inW, int inH, int inPitch, int outW, int outH,
                                    int outPitch, int planIndex, int imagePlaneIndex) {
     const long long bytes = static_cast<long long>(inW) * inH;
-    // equal bands of about 3 MB (at most six) + the three short ones at the end
     const int chunks = pipelineChunks_ > 1 ? std::min(pipelineChunks_, 32)
-                       : pipelineTaper_  ? static_cast<int>(std::min<long long>(6, std::max<long long>(2, bytes / (3ll << 20)))) + 3
-                                         : static_cast<int>(std::min<long long>(8, std::max<long long>(2, bytes / (3ll << 20))));
+                                           : static_cast<int>(std::min<long long>(8, std::max<long long>(2, bytes / (3ll << 20))));
     WavePlan& w = wavePlanFor(plan, planIndex, chunks);
     if (!copyIn_) {
       CU(cudaStreamCreateWithFlags(&copyIn_, cudaStreamNonBlocking));
@@ -1376,7 +1363,6 @@ class VideoFrameTransform {
   long long pipelineMinBytes_ = 6ll << 20;
   int pipelineChunks_ = 0, pipelineBlocks_ = 0;  // 0: automatic
   int pipelineInStreams_ = 1;
-  bool pipelineTaper_ = true;
   // The streamed call is ~100 runtime calls (chunk copies, events, wave launches, rectangle copies); issued one by one
   // the host thread becomes the bottleneck (measured: no faster than the plain path).  For page-locked caller planes the
   // whole sequence is captured once per (plan, buffers) into a CUDA graph and replayed with one launch.
