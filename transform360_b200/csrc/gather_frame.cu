@@ -402,22 +402,14 @@ gatherFrameKernel(const __grid_constant__ FrameGatherParams p, StagedParams jobs
     }
     // Jobs are claimed kClaimBatch at a time: the first two batches of a producer are static, every further one comes
     // from the global counter.  Lane i holds the header of job i of the batch.  The claim runs two batches ahead and the
-    // header loads one, so neither the atomic nor the loads are waited for, and the records and source window of a
-    // batch's jobs are requested into L2 a batch ahead of the copies into shared memory.
+    // header loads one, so neither the atomic nor the loads are waited for.  (Asking L2 for a job's records and source
+    // box a job ahead with cp.async.bulk.prefetch paid while a job's box was the whole stage buffer; with the boxes cut
+    // to the rows a job needs the copies are not waited for either, and the prefetches cost 1.3 % of the frame.)
     const int producer = blockIdx.x * GROUPS + g, dynamicBase = gridDim.x * GROUPS * 2 * kClaimBatch;
     auto loadBatch = [&](int base) {
       int4 h = make_int4(0, kJobExit << kJobKindShift, 0, 0);
       if (lane < kClaimBatch && base + lane < jobs.numTiles) h = __ldg(reinterpret_cast<const int4*>(jobs.tiles) + base + lane);
       return h;
-    };
-    auto prefetchBatch = [&](const int4& h) {
-      const int kind = (h.y >> kJobKindShift) & kJobKindMask;
-      if (kind != kJobShare && kind != kJobShareStay && kind != kJobClass0 && kind != kJobClass1 && kind != kJobSeam) return;
-      const int pl = h.y >> kJobPlaneShift;
-      const uint32_t recBytes = boxClassOf(kind) == 2 ? shareJobRecordBytes(K) : tileJobRecordBytes(h.x);
-      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(planes[pl].records + (unsigned)h.w), "r"(recBytes) : "memory");
-      asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];"
-                   ::"l"(reinterpret_cast<uint64_t>(&maps.map[pl][boxClassOf(kind)][jobBoxVariant(h.z)])), "r"(jobBoxX(h.z)), "r"(jobBoxY(h.z)) : "memory");
     };
     // (the first TWO batches are static, so that the first job is not held up by the round trip of an atomic)
     int4 batch = loadBatch(producer * 2 * kClaimBatch);
@@ -425,8 +417,6 @@ gatherFrameKernel(const __grid_constant__ FrameGatherParams p, StagedParams jobs
     asm volatile("griddepcontrol.wait;" ::: "memory");  // earlier kernels on the stream are complete and visible from here on
     int claimed = 0;  // lane 0: the claim for the batch after next, issued one batch before it is looked at
     if (lane == 0) claimed = atomicAdd(jobs.claimCounter, kClaimBatch);
-    prefetchBatch(batch);
-    prefetchBatch(batchNext);
     unsigned char* groupBase = smem + L::kWeights + g * L::kGroupBytes;
     uint64_t* full = barBase + g * 2 * S;
     uint64_t* empty = full + S;
@@ -443,7 +433,6 @@ gatherFrameKernel(const __grid_constant__ FrameGatherParams p, StagedParams jobs
         pos = 0;
         batchNext = loadBatch(dynamicBase + __shfl_sync(0xffffffffu, claimed, 0));
         if (lane == 0) claimed = atomicAdd(jobs.claimCounter, kClaimBatch);
-        prefetchBatch(batchNext);
       }
       int4 h;
       h.x = __shfl_sync(0xffffffffu, batch.x, pos); h.y = __shfl_sync(0xffffffffu, batch.y, pos);
