@@ -37,9 +37,10 @@ inline void jobOutputRect(const GatherJob& job, int k, int rect[4]) {
 }
 
 // Launch order of a job list that is sorted by kind (general, class 1, share, class 0): the general jobs -- latency-bound
-// reads through L1 that leave the shared-memory pipe idle -- are spread evenly over the first three quarters of the
-// staged jobs, so that they run beside them instead of all at once at the start of the launch.
+// reads through L1 that leave the shared-memory pipe idle -- are spread evenly over the first half of the staged jobs,
+// so that they run beside them instead of all at once at the start of the launch.
 void spreadGeneralJobs(std::vector<GatherJob>& jobs);
+
 
 // Deals n <= 32 pixels of one warp step to lanes (and table copies) so that the lanes one shared-memory pass serves
 // together ask for different bank groups of the weight table.  slot[i] = weightSlotOf(k, phase of pixel i).
