@@ -148,13 +148,9 @@ bool encodePlaneMap(CUtensorMap* map, const uint8_t* base, int w, int h, int pit
   const cuuint64_t strides[1] = {static_cast<cuuint64_t>(pitch)};
   const cuuint32_t box[2] = {static_cast<cuuint32_t>(t360::stageBoxW(k, cls)), static_cast<cuuint32_t>(t360::boxVariantRows(k, cls, variant))};
   const cuuint32_t elem[2] = {1, 1};
-  static const CUtensorMapL2promotion promotion = [] {  // T360B200_TMA_PROMOTION = 0 (none), 64, 128 (default), 256: tuning aid
-    const char* e = std::getenv("T360B200_TMA_PROMOTION");
-    const int v = e ? std::atoi(e) : 128;
-    return v == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : (v == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B : (v == 256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B));
-  }();
   return enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<uint8_t*>(base), dims, strides, box, elem,
-             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, promotion, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,  // (none / 64 / 256 B: no difference)
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 // Everything one image plane needs to be in flight independently of the others: the frame entry point runs the
