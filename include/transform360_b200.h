@@ -32,13 +32,17 @@ const int32_t* T360B200_hostPlanSamples(const T360HostPlan* plan);
 /* The gather plan of the host plan (no GPU needed): how the output plane is cut into jobs for the persistent gather
  * kernel and how the sampling records are laid out for it (formats: csrc/kernels.cuh).  info = {tilesPerRow, tileRows,
  * tileH of the full records, numJobs, class-0 jobs, class-1 jobs, seam jobs, general jobs, share jobs, words of compact
- * records}; *jobs: numJobs x 4 ints {outX, outY | kind << 24, boxX | boxY << 16, recordOffset (16-byte units)} in launch
+ * records}; *jobs: numJobs x 4 ints {outX, outY | kind << 24, boxX | boxY << 16 | box variant, recordOffset (16-byte units)} in launch
  * order (NULL when the plan is not staged: nearest neighbour, barrel layouts); *records: the full records,
  * tilesPerRow * tileRows * tileH * 32 pairs {col0 | column << 27, row0 << 10 | phase}, tile-major; *compact: the compact
  * records of the staged jobs (32-bit words).  Returns 1 on success.  The pointers stay valid until
  * T360B200_hostPlanDestroy. */
 int T360B200_hostPlanGather(T360HostPlan* plan, int info[10], const int32_t** jobs, const int32_t** records,
                             const uint32_t** compact);
+/* How the host deals the n <= 32 pixels of one warp step to lanes and copies of the weight table (csrc/gather_plan.h:
+ * dealLanes): phases[i] = (fracY32 << 5) | fracX32 of pixel i; laneOf[i] / copyOf[i] receive its lane and table copy.
+ * Returns the modelled shared-memory wavefronts of one 128-bit weight load of the warp (0 when n < 32: identity deal). */
+int T360B200_dealLanes(int interpolationAlg, int n, const int32_t* phases, int32_t* laneOf, int32_t* copyOf);
 /* The frame kernel's shared-memory image of the interpolation table (csrc/kernels.cuh: "Weight tables in shared
  * memory"); returns its size in bytes (0 if unsupported). */
 int T360B200_weightImage(int interpolationAlg, const uint8_t** image);

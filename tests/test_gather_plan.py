@@ -311,3 +311,39 @@ def test_gather_plan_invariants_on_random_contexts():
         finally:
             SMALL.pop("__random", None)
     assert checked >= 25
+
+
+def test_lane_dealing_is_a_valid_and_exact_deal():
+    """T360B200_dealLanes (csrc/gather_plan.cpp: GroupMatcher + PassDealer) on random and on adversarial warp steps: every
+    pixel gets its own lane and a copy that exists; the wavefronts it reports are what the bank model counts for the deal
+    (or fewer, when two pixels share a slot: one broadcast read); never worse than leaving the pixels where they are; and
+    the floor of 4 whenever the bank groups can be filled evenly."""
+    rng = np.random.default_rng(7)
+
+    def model(k, phases, lane, copy):
+        img_field = np.empty(32, np.int64)
+        for ph, ln, cp in zip(phases, lane, copy):
+            slot = (int(ph) & ~31) | ((int(ph) & 1) << 4) | ((int(ph) & 31) >> 1)  # kernels.cuh weightSlotOf
+            pos = (slot & ~7) | ((slot + int(cp)) & 7) if cp else slot               # weightSlotInCopy
+            img_field[ln] = (pos << 4) | (int(cp) << 14)
+        return _weight_load_wavefronts(img_field)
+
+    cases = [rng.integers(0, 1024, 32) for _ in range(300)]
+    cases += [np.full(32, 37), np.arange(32) * 32 + 5, np.arange(32), (np.arange(32) % 4) * 2 + 64]  # one slot; one fracX; one fracY; four bank groups
+    for smooth in range(100):  # an 8 x 4 patch of a smooth map: fracX and fracY drift slowly
+        fx0, fy0, dx, dy = rng.integers(0, 32), rng.integers(0, 32), rng.uniform(-3, 3, 2), rng.uniform(-3, 3, 2)
+        xs, ys = np.meshgrid(np.arange(8), np.arange(4))
+        cases.append((((fy0 + xs * dy[0] + ys * dy[1]).astype(int) & 31) << 5 | ((fx0 + xs * dx[0] + ys * dx[1]).astype(int) & 31)).ravel())
+    for phases in cases:
+        w, lane, copy = t360.deal_lanes(t360.CUBIC, phases)
+        assert sorted(lane.tolist()) == list(range(32)) and set(copy.tolist()) <= {0, 1}
+        got = model(4, phases, lane, copy)
+        assert 4 <= got <= w, (got, w)
+        assert w <= model(4, phases, np.arange(32), np.zeros(32, int)) or len(set(phases.tolist())) < 32
+        groups = np.bincount((phases.astype(int) & 31) >> 1 & 7, minlength=8)
+        if (groups == 4).all() and len(set(phases.tolist())) == 32:
+            assert w == 4
+    w, lane, copy = t360.deal_lanes(t360.CUBIC, np.arange(20))  # fewer than 32 pixels: identity
+    assert w == 0 and (lane == np.arange(20)).all() and (copy == 0).all()
+    w, lane, copy = t360.deal_lanes(t360.LANCZOS4, rng.integers(0, 1024, 32))  # one copy: lanes only
+    assert sorted(lane.tolist()) == list(range(32)) and (copy == 0).all()

@@ -7,4 +7,4 @@ from .handler import (CUBIC, LANCZOS4, LAYOUT_BARREL, LAYOUT_BARREL_SPLIT, LAYOU
                       LAYOUT_CUBEMAP_32, LAYOUT_EAC_32, LAYOUT_EQUIRECT, LAYOUT_FLAT_FIXED, LINEAR, NEAREST,
                       STEREO_FORMAT_GUESS, STEREO_FORMAT_LR, STEREO_FORMAT_MONO, STEREO_FORMAT_TB,
                       FrameTransformContext, HostPlan, VideoFrameTransform, device_count, kernel_launch_count, load,
-                      make_context, remap_table, weight_image)
+                      make_context, remap_table, weight_image, deal_lanes)

@@ -1483,6 +1483,17 @@ T360_API int T360B200_hostPlanSegment(const T360HostPlan* plan, int i, int rect[
   return 1;
 }
 T360_API int T360B200_remapTable(int interpolationAlg, const int16_t** table) { return t360::remapTable(interpolationAlg, table); }
+T360_API int T360B200_dealLanes(int interpolationAlg, int n, const int32_t* phases, int32_t* laneOf, int32_t* copyOf) {
+  const int16_t* table = nullptr;
+  const int k = t360::remapTable(interpolationAlg, &table);
+  if (k < 2 || n < 0 || n > 32 || !phases || !laneOf || !copyOf) return -1;
+  int slot[32], lane[32], copy[32];
+  for (int i = 0; i < n; ++i) slot[i] = t360::weightSlotOf(k, phases[i] & 1023);
+  const int wavefronts = t360::dealLanes(k, t360::weightCopies(k), n, slot, lane, copy);
+  for (int i = 0; i < n; ++i) { laneOf[i] = lane[i]; copyOf[i] = copy[i]; }
+  return wavefronts;
+}
+
 T360_API int T360B200_weightImage(int interpolationAlg, const uint8_t** image) {
   static std::mutex mu;
   static std::map<int, std::vector<uint8_t>> images;

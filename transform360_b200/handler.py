@@ -134,7 +134,7 @@ EXPORTED_SYMBOLS = [
     "VideoFrameTransform_new", "VideoFrameTransform_delete", "VideoFrameTransform_generateMapForPlane",
     "VideoFrameTransform_transformFramePlane", "T360B200_hostPlanCreate", "T360B200_hostPlanDestroy",
     "T360B200_hostPlanInfo", "T360B200_hostPlanMap", "T360B200_hostPlanSamples", "T360B200_hostPlanSegment",
-    "T360B200_hostPlanGather", "T360B200_weightImage",
+    "T360B200_hostPlanGather", "T360B200_weightImage", "T360B200_dealLanes",
     "T360B200_remapTable", "T360B200_transformFramePlaneAsync", "T360B200_transformFrameAsync",
     "T360B200_lowPassPlaneAsync",
     "T360B200_setPinHostPlanes", "T360B200_debugTrace", "T360B200_debugTraceRead", "T360B200_synchronize", "T360B200_stream", "T360B200_kernelLaunchCount", "T360B200_planDeviceBytes",
@@ -319,6 +319,19 @@ def remap_table(interpolation_alg: int) -> np.ndarray | None:
     if k < 2:
         return None
     return np.frombuffer((C.c_int16 * (1024 * k * k)).from_address(p.value), np.int16).reshape(1024, k, k).copy()
+
+
+def deal_lanes(interpolation_alg: int, phases) -> tuple[int, np.ndarray, np.ndarray]:
+    """(modelled wavefronts of a weight load, lane of every pixel, table copy of every pixel) for one warp step."""
+    L = load()
+    ph = np.ascontiguousarray(phases, np.int32)
+    lane, copy = np.zeros(ph.size, np.int32), np.zeros(ph.size, np.int32)
+    L.T360B200_dealLanes.restype = C.c_int
+    L.T360B200_dealLanes.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    w = L.T360B200_dealLanes(interpolation_alg, ph.size, ph.ctypes.data, lane.ctypes.data, copy.ctypes.data)
+    if w < 0:
+        raise ValueError("T360B200_dealLanes refused the arguments")
+    return int(w), lane, copy
 
 
 def weight_image(interpolation_alg: int) -> np.ndarray | None:
