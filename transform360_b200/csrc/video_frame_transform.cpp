@@ -166,7 +166,7 @@ struct PlaneMaps {
   CUtensorMap maps[t360::kNumBoxClasses][t360::kBoxVariants];
 };
 struct PlaneLane {
-  static constexpr int kMapCache = 8;
+  static constexpr int kMapCache = 32;  // (a decoder's surface pool holds 10 - 20 frames)
   PlaneMaps mapCache[kMapCache];
   int mapCacheNext = 0;
   cudaStream_t main = nullptr;                       // chroma lanes only (lane 0 runs on the caller's stream)
